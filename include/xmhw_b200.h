@@ -1,0 +1,141 @@
+/* xmhw_b200 -- C ABI of the B200 (sm_100a) marine-heatwave hot path.
+ *
+ * Drop-in boundary for the two per-cell loops of coecms/xmhw v0.9.3 (the
+ * reference has no FFI of its own; these entry points are what a ctypes binding
+ * inside the reference would call instead of its Python loops -- see
+ * INTEGRATION.md for the stub):
+ *
+ *   xmhw/xmhw.py:184-197   for c in ts.cell: calc_clim(...)      + dask.compute
+ *   xmhw/xmhw.py:440-454   for c in ts.cell: define_events(...)  + dask.compute
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never
+ *     allocates or frees and keeps no global state (re-entrant);
+ *   - all work is enqueued on the caller's cudaStream_t (`stream`, may be 0); no
+ *     call synchronises;
+ *   - return value: 0 = ok, negative = argument error (XMHW_E_*), positive =
+ *     cudaError_t of the failed launch; no C++ exception crosses the boundary;
+ *   - layouts are the reference's own: the series is (time, cell) row-major
+ *     float32 exactly as xarray holds (time, lat, lon) after
+ *     `stack(cell=sorted(dims))` (identify.py:520), climatologies are (doy, cell)
+ *     row-major float64 (the reference's `thresh`/`seas` variables, xmhw.py:204-216).
+ *     `cell` runs over the WHOLE grid, land included: land cells hold NaN
+ *     (the reference drops them, identify.py:522-525; the host wrapper does the
+ *     same from `nvalid`);
+ *   - indices are 0-based positions along time like the reference's idxarr
+ *     (xmhw.py:417); doy values are 1-based labels (identify.py:67-76).
+ */
+#ifndef XMHW_B200_H
+#define XMHW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XMHW_E_ARG   (-1)   /* null pointer / non-positive size            */
+#define XMHW_E_PLAN  (-2)   /* inconsistent climatology plan               */
+#define XMHW_E_SMEM  (-3)   /* plan needs more shared memory than one SM has */
+
+#define XMHW_ABI_VERSION 1
+
+/* event table columns (struct-of-arrays, column c of event i at [c * cap + i]) */
+enum xmhw_event_i32 {
+  XMHW_EI_CELL = 0,        /* flat grid cell                                  */
+  XMHW_EI_INDEX_START,     /* features.py:116                                  */
+  XMHW_EI_INDEX_END,       /* features.py:117                                  */
+  XMHW_EI_INDEX_PEAK,      /* features.py:120,181                              */
+  XMHW_EI_DURATION,        /* features.py:189                                  */
+  XMHW_EI_CATEGORY,        /* features.py:147,188 (-1 = undefined)             */
+  XMHW_EI_DURATION_MODERATE, XMHW_EI_DURATION_STRONG,
+  XMHW_EI_DURATION_SEVERE, XMHW_EI_DURATION_EXTREME,   /* features.py:148-151  */
+  XMHW_EI_COUNT
+};
+enum xmhw_event_f64 {
+  XMHW_EF_INTENSITY_MAX = 0, XMHW_EF_INTENSITY_MEAN, XMHW_EF_INTENSITY_CUMULATIVE, XMHW_EF_INTENSITY_VAR,
+  XMHW_EF_SEVERITY_MAX, XMHW_EF_SEVERITY_MEAN, XMHW_EF_SEVERITY_CUMULATIVE, XMHW_EF_SEVERITY_VAR,
+  XMHW_EF_INTENSITY_MAX_RELTHRESH, XMHW_EF_INTENSITY_MEAN_RELTHRESH,
+  XMHW_EF_INTENSITY_CUMULATIVE_RELTHRESH, XMHW_EF_INTENSITY_VAR_RELTHRESH,
+  XMHW_EF_INTENSITY_MAX_ABS, XMHW_EF_INTENSITY_MEAN_ABS,      /* float32-rounded, features.py:68 */
+  XMHW_EF_INTENSITY_CUMULATIVE_ABS, XMHW_EF_INTENSITY_VAR_ABS,
+  XMHW_EF_RATE_ONSET, XMHW_EF_RATE_DECLINE,                   /* features.py:290-291 */
+  XMHW_EF_COUNT
+};
+
+/* Climatology sweep plan: which time rows form each sorted list, when lists
+ * enter / leave the +-windowHalfWidth window as the day-of-year advances, and
+ * numpy's linear-quantile index table.  Built on the host from the doy vector
+ * (xmhw_b200/plan.py); all arrays are device-resident int32 unless noted.     */
+typedef struct xmhw_clim_plan {
+  int32_t nsteps;               /* = ndoy                                       */
+  int32_t pool_rows;            /* shared-memory rows (128 B) per 32-cell warp  */
+  int32_t nmax;                 /* q tables have nmax + 1 entries               */
+  int32_t max_size;             /* largest list, <= 32                          */
+  const int32_t* inst_base;     /* [ninst]                                      */
+  const int32_t* inst_size;     /* [ninst]                                      */
+  const int32_t* inst_row_off;  /* [ninst]                                      */
+  const int32_t* rows;          /* time indices                                 */
+  const int32_t* leave_off;     /* [nsteps+1]                                   */
+  const int32_t* leave;
+  const int32_t* enter_off;     /* [nsteps+1]                                   */
+  const int32_t* enter;
+  const int32_t* use_off;       /* [nsteps+1]                                   */
+  const int32_t* use;
+  const int32_t* q_lo;          /* [nmax+1] floor((n-1) q)                      */
+  const double*  q_gamma;       /* [nmax+1] (n-1) q - floor                     */
+} xmhw_clim_plan;
+
+int xmhw_abi_version(void);
+const char* xmhw_strerror(int code);
+
+/* identify.py:184-270 window_roll + calculate_thresh + calculate_seas (before the
+ * Feb-29 rule and smoothing) for every grid cell.
+ * ts [T][ngrid] f32 -> thresh_raw, seas_raw [nsteps][ngrid] f64 (NaN = no sample). */
+int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan* plan,
+                        double* thresh_raw, double* seas_raw, void* stream);
+
+/* identify.py:137-151 feb29 (if feb29 != 0: doy 60 <- mean of doys 59,60,61) then
+ * identify.py:154-181 runavg (circular centred mean, odd smooth_width; <= 1 = off).
+ * raw, out [ndoy][ngrid] f64, out must not alias raw.                           */
+int xmhw_clim_finish_f64(const double* raw, double* out, int32_t ndoy, int64_t ngrid,
+                         int32_t feb29, int32_t smooth_width, void* stream);
+
+/* identify.py:367-372: bthresh = ts > thresh[doy] (strict, float64 compare, NaN -> false).
+ * doy_ptr [ndoy+1], doy_tidx [T]: CSR of time indices per doy label.
+ * mask [ceil(ngrid/32)][T] u32: bit l of word (g, t) = exceedance of cell 32 g + l at t.
+ * nvalid [ngrid] i32 (pre-zeroed): += number of non-NaN samples per cell
+ * (land_check, identify.py:522-525).                                            */
+int xmhw_exceed_mask_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy_ptr,
+                         const int32_t* doy_tidx, int32_t ndoy, const double* thresh,
+                         uint32_t* mask, int32_t* nvalid, void* stream);
+
+/* identify.py:415-479 mhw_filter + :273-325 join_gaps: events per cell.
+ * Phase 1 counts, caller scans, phase 2 fills rows CELL/INDEX_START/INDEX_END of ev_i32. */
+int xmhw_events_count(const uint32_t* mask, int64_t T, int64_t ngrid, int32_t min_duration,
+                      int32_t join_gaps, int32_t max_gap, int32_t* counts, void* stream);
+/* offsets [n+1] i64 exclusive prefix sum of counts [n]; scratch [n/1024 + 2] i64. */
+int xmhw_exclusive_scan_i32(const int32_t* counts, int64_t n, int64_t* offsets, int64_t* scratch,
+                            void* stream);
+int xmhw_events_fill(const uint32_t* mask, int64_t T, int64_t ngrid, int32_t min_duration,
+                     int32_t join_gaps, int32_t max_gap, const int64_t* offsets, int64_t cap,
+                     int32_t* ev_i32, void* stream);
+
+/* features.py:22-295 mhw_df + agg_df + properties + onset_decline for nev events.
+ * doy [T] i32 (1-based labels); thresh, seas [ndoy][ngrid] f64;
+ * ev_i32 [XMHW_EI_COUNT][cap], ev_f64 [XMHW_EF_COUNT][cap].                       */
+int xmhw_event_stats_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy,
+                         const double* thresh, const double* seas, int64_t nev, int64_t cap,
+                         int32_t* ev_i32, double* ev_f64, void* stream);
+
+/* Deterministic synthetic SST: seasonal cycle + AR(1) noise rounded to
+ * 0.01 degC, NaN on land; bit-identical to xmhw_b200/synth.py on the host.
+ * season [T + 366] f64 host-computed sine table, land [ngrid] u8 (1 = land).    */
+int xmhw_synth_sst_f32(float* ts, int64_t T, int64_t ngrid, int64_t cell0, const uint8_t* land,
+                       const double* season, uint64_t seed, double rho, double sigma,
+                       double noise_scale, uint32_t nan_per_million, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XMHW_B200_H */

@@ -1,0 +1,57 @@
+// TEST INFRASTRUCTURE ONLY -- single-lane host emulation of xmhw_b200/csrc/xmhw_lane.h.
+//
+// The build container has no GPU.  Every xmhw_b200 kernel maps one grid cell to one
+// lane and lanes never exchange data, so the per-lane device functions can be
+// compiled for the host (this file, g++) and driven one cell at a time to debug
+// the plan/selection/run-length/statistics logic before spending GPU time.
+// The xmhw_b200 package never loads this library; product calls go to the CUDA
+// library only (xmhw_b200/_cabi.py raises if it is missing).
+#include <vector>
+#include "../../xmhw_b200/csrc/xmhw_lane.h"
+
+using namespace xmhw;
+
+struct HostEnv { bool any(bool p) const { return p; } };
+
+extern "C" {
+
+int emul_clim_sweep(const float* ts, int64_t T, int64_t ngrid, const ClimPlan* plan, double* thr, double* seas) {
+  (void)T;
+  std::vector<uint32_t> pool((size_t)plan->pool_rows * 32);
+  HostEnv env;
+  for (int64_t cell = 0; cell < ngrid; ++cell) {
+    SweepState st; st.C = 0; st.n = 0; st.pivot = 0xffffffffu;
+    const int lane = (int)(cell & 31);
+    for (int s = 0; s < plan->nsteps; ++s) {
+      double a, b;
+      sweep_step(env, *plan, s, st, pool.data(), lane, ts + cell, ngrid, true, a, b);
+      thr[(int64_t)s * ngrid + cell] = a;
+      seas[(int64_t)s * ngrid + cell] = b;
+    }
+  }
+  return 0;
+}
+
+struct VecEmit { int32_t* s; int32_t* e; int n; void operator()(int a, int b) { s[n] = a; e[n] = b; ++n; } };
+
+// b: exceedance booleans [T]; returns number of events, fills starts/ends
+int emul_find_events(const uint8_t* b, int T, int min_dur, int join, int max_gap, int32_t* starts, int32_t* ends) {
+  RunFinder rf(min_dur, join, max_gap);
+  VecEmit em{starts, ends, 0};
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    uint32_t bits = 0;
+    for (int i = 0; i < 32 && t0 + i < T; ++i) bits |= (uint32_t)(b[t0 + i] != 0) << i;
+    rf.feed(bits, t0, em);
+  }
+  rf.finish(T, em);
+  return em.n;
+}
+
+void emul_event_stats(const float* col, const double* th, const double* se, const int32_t* doy, int64_t ngrid,
+                      int T, int s, int e, int32_t* oi, double* of) {
+  event_stats(col, th, se, doy, ngrid, T, s, e, oi, of, 1);
+}
+
+uint32_t emul_f32_key(float f) { return f32_key(f); }
+float emul_key_f32(uint32_t k) { return key_f32(k); }
+}

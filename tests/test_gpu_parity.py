@@ -1,0 +1,223 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs, against the committed golden fixtures, and size-independent
+properties at BASELINE sizes.  Integer outputs bit-exact; thresh bit-exact; seas and
+float statistics within max(1e-5 abs, 1 float32 ulp rel)."""
+import numpy as np
+import pytest
+
+from tests.util import assert_events_match, bit_equal
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def core():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xmhw_b200 import core as c
+    return c
+
+
+def _oracle():
+    from oracle import xmhw_oracle as O
+    return O
+
+
+def _float_fields():
+    from xmhw_b200._cabi import EF_FIELDS
+    return EF_FIELDS
+
+
+def _clim_check(core, ts_h, doy, ndoy, **kw):
+    O = _oracle()
+    ts = torch.from_numpy(ts_h).cuda()
+    th, se = core.threshold_arrays(ts, doy, ndoy, **kw)
+    okw = dict(pctile=kw.get("pctile", 90), windowHalfWidth=kw.get("windowHalfWidth", 5),
+               smoothPercentile=kw.get("smoothPercentile", True),
+               smoothPercentileWidth=kw.get("smoothPercentileWidth", 31), tstep=not kw.get("feb29", True))
+    oth, ose = O.threshold(ts_h, doy, ndoy, **okw)
+    th_h, se_h = th.cpu().numpy(), se.cpu().numpy()
+    assert bit_equal(th_h, oth), "thresh not bit-equal, max diff %g" % np.nanmax(np.abs(th_h - oth))
+    assert np.array_equal(np.isnan(se_h), np.isnan(ose))
+    assert np.nanmax(np.abs(se_h - ose), initial=0) <= 1e-9
+    return ts, th, se, th_h, se_h
+
+
+def test_synth_device_matches_host(core):
+    from xmhw_b200 import synth
+    time = synth.daily_time(2001, 2003)
+    land = synth.land_mask(6, 16).ravel()
+    sea = synth.season_table(time)
+    host = synth.synth_sst(len(time), 96, sea, land=land, cell0=1000, nan_ppm=3000)
+    dev = core.synth_sst_device(len(time), 96, sea, land=land, cell0=1000, nan_ppm=3000).cpu().numpy()
+    assert np.array_equal(host.view(np.int32), dev.view(np.int32))
+
+
+def test_oisst_cube_threshold_and_detect(core, oisst, clim_gold):
+    """BASELINE config 1 data (reference test cube, 8x4 grid with 20 land cells)."""
+    O = _oracle()
+    doy = O.add_doy(oisst["time"])
+    ts_h = np.ascontiguousarray(oisst["sst"].reshape(len(doy), -1))
+    ts, th, se, th_h, se_h = _clim_check(core, ts_h, doy, 366)
+    smooth, _ = clim_gold
+    for cell, n in ((1 * 4 + 2, "1"), (5 * 4 + 3, "2")):     # points [1,2] and [5,3] (test_xmhw.py:24-66)
+        assert np.abs(th_h[82:, cell] - smooth["thresh" + n][82:]).max() < 1e-6
+        assert np.abs(se_h[82:, cell] - smooth["seas" + n][82:]).max() < 1e-4
+    ev = core.detect_arrays(ts, doy, 366, th, se)
+    got = ev.to_numpy()
+    exp = O.detect(ts_h, doy, th_h, se_h)
+    assert_events_match(got, exp, _float_fields())
+    m = got["cell"] == 6      # survey anchor: 9 events at point [1,2]
+    assert list(zip(got["index_start"][m], got["index_end"][m], got["index_peak"][m])) == [
+        (1, 7, 5), (75, 81, 79), (99, 103, 101), (114, 121, 118), (138, 150, 146), (172, 184, 182),
+        (225, 229, 228), (613, 618, 615), (709, 714, 712)]
+    nv = ev.nvalid.cpu().numpy()
+    assert np.array_equal(nv > 0, ~np.isnan(ts_h).all(0))
+
+
+def test_nosmooth_and_raw(core, oisst):
+    O = _oracle()
+    doy = O.add_doy(oisst["time"])
+    ts_h = np.ascontiguousarray(oisst["sst"].reshape(len(doy), -1))
+    _clim_check(core, ts_h, doy, 366, smoothPercentile=False)
+    _clim_check(core, ts_h, doy, 366, smoothPercentile=False, feb29=False)
+    _clim_check(core, ts_h, doy, 366, smoothPercentileWidth=5, windowHalfWidth=2, pctile=75)
+
+
+@pytest.mark.parametrize("years,ncell,nan_ppm,pctile", [((1982, 2011), 100, 0, 90),
+                                                          ((1982, 2011), 70, 20000, 99),
+                                                          ((1982, 2021), 64, 0, 90)])
+def test_synth_daily(core, years, ncell, nan_ppm, pctile):
+    """30/40-year daily series incl. land, scattered NaNs, NaN blocks, ragged last warp."""
+    from xmhw_b200 import synth
+    O = _oracle()
+    time = synth.daily_time(*years)
+    doy = synth.doy366(time)
+    land = np.zeros(ncell, np.uint8)
+    land[[3, 40, 41]] = 1
+    ts_h = synth.synth_sst(len(time), ncell, synth.season_table(time), land=land, nan_ppm=nan_ppm)
+    if nan_ppm:
+        ts_h[100:400, 7] = np.nan          # long block
+        ts_h[5000:, 9] = np.nan            # series ends early
+        for y in range(10):                # a NaN block every winter
+            ts_h[365 * y + 20:365 * y + 100, 11] = np.nan
+    ts, th, se, th_h, se_h = _clim_check(core, ts_h, doy, 366, pctile=pctile)
+    ev = core.detect_arrays(ts, doy, 366, th, se)
+    exp = O.detect(ts_h, doy, th_h, se_h)
+    assert len(ev) > 50
+    assert_events_match(ev.to_numpy(), exp, _float_fields())
+
+
+def test_pentad_tstep(core):
+    """BASELINE config 4(ii): 73 steps/yr, windowHalfWidth=5, smoothPercentileWidth=5, maxGap=1."""
+    from xmhw_b200 import synth
+    O = _oracle()
+    doy = np.tile(np.arange(1, 74), 30)
+    ts_h = synth.synth_sst(len(doy), 48, synth.season_table(len(doy)))
+    ts, th, se, th_h, se_h = _clim_check(core, ts_h, doy, 73, smoothPercentileWidth=5, feb29=False)
+    ev = core.detect_arrays(ts, doy, 73, th, se, minDuration=3, maxGap=1)
+    exp = O.detect(ts_h, doy, th_h, se_h, 3, True, 1)
+    assert_events_match(ev.to_numpy(), exp, _float_fields())
+
+
+def test_detect_options(core):
+    from xmhw_b200 import synth
+    O = _oracle()
+    time = synth.daily_time(1990, 1999)
+    doy = synth.doy366(time)
+    ts_h = synth.synth_sst(len(time), 40, synth.season_table(time), nan_ppm=8000)
+    ts = torch.from_numpy(ts_h).cuda()
+    th, se = core.threshold_arrays(ts, doy, 366)
+    th_h, se_h = th.cpu().numpy(), se.cpu().numpy()
+    for minD, join, maxG in ((5, False, 2), (3, True, 2), (7, True, 4), (1, True, 0), (2, False, 0)):
+        ev = core.detect_arrays(ts, doy, 366, th, se, minDuration=minD, joinGaps=join, maxGap=maxG)
+        exp = O.detect(ts_h, doy, th_h, se_h, minD, join, maxG)
+        assert_events_match(ev.to_numpy(), exp, _float_fields())
+    with pytest.raises(ValueError):
+        core.detect_arrays(ts, doy, 366, th, se, minDuration=3, maxGap=3)
+
+
+def test_reference_event_tables(core, ref_cases):
+    """Event tables from the UNMODIFIED reference pandas code (tests/golden/ref_detect_cases.npz)."""
+    from tests.util import F32_FIELDS
+    nev = 0
+    for c in ref_cases:
+        T = len(c["ts"])
+        minD, join, maxG = (int(v) for v in c["par"])
+        doy = np.arange(1, T + 1)
+        ts = torch.from_numpy(c["ts"][:, None].copy()).cuda()
+        th = torch.from_numpy(c["th"][:, None].copy()).cuda()
+        se = torch.from_numpy(c["se"][:, None].copy()).cuda()
+        got = core.detect_arrays(ts, doy, T, th, se, minD, bool(join), maxG).to_numpy()
+        assert len(got["cell"]) == len(c["index_start"])
+        for f in ("index_start", "index_end", "index_peak", "duration", "category", "duration_moderate",
+                  "duration_strong", "duration_severe", "duration_extreme"):
+            assert np.array_equal(got[f], np.where(np.isnan(c[f]), -1, c[f]).astype(np.int64)), f
+        for f in _float_fields():
+            tol = 5e-6 if f in F32_FIELDS else 1e-9
+            np.testing.assert_allclose(got[f], c[f], rtol=tol, atol=tol, equal_nan=True, err_msg=f)
+        nev += len(got["cell"])
+    assert nev > 500
+
+
+def test_all_land_and_tiny(core):
+    """Edge cases: all-NaN grid (no events, NaN climatology), single cell, T < window."""
+    doy = np.tile(np.arange(1, 13), 3)
+    ts = torch.full((36, 5), float("nan"), dtype=torch.float32).cuda()
+    th, se = core.threshold_arrays(ts, doy, 12, windowHalfWidth=1, smoothPercentileWidth=3, feb29=False)
+    assert bool(torch.isnan(th).all()) and bool(torch.isnan(se).all())
+    ev = core.detect_arrays(ts, doy, 12, th, se)
+    assert len(ev) == 0 and int(ev.nvalid.sum()) == 0
+    O = _oracle()
+    rng = np.random.default_rng(3)
+    ts_h = rng.normal(10, 2, (36, 1)).astype(np.float32)
+    _clim_check(core, ts_h, doy, 12, windowHalfWidth=1, smoothPercentileWidth=3, feb29=False)
+
+
+def test_regional_properties(core):
+    """BASELINE config 2 shape (240x160 cells, 1982-2021, T=14610, 2.2 GB): size-independent
+    properties + oracle spot check on a random sample of cells."""
+    from xmhw_b200 import synth
+    O = _oracle()
+    time = synth.daily_time(1982, 2021)
+    doy = synth.doy366(time)
+    T, ngrid = len(time), 240 * 160
+    sea = synth.season_table(time)
+    ts = core.synth_sst_device(T, ngrid, sea)
+    th, se = core.threshold_arrays(ts, doy, 366)
+    ev = core.detect_arrays(ts, doy, 366, th, se)
+    torch.cuda.synchronize()
+    assert not bool(torch.isnan(th).any())
+    assert bool((th > se).all())                        # 90th percentile above the mean
+    got = ev.to_numpy()
+    n = len(got["cell"])
+    assert 1.5 < n / (ngrid * 40) < 3.5                 # ~2.4 events per cell-year
+    assert np.all(got["duration"] == got["index_end"] - got["index_start"] + 1)
+    assert np.all(got["duration"] >= 5) and np.all(got["index_start"] >= 1) and np.all(got["index_end"] < T)
+    assert np.all((got["index_peak"] >= got["index_start"]) & (got["index_peak"] <= got["index_end"]))
+    same = got["cell"][1:] == got["cell"][:-1]
+    assert np.all(np.diff(got["cell"]) >= 0)
+    assert np.all((got["index_start"][1:] - got["index_end"][:-1] - 1)[same] > 2)     # gaps > maxGap after joining
+    assert np.all(got["duration_moderate"] + got["duration_strong"] + got["duration_severe"]
+                  + got["duration_extreme"] <= got["duration"])
+    assert np.all(got["category"] >= 1) and np.all(got["intensity_max"] > 0)
+    assert np.array_equal(np.bincount(got["cell"], minlength=ngrid), np.diff(ev.offsets.cpu().numpy()))
+    # determinism / idempotence: a second run gives the identical table
+    ev2 = core.detect_arrays(ts, doy, 366, th, se).to_numpy()
+    for k in got:
+        assert np.array_equal(got[k], ev2[k], equal_nan=True), k
+    # oracle spot check
+    cells = np.sort(np.random.default_rng(1).choice(ngrid, 48, replace=False))
+    ts_h = ts[:, torch.from_numpy(cells).cuda()].cpu().numpy()
+    oth, ose = O.threshold(ts_h, doy, 366)
+    th_h = th[:, torch.from_numpy(cells).cuda()].cpu().numpy()
+    se_h = se[:, torch.from_numpy(cells).cuda()].cpu().numpy()
+    assert bit_equal(th_h, oth)
+    assert np.abs(se_h - ose).max() <= 1e-9
+    exp = O.detect(ts_h, doy, th_h, se_h)
+    sel = np.isin(got["cell"], cells)
+    sub = {k: v[sel] for k, v in got.items()}
+    sub["cell"] = np.searchsorted(cells, sub["cell"])
+    assert_events_match(sub, exp, _float_fields())

@@ -1,0 +1,113 @@
+"""ctypes binding of the C ABI in include/xmhw_b200.h.
+
+The CUDA library is the ONLY compute path of this package: if the shared
+object is missing or does not load, importing this module raises -- there is no
+CPU or PyTorch fallback (build it with `python -c "import __graft_entry__ as g; g.build()"`).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_xmhw_b200.so")
+
+EI_FIELDS = ("cell", "index_start", "index_end", "index_peak", "duration", "category",
+             "duration_moderate", "duration_strong", "duration_severe", "duration_extreme")
+EF_FIELDS = ("intensity_max", "intensity_mean", "intensity_cumulative", "intensity_var",
+             "severity_max", "severity_mean", "severity_cumulative", "severity_var",
+             "intensity_max_relThresh", "intensity_mean_relThresh",
+             "intensity_cumulative_relThresh", "intensity_var_relThresh",
+             "intensity_max_abs", "intensity_mean_abs", "intensity_cumulative_abs",
+             "intensity_var_abs", "rate_onset", "rate_decline")
+EI_COUNT = len(EI_FIELDS)
+EF_COUNT = len(EF_FIELDS)
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+class ClimPlanStruct(C.Structure):
+    """Mirror of `xmhw_clim_plan` (include/xmhw_b200.h)."""
+    _fields_ = [("nsteps", C.c_int32), ("pool_rows", C.c_int32), ("nmax", C.c_int32),
+                ("max_size", C.c_int32),
+                ("inst_base", C.c_void_p), ("inst_size", C.c_void_p), ("inst_row_off", C.c_void_p),
+                ("rows", C.c_void_p),
+                ("leave_off", C.c_void_p), ("leave", C.c_void_p),
+                ("enter_off", C.c_void_p), ("enter", C.c_void_p),
+                ("use_off", C.c_void_p), ("use", C.c_void_p),
+                ("q_lo", C.c_void_p), ("q_gamma", C.c_void_p)]
+
+
+PLAN_ARRAYS = ("inst_base", "inst_size", "inst_row_off", "rows", "leave_off", "leave",
+               "enter_off", "enter", "use_off", "use", "q_lo", "q_gamma")
+
+_SIGNATURES = {
+    "xmhw_abi_version": (C.c_int, []),
+    "xmhw_strerror": (C.c_char_p, [C.c_int]),
+    "xmhw_clim_sweep_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlanStruct),
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xmhw_clim_finish_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                                       C.c_int32, C.c_void_p]),
+    "xmhw_exceed_mask_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xmhw_events_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p]),
+    "xmhw_exclusive_scan_i32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xmhw_events_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "xmhw_event_stats_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+    "xmhw_synth_sst_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_double,
+                                     C.c_uint32, C.c_void_p]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "xmhw_b200: CUDA library %s not found. Build it first "
+            "(python -c \"import __graft_entry__ as g; g.build()\"). "
+            "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+if lib.xmhw_abi_version() != 1:
+    raise ImportError("xmhw_b200: ABI version mismatch in %s" % LIB_PATH)
+
+
+class XmhwCudaError(RuntimeError):
+    pass
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib.xmhw_strerror(code).decode()
+        raise XmhwCudaError("%s failed: %s (code %d)" % (what, msg, code))
+
+
+def plan_struct(host_plan, pointers):
+    """Build a ClimPlanStruct from a plan.ClimPlanHost and {array name: address}."""
+    s = ClimPlanStruct()
+    s.nsteps, s.pool_rows = host_plan.nsteps, host_plan.pool_rows
+    s.nmax, s.max_size = host_plan.nmax, host_plan.max_size
+    for name in PLAN_ARRAYS:
+        setattr(s, name, pointers[name])
+    return s
+
+
+def numpy_plan_struct(host_plan):
+    """Plan struct over HOST arrays (used only by the test-side lane emulator)."""
+    keep = {n: np.ascontiguousarray(getattr(host_plan, n)) for n in PLAN_ARRAYS}
+    s = plan_struct(host_plan, {n: a.ctypes.data for n, a in keep.items()})
+    return s, keep

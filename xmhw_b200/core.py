@@ -1,0 +1,212 @@
+"""Array-level API of the B200 hot path (device tensors in, device tensors out).
+
+These two functions replace the reference's per-cell Python loops
+
+    xmhw/xmhw.py:184-197   for c in ts.cell: calc_clim(...)     -> threshold_arrays
+    xmhw/xmhw.py:440-454   for c in ts.cell: define_events(...) -> detect_arrays
+
+with a handful of batched kernel launches over the whole (time, cell) array.
+PyTorch is plumbing only (device memory, streams); all arithmetic happens in
+the CUDA library reached through the C ABI (xmhw_b200/_cabi.py).  There is no
+CPU path: tensors must live on a CUDA device.
+"""
+import hashlib
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import plan as _plan
+from ._cabi import EF_COUNT, EF_FIELDS, EI_COUNT, EI_FIELDS, check, lib
+
+_plan_cache = {}
+
+
+def _ptr(t):
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t, name, dtype):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor (xmhw_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+
+
+@dataclass
+class DevicePlan:
+    host: _plan.ClimPlanHost
+    tensors: dict
+    struct: _cabi.ClimPlanStruct
+
+
+def device_plan(doy, ndoy, w, q, device):
+    """Build (or fetch from cache) the climatology sweep plan on `device`."""
+    doy = np.ascontiguousarray(doy, dtype=np.int64)
+    key = (hashlib.sha1(doy.tobytes()).hexdigest(), int(ndoy), int(w), float(q), str(device))
+    hit = _plan_cache.get(key)
+    if hit is not None:
+        return hit
+    host = _plan.build_clim_plan(doy, ndoy, w, q)
+    if host.smem_bytes() > 227 * 1024:
+        raise ValueError("climatology window needs %d KB of shared memory per warp (> 227 KB)"
+                         % (host.smem_bytes() // 1024))
+    tensors = {n: torch.from_numpy(np.ascontiguousarray(getattr(host, n))).to(device)
+               for n in _cabi.PLAN_ARRAYS}
+    struct = _cabi.plan_struct(host, {n: _ptr(t) for n, t in tensors.items()})
+    dp = DevicePlan(host, tensors, struct)
+    if len(_plan_cache) > 16:
+        _plan_cache.clear()
+    _plan_cache[key] = dp
+    return dp
+
+
+_csr_cache = {}
+
+
+def _doy_tables(doy, ndoy, device):
+    doy = np.ascontiguousarray(doy, dtype=np.int64)
+    key = (hashlib.sha1(doy.tobytes()).hexdigest(), int(ndoy), str(device))
+    hit = _csr_cache.get(key)
+    if hit is None:
+        ptr, tidx = _plan.doy_csr(doy, ndoy)
+        hit = (torch.from_numpy(ptr).to(device), torch.from_numpy(tidx).to(device),
+               torch.from_numpy(doy.astype(np.int32)).to(device))
+        if len(_csr_cache) > 16:
+            _csr_cache.clear()
+        _csr_cache[key] = hit
+    return hit
+
+
+def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercentile=True,
+                     smoothPercentileWidth=31, feb29=True, return_raw=False):
+    """Climatological threshold and seasonal mean for every cell of ts.
+
+    ts   CUDA float32 [T, ngrid] (time-major, the reference's (time, cell) stack)
+    doy  host int array [T], 1-based day-of-year labels (identify.py:28-79)
+    Returns (thresh, seas): CUDA float64 [ndoy, ngrid]; NaN where a (cell, doy)
+    has no sample (land).  Semantics: identify.py:184-270 + :137-181, xmhw.py:250-307.
+    """
+    _require_cuda(ts, "ts", torch.float32)
+    if ts.dim() != 2:
+        raise ValueError("ts must be [T, ngrid]")
+    T, ngrid = ts.shape
+    if len(doy) != T:
+        raise ValueError("doy must have one label per time step")
+    if smoothPercentile and smoothPercentileWidth % 2 == 0:
+        raise ValueError("smoothPercentileWidth should be odd")
+    with torch.cuda.device(ts.device):
+        dp = device_plan(doy, ndoy, windowHalfWidth, pctile / 100.0, ts.device)
+        st = _stream()
+        raw_t = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
+        raw_s = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
+        check(lib.xmhw_clim_sweep_f32(_ptr(ts), T, ngrid, dp.struct, _ptr(raw_t), _ptr(raw_s), st),
+              "xmhw_clim_sweep_f32")
+        W = int(smoothPercentileWidth) if smoothPercentile else 1
+        do_feb = bool(feb29) and ndoy >= 61
+        if W <= 1 and not do_feb:
+            return (raw_t, raw_s, raw_t, raw_s) if return_raw else (raw_t, raw_s)
+        out_t = torch.empty_like(raw_t)
+        out_s = torch.empty_like(raw_s)
+        for raw, out in ((raw_t, out_t), (raw_s, out_s)):
+            check(lib.xmhw_clim_finish_f64(_ptr(raw), _ptr(out), ndoy, ngrid, int(do_feb), W, st),
+                  "xmhw_clim_finish_f64")
+    return (out_t, out_s, raw_t, raw_s) if return_raw else (out_t, out_s)
+
+
+class EventTable:
+    """Compact event table on the device (struct of arrays).
+
+    i32 [EI_COUNT, n] int32 and f64 [EF_COUNT, n] float64 hold the columns named in
+    `_cabi.EI_FIELDS` / `_cabi.EF_FIELDS` (the reference's per-event variables,
+    features.py:114-152, :181-189, :290-291), ordered by cell then start index.
+    `nvalid` [ngrid] int32 is the number of non-NaN samples per cell (land_check).
+    """
+
+    def __init__(self, i32, f64, n, offsets, nvalid, T, ngrid):
+        self.i32, self.f64, self.n = i32, f64, n
+        self.offsets, self.nvalid, self.T, self.ngrid = offsets, nvalid, T, ngrid
+
+    def __len__(self):
+        return self.n
+
+    def column(self, name):
+        if name in EI_FIELDS:
+            return self.i32[EI_FIELDS.index(name), :self.n]
+        return self.f64[EF_FIELDS.index(name), :self.n]
+
+    def to_numpy(self):
+        i32 = self.i32[:, :self.n].cpu().numpy()
+        f64 = self.f64[:, :self.n].cpu().numpy()
+        out = {f: i32[k].astype(np.int64) for k, f in enumerate(EI_FIELDS)}
+        out.update({f: f64[k] for k, f in enumerate(EF_FIELDS)})
+        return out
+
+
+def detect_arrays(ts, doy, ndoy, thresh, seas, minDuration=5, joinGaps=True, maxGap=2):
+    """Marine-heatwave events of every cell of ts given the climatologies.
+
+    ts CUDA float32 [T, ngrid]; thresh, seas CUDA float64 [ndoy, ngrid]; doy host
+    int [T].  Semantics: identify.py:328-479 (define_events, mhw_filter, join_gaps)
+    and features.py:22-295.  Returns an EventTable.
+    """
+    _require_cuda(ts, "ts", torch.float32)
+    _require_cuda(thresh, "thresh", torch.float64)
+    _require_cuda(seas, "seas", torch.float64)
+    T, ngrid = ts.shape
+    if thresh.shape != (ndoy, ngrid) or seas.shape != (ndoy, ngrid):
+        raise ValueError("thresh/seas must be [ndoy, ngrid]")
+    if len(doy) != T:
+        raise ValueError("doy must have one label per time step")
+    if maxGap >= minDuration:
+        raise ValueError("Maximum gap between mhw events should be smaller than event minimum duration")
+    dev = ts.device
+    with torch.cuda.device(dev):
+        st = _stream()
+        ptr, tidx, doy32 = _doy_tables(doy, ndoy, dev)
+        ncg = (ngrid + 31) // 32
+        mask = torch.empty((ncg, T), dtype=torch.int32, device=dev)
+        nvalid = torch.zeros(ngrid, dtype=torch.int32, device=dev)
+        check(lib.xmhw_exceed_mask_f32(_ptr(ts), T, ngrid, _ptr(ptr), _ptr(tidx), ndoy, _ptr(thresh),
+                                       _ptr(mask), _ptr(nvalid), st), "xmhw_exceed_mask_f32")
+        counts = torch.empty(ngrid, dtype=torch.int32, device=dev)
+        check(lib.xmhw_events_count(_ptr(mask), T, ngrid, int(minDuration), int(bool(joinGaps)), int(maxGap),
+                                    _ptr(counts), st), "xmhw_events_count")
+        offsets = torch.empty(ngrid + 1, dtype=torch.int64, device=dev)
+        scratch = torch.empty(ngrid // 1024 + 2, dtype=torch.int64, device=dev)
+        check(lib.xmhw_exclusive_scan_i32(_ptr(counts), ngrid, _ptr(offsets), _ptr(scratch), st),
+              "xmhw_exclusive_scan_i32")
+        nev = int(offsets[-1].item())          # the one host sync: sizes the event table
+        cap = max(nev, 1)
+        ev_i32 = torch.empty((EI_COUNT, cap), dtype=torch.int32, device=dev)
+        ev_f64 = torch.empty((EF_COUNT, cap), dtype=torch.float64, device=dev)
+        if nev:
+            check(lib.xmhw_events_fill(_ptr(mask), T, ngrid, int(minDuration), int(bool(joinGaps)), int(maxGap),
+                                       _ptr(offsets), cap, _ptr(ev_i32), st), "xmhw_events_fill")
+            check(lib.xmhw_event_stats_f32(_ptr(ts), T, ngrid, _ptr(doy32), _ptr(thresh), _ptr(seas), nev, cap,
+                                           _ptr(ev_i32), _ptr(ev_f64), st), "xmhw_event_stats_f32")
+    return EventTable(ev_i32, ev_f64, nev, offsets, nvalid, T, ngrid)
+
+
+def synth_sst_device(T, ngrid, season, land=None, cell0=0, seed=None, nan_ppm=0, device="cuda", out=None):
+    """Device twin of synth.synth_sst (bit-identical): float32 [T, ngrid] on `device`."""
+    from . import synth
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        ts = out if out is not None else torch.empty((T, ngrid), dtype=torch.float32, device=dev)
+        sea = torch.from_numpy(np.ascontiguousarray(season, np.float64)).to(dev)
+        if sea.numel() < T + 366:
+            raise ValueError("season table must have T + 366 entries")
+        ld = None if land is None else torch.from_numpy(np.ascontiguousarray(land, np.uint8).ravel()).to(dev)
+        check(lib.xmhw_synth_sst_f32(_ptr(ts), T, ngrid, int(cell0), 0 if ld is None else _ptr(ld), _ptr(sea),
+                                     synth.SEED if seed is None else int(seed), synth.RHO, synth.SIGMA,
+                                     synth.NOISE_SCALE, int(nan_ppm), _stream()), "xmhw_synth_sst_f32")
+        torch.cuda.current_stream().synchronize()   # keep `sea`/`ld` alive until the kernel is done
+    return ts

@@ -1,0 +1,432 @@
+// xmhw_b200 CUDA kernels (sm_100a) + C ABI.  See include/xmhw_b200.h for the
+// boundary contract and xmhw_lane.h for the per-lane algorithms.
+//
+// All kernels map one grid cell to one lane (32 adjacent cells per warp): the
+// reference layouts (time, cell) / (doy, cell) are then read and written as
+// contiguous 128 B / 256 B row segments with no transpose pass.  None of this
+// is a contraction, so tensor cores are not used; the kernels are HBM-, LSU- and
+// ALU-bound.  Compiled with --fmad=false so that the float64 expressions round
+// exactly like numpy/pandas (no FMA contraction).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/xmhw_b200.h"
+#include "xmhw_lane.h"
+
+namespace {
+
+using namespace xmhw;
+
+struct WarpEnv {
+  __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
+};
+
+static_assert(sizeof(xmhw_clim_plan) == sizeof(ClimPlan), "plan ABI mismatch");
+static_assert((int)XMHW_EI_COUNT == (int)EI_COUNT && (int)XMHW_EF_COUNT == (int)EF_COUNT, "event ABI mismatch");
+
+// ---------------------------------------------------------------------------
+// K1  climatology sweep: one warp = 32 cells, sequential over day-of-year.
+// Shared memory per warp: plan.pool_rows rows of 32 words (sorted lists of the
+// current +-w window, their f64 sums and per-lane cut pointers).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) clim_sweep_kernel(ClimPlan p, const float* __restrict__ ts,
+                                                        int64_t ngrid, double* __restrict__ thr,
+                                                        double* __restrict__ seas) {
+  extern __shared__ uint32_t pool[];
+  const int lane = threadIdx.x;
+  const int64_t cell = (int64_t)blockIdx.x * 32 + lane;
+  const bool ok = cell < ngrid;
+  const float* col = ts + (ok ? cell : 0);
+  SweepState st;
+  st.C = 0; st.n = 0; st.pivot = 0xffffffffu;
+  WarpEnv env;
+  for (int s = 0; s < p.nsteps; ++s) {
+    double a, b;
+    sweep_step(env, p, s, st, pool, lane, col, ngrid, ok, a, b);
+    if (ok) {
+      thr[(int64_t)s * ngrid + cell] = a;
+      seas[(int64_t)s * ngrid + cell] = b;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1b  Feb-29 rule + circular running mean over doy.  One thread = one cell,
+// a ring of `W` raw values per thread in shared memory (column = thread, so
+// bank-conflict free); fresh left-to-right f64 sum per output (bit-equal to the
+// oracle's order).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double finish_value(const double* __restrict__ raw, int64_t ngrid, int64_t cell,
+                                               int ndoy, int feb29, int idx) {
+  if (feb29 && idx == 59 && ndoy >= 61) {
+    double acc = 0.0; int n = 0;
+#pragma unroll
+    for (int d = 58; d <= 60; ++d) {
+      double v = raw[(int64_t)d * ngrid + cell];
+      if (v == v) { acc = acc + v; ++n; }
+    }
+    return n ? acc / (double)n : qnan();
+  }
+  return raw[(int64_t)idx * ngrid + cell];
+}
+
+__global__ void clim_finish_kernel(const double* __restrict__ raw, double* __restrict__ out, int ndoy,
+                                   int64_t ngrid, int feb29, int W) {
+  extern __shared__ double ring[];
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ngrid) return;
+  if (W <= 1) {
+    for (int d = 0; d < ndoy; ++d) out[(int64_t)d * ngrid + cell] = finish_value(raw, ngrid, cell, ndoy, feb29, d);
+    return;
+  }
+  const int h = (W - 1) / 2;
+  const int nt = blockDim.x, tid = threadIdx.x;
+  // unwrapped index u = d + k, k in [-h, h]; ring slot = (u + h) mod W
+  for (int u = -h; u < h; ++u) {
+    int idx = ((u % ndoy) + ndoy) % ndoy;
+    ring[((u + h) % W) * nt + tid] = finish_value(raw, ngrid, cell, ndoy, feb29, idx);
+  }
+  for (int d = 0; d < ndoy; ++d) {
+    int u = d + h;
+    ring[((u + h) % W) * nt + tid] = finish_value(raw, ngrid, cell, ndoy, feb29, u % ndoy);
+    int slot = d % W;     // slot of u = d - h
+    double acc = 0.0;
+    for (int k = 0; k < W; ++k) {
+      acc = acc + ring[slot * nt + tid];
+      slot = slot + 1 == W ? 0 : slot + 1;
+    }
+    out[(int64_t)d * ngrid + cell] = acc / (double)W;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2  exceedance sweep, doy-major: the threshold of (cell, doy) stays in a
+// register while every year's sample of that doy streams through, so no
+// per-timestep threshold fetch is needed.  ts > thresh in float64 is evaluated
+// exactly as ts > round_down_f32(thresh).
+// ---------------------------------------------------------------------------
+constexpr int EXC_WARPS = 8;
+constexpr int EXC_BATCH = 8;
+
+__global__ void __launch_bounds__(EXC_WARPS * 32) exceed_kernel(
+    const float* __restrict__ ts, int64_t T, int64_t ngrid, const int32_t* __restrict__ doy_ptr,
+    const int32_t* __restrict__ doy_tidx, int ndoy, int nchunk, const double* __restrict__ thresh,
+    uint32_t* __restrict__ mask, int32_t* __restrict__ nvalid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * EXC_WARPS + (threadIdx.x >> 5);
+  const int64_t ncg = (ngrid + 31) / 32;
+  const int64_t cg = w / nchunk;
+  const int chunk = (int)(w % nchunk);
+  if (cg >= ncg) return;
+  const int64_t cell = cg * 32 + lane;
+  const bool ok = cell < ngrid;
+  const float* col = ts + (ok ? cell : 0);
+  uint32_t* mrow = mask + cg * T;
+  const int d0 = (int)((int64_t)ndoy * chunk / nchunk), d1 = (int)((int64_t)ndoy * (chunk + 1) / nchunk);
+  int cnt = 0;
+  for (int d = d0; d < d1; ++d) {
+    const double th = ok ? thresh[(int64_t)d * ngrid + cell] : qnan();
+    const float thr = __double2float_rd(th);
+    const int j1 = doy_ptr[d + 1];
+    for (int j = doy_ptr[d]; j < j1; j += EXC_BATCH) {
+      float v[EXC_BATCH];
+      int t[EXC_BATCH];
+#pragma unroll
+      for (int i = 0; i < EXC_BATCH; ++i) {
+        t[i] = j + i < j1 ? doy_tidx[j + i] : -1;
+        v[i] = (t[i] >= 0 && ok) ? __ldg(col + (int64_t)t[i] * ngrid) : __uint_as_float(0x7fc00000u);
+      }
+#pragma unroll
+      for (int i = 0; i < EXC_BATCH; ++i) {
+        if (t[i] >= 0) {
+          cnt += v[i] == v[i];
+          uint32_t bits = __ballot_sync(0xffffffffu, v[i] > thr);
+          if (lane == 0) mrow[t[i]] = bits;
+        }
+      }
+    }
+  }
+  if (ok && cnt) atomicAdd(nvalid + cell, cnt);
+}
+
+// ---------------------------------------------------------------------------
+// K3  event finding: warp = 32 cells; 32 mask words (32 consecutive times) are
+// bit-transposed in the warp so each lane holds 32 time steps of its own cell,
+// then the lane runs the run-length / min-duration / gap-join rules.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+  // lane i holds row i (bit c = column c); returns column `lane` (bit r = row r)
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu
+                     : j == 2 ? 0x33333333u : 0x55555555u;
+    uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+    x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y & m) << j));
+  }
+  return x;
+}
+
+constexpr int EVT_WARPS = 4;
+
+struct CountEmit {
+  int n;
+  __device__ __forceinline__ void operator()(int, int) { ++n; }
+};
+struct FillEmit {
+  int32_t* ev; int64_t cap, pos; int32_t cell;
+  __device__ __forceinline__ void operator()(int s, int e) {
+    ev[EI_CELL * cap + pos] = cell;
+    ev[EI_START * cap + pos] = s;
+    ev[EI_END * cap + pos] = e;
+    ++pos;
+  }
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(EVT_WARPS * 32) events_kernel(
+    const uint32_t* __restrict__ mask, int64_t T, int64_t ngrid, int min_dur, int join, int max_gap,
+    int32_t* __restrict__ counts, const int64_t* __restrict__ offsets, int64_t cap, int32_t* __restrict__ ev) {
+  const int lane = threadIdx.x & 31;
+  const int64_t cg = (int64_t)blockIdx.x * EVT_WARPS + (threadIdx.x >> 5);
+  if (cg >= (ngrid + 31) / 32) return;
+  const int64_t cell = cg * 32 + lane;
+  const bool ok = cell < ngrid;
+  const uint32_t* mrow = mask + cg * T;
+  RunFinder rf(min_dur, join, max_gap);
+  CountEmit ce; ce.n = 0;
+  FillEmit fe; fe.ev = ev; fe.cap = cap; fe.cell = (int32_t)cell; fe.pos = (FILL && ok) ? offsets[cell] : 0;
+  for (int64_t t0 = 0; t0 < T; t0 += 32) {
+    uint32_t x = (t0 + lane < T) ? __ldg(mrow + t0 + lane) : 0u;
+    uint32_t bits = transpose32(x, lane);
+    if (FILL) { if (ok) rf.feed(bits, (int)t0, fe); } else rf.feed(bits, (int)t0, ce);
+  }
+  if (FILL) { if (ok) rf.finish((int)T, fe); }
+  else { rf.finish((int)T, ce); if (ok) counts[cell] = ce.n; }
+}
+
+// ---------------------------------------------------------------------------
+// exclusive scan int32 -> int64 (three small kernels; n <= a few million)
+// ---------------------------------------------------------------------------
+constexpr int SCAN_ITEMS = 1024;
+
+__global__ void scan_block_sums(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ bsum) {
+  __shared__ long long red[32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_ITEMS;
+  long long s = 0;
+  for (int i = threadIdx.x; i < SCAN_ITEMS; i += blockDim.x)
+    if (base + i < n) s += in[base + i];
+  for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tot = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    bsum[blockIdx.x] = tot;
+  }
+}
+__global__ void scan_of_sums(int64_t* bsum, int64_t nb) {
+  // single warp: chunks of 32 block sums, exclusive scan in place, total at bsum[nb]
+  const int lane = threadIdx.x;
+  long long carry = 0;
+  for (int64_t b0 = 0; b0 < nb; b0 += 32) {
+    long long v = (b0 + lane < nb) ? bsum[b0 + lane] : 0, x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (b0 + lane < nb) bsum[b0 + lane] = carry + x - v;
+    carry += __shfl_sync(0xffffffffu, x, 31);
+  }
+  if (lane == 0) bsum[nb] = carry;
+}
+__global__ void scan_apply(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ bsum,
+                           int64_t nb, int64_t* __restrict__ out) {
+  // one warp per 1024-item block, sequential over 32 chunks of 32
+  const int lane = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_ITEMS;
+  long long carry = bsum[blockIdx.x];
+  for (int c = 0; c < SCAN_ITEMS / 32; ++c) {
+    int64_t i = base + c * 32 + lane;
+    long long v = i < n ? in[i] : 0, x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (i < n) out[i] = carry + x - v;
+    carry += __shfl_sync(0xffffffffu, x, 31);
+  }
+  if (blockIdx.x == nb - 1 && lane == 0) out[n] = bsum[nb];
+}
+
+// ---------------------------------------------------------------------------
+// K4  per-event statistics: one thread = one event.
+// ---------------------------------------------------------------------------
+__global__ void event_stats_kernel(const float* __restrict__ ts, int64_t T, int64_t ngrid,
+                                   const int32_t* __restrict__ doy, const double* __restrict__ thr,
+                                   const double* __restrict__ seas, int64_t nev, int64_t cap,
+                                   int32_t* __restrict__ ei, double* __restrict__ ef) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nev) return;
+  const int64_t cell = ei[EI_CELL * cap + i];
+  const int s = ei[EI_START * cap + i], e = ei[EI_END * cap + i];
+  event_stats(ts + cell, thr + cell, seas + cell, doy, ngrid, (int)T, s, e, ei + i, ef + i, cap);
+}
+
+// ---------------------------------------------------------------------------
+// synthetic SST generator (bit-identical to xmhw_b200/synth.py)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ double u01(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0); }
+
+__global__ void synth_kernel(float* __restrict__ ts, int64_t T, int64_t ngrid, int64_t cell0,
+                             const uint8_t* __restrict__ land, const double* __restrict__ season,
+                             uint64_t seed, double rho, double sigma, double noise_scale,
+                             uint32_t nan_ppm) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ngrid) return;
+  const uint64_t gid = (uint64_t)(cell0 + cell);
+  const bool is_land = land && land[cell];
+  const uint64_t h0 = splitmix64(seed ^ (gid * 0xD1B54A32D192ED03ull));
+  const double m = 28.0 * u01(splitmix64(h0 + 1));
+  const double A = 1.0 + 5.0 * u01(splitmix64(h0 + 2));
+  const int phi = (int)(365.0 * u01(splitmix64(h0 + 3)));
+  double x = 0.0;
+  for (int64_t t = 0; t < T; ++t) {
+    const uint64_t r = splitmix64(h0 ^ ((uint64_t)t * 0x9E3779B97F4A7C15ull + 0x1234567ull));
+    const int sum16 = (int)(r & 0xffff) + (int)((r >> 16) & 0xffff) + (int)((r >> 32) & 0xffff) + (int)(r >> 48);
+    const double eps = (double)(sum16 - 131070) * noise_scale;
+    x = rho * x + sigma * eps;
+    const double v = (m + A * season[t + phi]) + x;
+    float out = (float)(rint(v * 100.0) / 100.0);
+    if (nan_ppm) {
+      const uint64_t q = splitmix64(r ^ 0xA5A5A5A5A5A5A5A5ull);
+      if ((uint32_t)(q % 1000000ull) < nan_ppm) out = __uint_as_float(0x7fc00000u);
+    }
+    if (is_land) out = __uint_as_float(0x7fc00000u);
+    ts[t * ngrid + cell] = out;
+  }
+}
+
+inline int cuda_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int xmhw_abi_version(void) { return XMHW_ABI_VERSION; }
+
+const char* xmhw_strerror(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case XMHW_E_ARG: return "invalid argument (null pointer or non-positive size)";
+    case XMHW_E_PLAN: return "inconsistent climatology plan";
+    case XMHW_E_SMEM: return "climatology plan needs more shared memory than one SM provides";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown xmhw error";
+  }
+}
+
+int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan* plan,
+                        double* thresh_raw, double* seas_raw, void* stream) {
+  if (!ts || !plan || !thresh_raw || !seas_raw || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
+  if (plan->nsteps <= 0 || plan->pool_rows <= 0 || plan->max_size > 32 || plan->nmax <= 0) return XMHW_E_PLAN;
+  const size_t smem = (size_t)plan->pool_rows * 128;
+  if (smem > 227 * 1024) return XMHW_E_SMEM;
+  cudaError_t e = cudaFuncSetAttribute(clim_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  ClimPlan p;
+  memcpy(&p, plan, sizeof(p));
+  const int64_t ncg = (ngrid + 31) / 32;
+  clim_sweep_kernel<<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw);
+  return cuda_status();
+}
+
+int xmhw_clim_finish_f64(const double* raw, double* out, int32_t ndoy, int64_t ngrid, int32_t feb29,
+                         int32_t smooth_width, void* stream) {
+  if (!raw || !out || raw == out || ndoy <= 0 || ngrid <= 0) return XMHW_E_ARG;
+  if (smooth_width > 1 && smooth_width % 2 == 0) return XMHW_E_ARG;
+  const int nt = 128;
+  const size_t smem = smooth_width > 1 ? (size_t)smooth_width * nt * sizeof(double) : 0;
+  if (smem > 227 * 1024) return XMHW_E_SMEM;
+  cudaError_t e = cudaFuncSetAttribute(clim_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  clim_finish_kernel<<<(unsigned)((ngrid + nt - 1) / nt), nt, smem, (cudaStream_t)stream>>>(
+      raw, out, ndoy, ngrid, feb29, smooth_width);
+  return cuda_status();
+}
+
+int xmhw_exceed_mask_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy_ptr,
+                         const int32_t* doy_tidx, int32_t ndoy, const double* thresh, uint32_t* mask,
+                         int32_t* nvalid, void* stream) {
+  if (!ts || !doy_ptr || !doy_tidx || !thresh || !mask || !nvalid || T <= 0 || ngrid <= 0 || ndoy <= 0)
+    return XMHW_E_ARG;
+  const int64_t ncg = (ngrid + 31) / 32;
+  // enough warps to fill the machine: 148 SMs x 64 warps; split the doy axis on small grids
+  int nchunk = (int)((148 * 64 * 2 + ncg - 1) / ncg);
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > ndoy) nchunk = ndoy;
+  const int64_t nwarp = ncg * nchunk;
+  exceed_kernel<<<(unsigned)((nwarp + EXC_WARPS - 1) / EXC_WARPS), EXC_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      ts, T, ngrid, doy_ptr, doy_tidx, ndoy, nchunk, thresh, mask, nvalid);
+  return cuda_status();
+}
+
+int xmhw_events_count(const uint32_t* mask, int64_t T, int64_t ngrid, int32_t min_duration,
+                      int32_t join_gaps, int32_t max_gap, int32_t* counts, void* stream) {
+  if (!mask || !counts || T <= 0 || ngrid <= 0 || min_duration < 1 || max_gap < 0) return XMHW_E_ARG;
+  const int64_t ncg = (ngrid + 31) / 32;
+  events_kernel<false><<<(unsigned)((ncg + EVT_WARPS - 1) / EVT_WARPS), EVT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      mask, T, ngrid, min_duration, join_gaps, max_gap, counts, nullptr, 0, nullptr);
+  return cuda_status();
+}
+
+int xmhw_exclusive_scan_i32(const int32_t* counts, int64_t n, int64_t* offsets, int64_t* scratch, void* stream) {
+  if (!counts || !offsets || !scratch || n <= 0) return XMHW_E_ARG;
+  const int64_t nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+  cudaStream_t st = (cudaStream_t)stream;
+  scan_block_sums<<<(unsigned)nb, 256, 0, st>>>(counts, n, scratch);
+  scan_of_sums<<<1, 32, 0, st>>>(scratch, nb);
+  scan_apply<<<(unsigned)nb, 32, 0, st>>>(counts, n, scratch, nb, offsets);
+  return cuda_status();
+}
+
+int xmhw_events_fill(const uint32_t* mask, int64_t T, int64_t ngrid, int32_t min_duration, int32_t join_gaps,
+                     int32_t max_gap, const int64_t* offsets, int64_t cap, int32_t* ev_i32, void* stream) {
+  if (!mask || !offsets || !ev_i32 || T <= 0 || ngrid <= 0 || cap <= 0 || min_duration < 1 || max_gap < 0)
+    return XMHW_E_ARG;
+  const int64_t ncg = (ngrid + 31) / 32;
+  events_kernel<true><<<(unsigned)((ncg + EVT_WARPS - 1) / EVT_WARPS), EVT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      mask, T, ngrid, min_duration, join_gaps, max_gap, nullptr, offsets, cap, ev_i32);
+  return cuda_status();
+}
+
+int xmhw_event_stats_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy, const double* thresh,
+                         const double* seas, int64_t nev, int64_t cap, int32_t* ev_i32, double* ev_f64,
+                         void* stream) {
+  if (!ts || !doy || !thresh || !seas || !ev_i32 || !ev_f64 || T <= 0 || ngrid <= 0 || nev < 0 || cap < nev)
+    return XMHW_E_ARG;
+  if (nev == 0) return 0;
+  const int nt = 128;
+  event_stats_kernel<<<(unsigned)((nev + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
+      ts, T, ngrid, doy, thresh, seas, nev, cap, ev_i32, ev_f64);
+  return cuda_status();
+}
+
+int xmhw_synth_sst_f32(float* ts, int64_t T, int64_t ngrid, int64_t cell0, const uint8_t* land,
+                       const double* season, uint64_t seed, double rho, double sigma, double noise_scale,
+                       uint32_t nan_per_million, void* stream) {
+  if (!ts || !season || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
+  const int nt = 128;
+  synth_kernel<<<(unsigned)((ngrid + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
+      ts, T, ngrid, cell0, land, season, seed, rho, sigma, noise_scale, nan_per_million);
+  return cuda_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+"""Host-side planning for the climatology sweep kernel.
+
+The reference pools, for every day-of-year d, the samples ts[t+k] with
+doy[t] == d and |k| <= windowHalfWidth (xmhw/identify.py:184-209 window_roll,
+then groupby("doy") at identify.py:233/263).  Windows of consecutive doys share
+all but one "column" of samples, so the GPU kernel sorts each column once and
+slides over doy.  This module derives that structure from the ACTUAL doy
+vector, which makes leap days (doy 60 only exists in leap years,
+identify.py:73-76), truncated windows at the series edges, `tstep=True`
+calendars (identify.py:58-71) and any half-width one uniform case:
+
+* the *signature* of time row t' is the set of doys whose window contains it,
+  {doy[t] : |t - t'| <= w};
+* rows with equal signature form a *class*; a class is cut into *instances*
+  of at most 32 rows (one register-resident sorting network each) and into
+  separate visits when its doys are not contiguous in sweep order (the year
+  wrap-around);
+* the window of doy d is the disjoint union of the instances whose signature
+  contains d.
+
+The plan also carries numpy's 'linear' quantile index table
+(floor((n-1) q), fractional part) for every possible sample count n, computed
+here in float64 exactly as numpy does, and a static shared-memory allocation
+for the instances (the kernel never allocates).
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+MAX_LIST = 32          # rows per instance = keys per register sorting network
+META_ROWS = 3          # meta word + f64 sum (2 words) per instance and lane
+LOAD_FLAG = 1 << 30
+MAX_GAP_STEPS = 2      # a class stays resident across holes of up to this many sweep steps
+
+
+@dataclass
+class ClimPlanHost:
+    nsteps: int
+    pool_rows: int
+    nmax: int
+    max_size: int
+    inst_base: np.ndarray
+    inst_size: np.ndarray
+    inst_row_off: np.ndarray
+    rows: np.ndarray
+    leave_off: np.ndarray
+    leave: np.ndarray
+    enter_off: np.ndarray
+    enter: np.ndarray
+    use_off: np.ndarray
+    use: np.ndarray
+    q_lo: np.ndarray
+    q_gamma: np.ndarray
+    # diagnostics
+    n_instances: int = 0
+    n_loads: int = 0
+    rows_loaded: int = 0
+    max_lists: int = 0
+
+    def smem_bytes(self):
+        return self.pool_rows * 128
+
+
+def quantile_table(nmax, q):
+    """numpy 2.x `method="linear"`: virtual index v = (n-1)*q evaluated in float64
+    (numpy/lib/_function_base_impl.py `_QuantileMethods['linear']`), previous index
+    floor(v), gamma = v - floor(v); v >= n-1 selects the maximum (`_get_indexes`)."""
+    n = np.arange(nmax + 1, dtype=np.int64)
+    v = (n - 1) * np.float64(q)
+    lo = np.floor(v)
+    gamma = v - lo
+    above = v >= (n - 1)
+    lo = np.where(above, n - 1, lo)
+    gamma = np.where(above, 0.0, gamma)
+    lo = np.where(n == 0, 0, lo)
+    return lo.astype(np.int32), gamma.astype(np.float64)
+
+
+def build_clim_plan(doy, ndoy, w, q):
+    """doy: int array [T] of 1-based labels in 1..ndoy; w: window half width; q in [0,1]."""
+    doy = np.asarray(doy, dtype=np.int64)
+    T = len(doy)
+    if T == 0:
+        raise ValueError("empty time axis")
+    if doy.min() < 1 or doy.max() > ndoy:
+        raise ValueError("doy labels must lie in 1..ndoy")
+    if w < 0:
+        raise ValueError("windowHalfWidth must be >= 0")
+    # signature of every row
+    classes = {}
+    for tp in range(T):
+        lo, hi = max(0, tp - w), min(T, tp + w + 1)
+        seg = doy[lo:hi]
+        sig = tuple(sorted(set(seg.tolist())))
+        if len(sig) != hi - lo:
+            raise NotImplementedError(
+                "window (2*windowHalfWidth+1) spans repeated day-of-year labels; "
+                "windows wider than one year are not supported")
+        classes.setdefault(sig, []).append(tp)
+
+    # instances: (rows, sorted step list) split into visits and into <= MAX_LIST pieces
+    insts = []   # dict(rows=array, steps=list)
+    for sig, rws in classes.items():
+        steps = [d - 1 for d in sig]
+        visits = [[steps[0]]]
+        for s in steps[1:]:
+            if s - visits[-1][-1] <= MAX_GAP_STEPS:
+                visits[-1].append(s)
+            else:
+                visits.append([s])
+        rws = np.asarray(rws, np.int32)
+        npieces = -(-len(rws) // MAX_LIST)
+        pieces = np.array_split(rws, npieces)
+        for v in visits:
+            for pc in pieces:
+                insts.append({"rows": pc, "steps": v})
+    insts.sort(key=lambda i: (i["steps"][0], int(i["rows"][0])))
+    ninst = len(insts)
+
+    by_first = [[] for _ in range(ndoy)]
+    in_use = [[] for _ in range(ndoy)]
+    for i, it in enumerate(insts):
+        by_first[it["steps"][0]].append(i)
+        for s in it["steps"]:
+            in_use[s].append(i)
+
+    # static pool allocation (first fit over the sweep)
+    free = [(0, 1 << 30)]
+    base = np.zeros(ninst, np.int32)
+    pool_rows = 0
+    release_at = [[] for _ in range(ndoy + 1)]
+
+    def alloc(n):
+        nonlocal pool_rows
+        for k, (a, sz) in enumerate(free):
+            if sz >= n:
+                if sz == n:
+                    free.pop(k)
+                else:
+                    free[k] = (a + n, sz - n)
+                pool_rows = max(pool_rows, a + n)
+                return a
+        raise RuntimeError("pool exhausted")
+
+    def release(a, n):
+        free.append((a, n))
+        free.sort()
+        merged = []
+        for seg in free:
+            if merged and merged[-1][0] + merged[-1][1] == seg[0]:
+                merged[-1] = (merged[-1][0], merged[-1][1] + seg[1])
+            else:
+                merged.append(seg)
+        free[:] = merged
+
+    leave_off, leave, enter_off, enter, use_off, use = [0], [], [0], [], [0], []
+    prev_use = set()
+    loaded = set()
+    n_loads = rows_loaded = max_lists = 0
+    for s in range(ndoy):
+        for (a, n) in release_at[s]:
+            release(a, n)
+        cur = in_use[s]
+        cur_set = set(cur)
+        for i in sorted(prev_use - cur_set):
+            leave.append(int(base[i]))
+        for i in cur:
+            if i in prev_use:
+                continue
+            if i not in loaded:
+                n = len(insts[i]["rows"]) + META_ROWS
+                base[i] = alloc(n)
+                release_at[insts[i]["steps"][-1] + 1].append((int(base[i]), n))
+                loaded.add(i)
+                enter.append(i | LOAD_FLAG)
+                n_loads += 1
+                rows_loaded += len(insts[i]["rows"])
+            else:
+                enter.append(i)
+        for i in cur:
+            use.append(int(base[i]))
+        max_lists = max(max_lists, len(cur))
+        leave_off.append(len(leave))
+        enter_off.append(len(enter))
+        use_off.append(len(use))
+        prev_use = cur_set
+
+    sizes = np.array([len(it["rows"]) for it in insts], np.int32)
+    row_off = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)
+    rows = np.concatenate([it["rows"] for it in insts]).astype(np.int32)
+    nmax = max(1, max(sum(int(sizes[i]) for i in in_use[s]) for s in range(ndoy)))
+    q_lo, q_gamma = quantile_table(nmax, q)
+
+    def arr(x):
+        a = np.asarray(x, np.int32)
+        return a if a.size else np.zeros(1, np.int32)
+
+    return ClimPlanHost(
+        nsteps=ndoy, pool_rows=int(pool_rows), nmax=int(nmax), max_size=int(sizes.max()),
+        inst_base=base, inst_size=sizes, inst_row_off=row_off, rows=rows,
+        leave_off=arr(leave_off), leave=arr(leave), enter_off=arr(enter_off), enter=arr(enter),
+        use_off=arr(use_off), use=arr(use), q_lo=q_lo, q_gamma=q_gamma,
+        n_instances=ninst, n_loads=n_loads, rows_loaded=rows_loaded, max_lists=max_lists)
+
+
+def doy_csr(doy, ndoy):
+    """CSR of time indices per doy label: (ptr [ndoy+1], tidx [T]) int32."""
+    doy = np.asarray(doy, np.int64)
+    order = np.argsort(doy, kind="stable").astype(np.int32)
+    counts = np.bincount(doy - 1, minlength=ndoy)
+    ptr = np.concatenate(([0], np.cumsum(counts))).astype(np.int32)
+    return ptr, order
