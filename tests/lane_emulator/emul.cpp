@@ -11,20 +11,26 @@
 
 using namespace xmhw;
 
-struct HostEnv { bool any(bool p) const { return p; } };
+struct HostEnv {
+  bool any(bool p) const { return p; }
+  void stage(uint32_t* ub, const int32_t* src, int m, int m4, int) const {
+    for (int i = 0; i < m4; ++i) ub[i] = i < m ? (uint32_t)src[i] : 0u;
+  }
+};
 
 extern "C" {
 
 int emul_clim_sweep(const float* ts, int64_t T, int64_t ngrid, const ClimPlan* plan, double* thr, double* seas) {
   (void)T;
-  std::vector<uint32_t> pool((size_t)plan->pool_rows * 32);
+  std::vector<uint32_t> pool((size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 32);
   HostEnv env;
   for (int64_t cell = 0; cell < ngrid; ++cell) {
-    SweepState st; st.C = 0; st.n = 0; st.pivot = 0xffffffffu;
     const int lane = (int)(cell & 31);
+    Sweeper<HostEnv> sw(env, *plan, pool.data(), lane, ts + cell, ngrid, true);
+    sw.init();
     for (int s = 0; s < plan->nsteps; ++s) {
       double a, b;
-      sweep_step(env, *plan, s, st, pool.data(), lane, ts + cell, ngrid, true, a, b);
+      sw.step(s, a, b);
       thr[(int64_t)s * ngrid + cell] = a;
       seas[(int64_t)s * ngrid + cell] = b;
     }

@@ -1,0 +1,138 @@
+"""CPU tests of the host-side plan builder and of the per-lane device logic compiled for
+the host (tests/lane_emulator, TEST INFRASTRUCTURE ONLY): plan + sweep selection, run
+finding and event statistics against the oracle and the reference-generated goldens."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import xmhw_oracle as O
+from tests.util import bit_equal
+from xmhw_b200 import plan as P
+from xmhw_b200 import synth as S
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def em(_built):
+    from xmhw_b200 import _cabi
+    lib = C.CDLL(os.path.join(HERE, "lane_emulator", "_lane_emul.so"))
+    lib.emul_find_events.restype = C.c_int
+    return lib, _cabi
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def sweep(em, ts, doy, ndoy, w, q):
+    lib, cabi = em
+    hp = P.build_clim_plan(doy, ndoy, w, q)
+    s, keep = cabi.numpy_plan_struct(hp)
+    ts = np.ascontiguousarray(ts, np.float32)
+    T, ng = ts.shape
+    thr = np.empty((ndoy, ng))
+    se = np.empty((ndoy, ng))
+    lib.emul_clim_sweep(_vp(ts), C.c_int64(T), C.c_int64(ng), C.byref(s), _vp(thr), _vp(se))
+    return hp, thr, se
+
+
+CASES = [
+    ("30yr", (1982, 2011), 24, 0, 5, 90),
+    ("30yr_nan_p99", (1982, 2011), 24, 20000, 5, 99),
+    ("40yr_split_lists", (1982, 2021), 12, 0, 5, 90),
+    ("noleap_w2", (2001, 2003), 12, 0, 2, 90),
+    ("w0_median", (2001, 2003), 8, 0, 0, 50),
+    ("w15_p10", (2001, 2004), 8, 0, 15, 10),
+]
+
+
+@pytest.mark.parametrize("name,years,ncell,nan_ppm,w,pct", CASES, ids=[c[0] for c in CASES])
+def test_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct):
+    tm = S.daily_time(*years)
+    doy = S.doy366(tm)
+    assert np.array_equal(doy, O.add_doy(tm))
+    ts = S.synth_sst(len(tm), ncell, S.season_table(tm), nan_ppm=nan_ppm)
+    if nan_ppm:
+        ts[100:300, 3] = np.nan
+        ts[:, 5] = np.nan
+        ts[700:, 7] = np.nan
+    hp, thr, se = sweep(em, ts, doy, 366, w, pct / 100.0)
+    oth, ose = O.threshold(ts, doy, 366, pctile=pct, windowHalfWidth=w, smoothPercentile=False, tstep=True)
+    assert bit_equal(thr, oth)
+    assert np.nanmax(np.abs(se - ose), initial=0) <= 1e-12
+    assert hp.rows_loaded < len(doy) * 1.1 and hp.max_size <= 32
+
+
+def test_sweep_pentad_and_reference_cube(em, oisst):
+    doy = np.tile(np.arange(1, 74), 30)
+    ts = S.synth_sst(len(doy), 16, S.season_table(len(doy)))
+    hp, thr, se = sweep(em, ts, doy, 73, 5, 0.9)
+    oth, ose = O.threshold(ts, doy, 73, smoothPercentile=False, tstep=True)
+    assert bit_equal(thr, oth) and np.abs(se - ose).max() <= 1e-12
+    d = O.add_doy(oisst["time"])
+    cube = oisst["sst"].reshape(len(d), -1)
+    hp, thr, se = sweep(em, cube, d, 366, 5, 0.9)
+    oth, ose = O.threshold(cube, d, 366, smoothPercentile=False, tstep=True)
+    assert bit_equal(thr, oth) and bit_equal(se, ose)
+
+
+def test_plan_rejects_unsupported():
+    with pytest.raises(NotImplementedError):
+        P.build_clim_plan(np.tile(np.arange(1, 13), 3), 12, 6, 0.9)     # window wider than a year
+    with pytest.raises(ValueError):
+        P.build_clim_plan(np.array([0, 1, 2]), 3, 1, 0.9)
+    lo, g = P.quantile_table(440, 0.9)
+    olo, og = O.quantile_table(440, 0.9)
+    assert np.array_equal(lo, olo) and np.array_equal(g, og)
+    ptr, tidx = P.doy_csr(np.array([2, 1, 2, 3, 1]), 3)
+    assert ptr.tolist() == [0, 2, 4, 5] and tidx.tolist() == [1, 4, 0, 2, 3]
+
+
+def test_run_finder_fuzz(em):
+    lib, _ = em
+    rng = np.random.default_rng(5)
+    for trial in range(1500):
+        T = int(rng.integers(1, 200))
+        b = (rng.random(T) < rng.uniform(0.05, 0.95)).astype(np.uint8)
+        if trial % 2:
+            b = np.repeat(b, rng.integers(1, 6))[:T].copy()
+            T = len(b)
+        minD = int(rng.integers(1, 8))
+        maxG = int(rng.integers(0, max(1, minD)))
+        join = int(rng.integers(0, 2))
+        s = np.zeros(T + 1, np.int32)
+        e = np.zeros(T + 1, np.int32)
+        n = lib.emul_find_events(_vp(b), T, minD, join, maxG, _vp(s), _vp(e))
+        so, eo = O.find_events(b.astype(bool), minD, bool(join), maxG)
+        assert n == len(so) and np.array_equal(s[:n], so) and np.array_equal(e[:n], eo)
+
+
+def test_event_stats_vs_reference_tables(em, ref_cases):
+    lib, cabi = em
+    nev = 0
+    for c in ref_cases:
+        ts, th, se = c["ts"], c["th"], c["se"]
+        minD, join, maxG = (int(v) for v in c["par"])
+        T = len(ts)
+        doy = np.arange(1, T + 1, dtype=np.int32)
+        b = (ts.astype(np.float64) > th).astype(np.uint8)
+        s = np.zeros(T + 1, np.int32)
+        e = np.zeros(T + 1, np.int32)
+        n = lib.emul_find_events(_vp(b), T, minD, join, maxG, _vp(s), _vp(e))
+        assert n == len(c["index_start"])
+        for k in range(n):
+            oi = np.zeros(cabi.EI_COUNT, np.int32)
+            of = np.zeros(cabi.EF_COUNT)
+            lib.emul_event_stats(_vp(ts), _vp(th), _vp(se), _vp(doy), C.c_int64(1), T, int(s[k]), int(e[k]),
+                                 _vp(oi), _vp(of))
+            for j, f in enumerate(cabi.EI_FIELDS[1:], start=1):
+                ref = c[f][k]
+                assert oi[j] == (-1 if np.isnan(ref) else ref), f
+            for j, f in enumerate(cabi.EF_FIELDS):
+                tol = 5e-6 if f.endswith("_abs") else 1e-9
+                np.testing.assert_allclose(of[j], c[f][k], rtol=tol, atol=tol, equal_nan=True, err_msg=f)
+            nev += 1
+    assert nev > 500

@@ -22,6 +22,26 @@ from ._cabi import EF_COUNT, EF_FIELDS, EI_COUNT, EI_FIELDS, check, lib
 
 _plan_cache = {}
 
+# Optional per-kernel timing (bench.py): when TRACE is a list, every library call is
+# bracketed by CUDA events on the launch stream and (name, start, end) is appended.
+TRACE = None
+LAUNCHES = {"n": 0}
+_KERNELS_PER_CALL = {"xmhw_exclusive_scan_i32": 3}
+
+
+def _call(name, *args):
+    fn = getattr(lib, name)
+    LAUNCHES["n"] += _KERNELS_PER_CALL.get(name, 1)
+    if TRACE is None:
+        check(fn(*args), name)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(*args), name)
+    e1.record()
+    TRACE.append((name, e0, e1))
+
 
 def _ptr(t):
     return t.data_ptr()
@@ -107,8 +127,7 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
         st = _stream()
         raw_t = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
         raw_s = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
-        check(lib.xmhw_clim_sweep_f32(_ptr(ts), T, ngrid, dp.struct, _ptr(raw_t), _ptr(raw_s), st),
-              "xmhw_clim_sweep_f32")
+        _call("xmhw_clim_sweep_f32", _ptr(ts), T, ngrid, dp.struct, _ptr(raw_t), _ptr(raw_s), st)
         W = int(smoothPercentileWidth) if smoothPercentile else 1
         do_feb = bool(feb29) and ndoy >= 61
         if W <= 1 and not do_feb:
@@ -116,8 +135,7 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
         out_t = torch.empty_like(raw_t)
         out_s = torch.empty_like(raw_s)
         for raw, out in ((raw_t, out_t), (raw_s, out_s)):
-            check(lib.xmhw_clim_finish_f64(_ptr(raw), _ptr(out), ndoy, ngrid, int(do_feb), W, st),
-                  "xmhw_clim_finish_f64")
+            _call("xmhw_clim_finish_f64", _ptr(raw), _ptr(out), ndoy, ngrid, int(do_feb), W, st)
     return (out_t, out_s, raw_t, raw_s) if return_raw else (out_t, out_s)
 
 
@@ -174,24 +192,23 @@ def detect_arrays(ts, doy, ndoy, thresh, seas, minDuration=5, joinGaps=True, max
         ncg = (ngrid + 31) // 32
         mask = torch.empty((ncg, T), dtype=torch.int32, device=dev)
         nvalid = torch.zeros(ngrid, dtype=torch.int32, device=dev)
-        check(lib.xmhw_exceed_mask_f32(_ptr(ts), T, ngrid, _ptr(ptr), _ptr(tidx), ndoy, _ptr(thresh),
-                                       _ptr(mask), _ptr(nvalid), st), "xmhw_exceed_mask_f32")
+        _call("xmhw_exceed_mask_f32", _ptr(ts), T, ngrid, _ptr(ptr), _ptr(tidx), ndoy, _ptr(thresh),
+                                       _ptr(mask), _ptr(nvalid), st)
         counts = torch.empty(ngrid, dtype=torch.int32, device=dev)
-        check(lib.xmhw_events_count(_ptr(mask), T, ngrid, int(minDuration), int(bool(joinGaps)), int(maxGap),
-                                    _ptr(counts), st), "xmhw_events_count")
+        _call("xmhw_events_count", _ptr(mask), T, ngrid, int(minDuration), int(bool(joinGaps)), int(maxGap),
+                                    _ptr(counts), st)
         offsets = torch.empty(ngrid + 1, dtype=torch.int64, device=dev)
         scratch = torch.empty(ngrid // 1024 + 2, dtype=torch.int64, device=dev)
-        check(lib.xmhw_exclusive_scan_i32(_ptr(counts), ngrid, _ptr(offsets), _ptr(scratch), st),
-              "xmhw_exclusive_scan_i32")
+        _call("xmhw_exclusive_scan_i32", _ptr(counts), ngrid, _ptr(offsets), _ptr(scratch), st)
         nev = int(offsets[-1].item())          # the one host sync: sizes the event table
         cap = max(nev, 1)
         ev_i32 = torch.empty((EI_COUNT, cap), dtype=torch.int32, device=dev)
         ev_f64 = torch.empty((EF_COUNT, cap), dtype=torch.float64, device=dev)
         if nev:
-            check(lib.xmhw_events_fill(_ptr(mask), T, ngrid, int(minDuration), int(bool(joinGaps)), int(maxGap),
-                                       _ptr(offsets), cap, _ptr(ev_i32), st), "xmhw_events_fill")
-            check(lib.xmhw_event_stats_f32(_ptr(ts), T, ngrid, _ptr(doy32), _ptr(thresh), _ptr(seas), nev, cap,
-                                           _ptr(ev_i32), _ptr(ev_f64), st), "xmhw_event_stats_f32")
+            _call("xmhw_events_fill", _ptr(mask), T, ngrid, int(minDuration), int(bool(joinGaps)), int(maxGap),
+                                       _ptr(offsets), cap, _ptr(ev_i32), st)
+            _call("xmhw_event_stats_f32", _ptr(ts), T, ngrid, _ptr(doy32), _ptr(thresh), _ptr(seas), nev, cap,
+                                           _ptr(ev_i32), _ptr(ev_f64), st)
     return EventTable(ev_i32, ev_f64, nev, offsets, nvalid, T, ngrid)
 
 
@@ -205,8 +222,45 @@ def synth_sst_device(T, ngrid, season, land=None, cell0=0, seed=None, nan_ppm=0,
         if sea.numel() < T + 366:
             raise ValueError("season table must have T + 366 entries")
         ld = None if land is None else torch.from_numpy(np.ascontiguousarray(land, np.uint8).ravel()).to(dev)
-        check(lib.xmhw_synth_sst_f32(_ptr(ts), T, ngrid, int(cell0), 0 if ld is None else _ptr(ld), _ptr(sea),
+        _call("xmhw_synth_sst_f32", _ptr(ts), T, ngrid, int(cell0), 0 if ld is None else _ptr(ld), _ptr(sea),
                                      synth.SEED if seed is None else int(seed), synth.RHO, synth.SIGMA,
-                                     synth.NOISE_SCALE, int(nan_ppm), _stream()), "xmhw_synth_sst_f32")
+                                     synth.NOISE_SCALE, int(nan_ppm), _stream())
         torch.cuda.current_stream().synchronize()   # keep `sea`/`ld` alive until the kernel is done
     return ts
+
+
+def threshold_detect_host(ts_host, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercentile=True,
+                          smoothPercentileWidth=31, feb29=True, minDuration=5, joinGaps=True, maxGap=2,
+                          device="cuda", out=None):
+    """Host-buffer entry point (what the reference-side binding calls): `ts_host` is a
+    (pinned) host float32 tensor/array [T, ngrid]; the series is copied to the device,
+    threshold + detect run there, and thresh/seas/event table are copied back to host
+    memory.  Returns dict(thresh, seas, nvalid, events) of host arrays plus byte counts.
+    `out` may hold preallocated pinned result tensors ('thresh', 'seas') to reuse."""
+    dev = torch.device(device)
+    if isinstance(ts_host, np.ndarray):
+        ts_host = torch.from_numpy(ts_host)
+    if ts_host.dtype != torch.float32 or ts_host.dim() != 2:
+        raise TypeError("ts_host must be float32 [T, ngrid]")
+    T, ngrid = ts_host.shape
+    with torch.cuda.device(dev):
+        ts = torch.empty((T, ngrid), dtype=torch.float32, device=dev)
+        ts.copy_(ts_host, non_blocking=True)
+        th, se = threshold_arrays(ts, doy, ndoy, pctile, windowHalfWidth, smoothPercentile,
+                                  smoothPercentileWidth, feb29)
+        ev = detect_arrays(ts, doy, ndoy, th, se, minDuration, joinGaps, maxGap)
+        res = {}
+        if out is not None and "thresh" in out:
+            out["thresh"].copy_(th, non_blocking=True)
+            out["seas"].copy_(se, non_blocking=True)
+            res["thresh"], res["seas"] = out["thresh"], out["seas"]
+        else:
+            res["thresh"], res["seas"] = th.cpu(), se.cpu()
+        res["nvalid"] = ev.nvalid.cpu()
+        res["ev_i32"] = ev.i32[:, :ev.n].cpu()
+        res["ev_f64"] = ev.f64[:, :ev.n].cpu()
+        torch.cuda.current_stream().synchronize()
+    res["n_events"] = ev.n
+    res["h2d_bytes"] = T * ngrid * 4
+    res["d2h_bytes"] = 2 * ndoy * ngrid * 8 + ngrid * 4 + ev.n * (EI_COUNT * 4 + EF_COUNT * 8)
+    return res

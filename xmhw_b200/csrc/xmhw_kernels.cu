@@ -19,6 +19,12 @@ using namespace xmhw;
 
 struct WarpEnv {
   __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
+  // warp-cooperative copy of the step's list bases into shared memory (0 = null list)
+  __device__ __forceinline__ void stage(uint32_t* ub, const int32_t* src, int m, int m4, int lane) const {
+    __syncwarp();
+    for (int i = lane; i < m4; i += 32) ub[i] = i < m ? (uint32_t)__ldg(src + i) : 0u;
+    __syncwarp();
+  }
 };
 
 static_assert(sizeof(xmhw_clim_plan) == sizeof(ClimPlan), "plan ABI mismatch");
@@ -37,12 +43,12 @@ __global__ void __launch_bounds__(32) clim_sweep_kernel(ClimPlan p, const float*
   const int64_t cell = (int64_t)blockIdx.x * 32 + lane;
   const bool ok = cell < ngrid;
   const float* col = ts + (ok ? cell : 0);
-  SweepState st;
-  st.C = 0; st.n = 0; st.pivot = 0xffffffffu;
   WarpEnv env;
+  Sweeper<WarpEnv> sw(env, p, pool, lane, col, ngrid, ok);
+  sw.init();
   for (int s = 0; s < p.nsteps; ++s) {
     double a, b;
-    sweep_step(env, p, s, st, pool, lane, col, ngrid, ok, a, b);
+    sw.step(s, a, b);
     if (ok) {
       thr[(int64_t)s * ngrid + cell] = a;
       seas[(int64_t)s * ngrid + cell] = b;
@@ -337,7 +343,7 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
                         double* thresh_raw, double* seas_raw, void* stream) {
   if (!ts || !plan || !thresh_raw || !seas_raw || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
   if (plan->nsteps <= 0 || plan->pool_rows <= 0 || plan->max_size > 32 || plan->nmax <= 0) return XMHW_E_PLAN;
-  const size_t smem = (size_t)plan->pool_rows * 128;
+  const size_t smem = (size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 128;
   if (smem > 227 * 1024) return XMHW_E_SMEM;
   cudaError_t e = cudaFuncSetAttribute(clim_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

@@ -120,8 +120,13 @@ struct ClimPlan {
 // Instance block layout in the pool (row = 32 words, word index = lane):
 //   row 0      meta: len | ptr << 8   (len = valid samples, ptr = #keys above the cut)
 //   row 1, 2   f64 sum of the valid samples (lo, hi words)
-//   row 3 + r  r-th largest key (r < size); invalid samples are key 0 at the end
-enum { POOL_META = 0, POOL_SUM = 1, POOL_KEYS = 3 };
+//   row 3      cinc: smallest key above the cut (key[ptr-1]), 0xffffffff if ptr == 0
+//   row 4      cexc: largest key below the cut (key[ptr]),    0 if ptr == len
+//   row 5 + r  r-th largest key (r < size); invalid samples are key 0 at the end
+// Block 0 of every pool is a "null list" (len 0) used to pad scans to multiples of 4;
+// the two rows after plan.pool_rows hold the staged base rows of the lists in use.
+enum { POOL_META = 0, POOL_SUM = 1, POOL_CINC = 3, POOL_CEXC = 4, POOL_KEYS = 5, POOL_NULL_ROWS = 5,
+       POOL_STAGE_ROWS = 2, MAX_LISTS = 64 };
 
 #ifdef __CUDA_ARCH__
 #define XMHW_LDG(p) __ldg(p)
@@ -131,56 +136,11 @@ enum { POOL_META = 0, POOL_SUM = 1, POOL_KEYS = 3 };
 
 #define XMHW_CE(i, j) { uint32_t hi_ = k[i] > k[j] ? k[i] : k[j]; uint32_t lo_ = k[i] > k[j] ? k[j] : k[i]; k[i] = hi_; k[j] = lo_; }
 
-template <int N> XMHW_HD void sort_desc(uint32_t (&k)[N]);
-template <> XMHW_HD void sort_desc<4>(uint32_t (&k)[4]) { XMHW_SORTNET_4 }
-template <> XMHW_HD void sort_desc<8>(uint32_t (&k)[8]) { XMHW_SORTNET_8 }
-template <> XMHW_HD void sort_desc<12>(uint32_t (&k)[12]) { XMHW_SORTNET_12 }
-template <> XMHW_HD void sort_desc<16>(uint32_t (&k)[16]) { XMHW_SORTNET_16 }
-template <> XMHW_HD void sort_desc<20>(uint32_t (&k)[20]) { XMHW_SORTNET_20 }
-template <> XMHW_HD void sort_desc<24>(uint32_t (&k)[24]) { XMHW_SORTNET_24 }
-template <> XMHW_HD void sort_desc<28>(uint32_t (&k)[28]) { XMHW_SORTNET_28 }
-template <> XMHW_HD void sort_desc<32>(uint32_t (&k)[32]) { XMHW_SORTNET_32 }
-
-// Load one instance (size <= N rows) for this lane's cell, convert to keys,
-// accumulate the f64 sum in row order, sort descending, store into the pool.
-// Returns the number of valid (non-NaN) samples.  `any` = warp-uniform vote.
-template <int N, class Env>
-XMHW_HD int load_sort_store(const Env& env, uint32_t* pool, int lane, int base, int size,
-                            const int32_t* rows, const float* col, int64_t ngrid, bool ok) {
-  float v[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    v[i] = bits_f32(0x7fc00000u);
-    if (i < size && ok) v[i] = XMHW_LDG(col + (int64_t)XMHW_LDG(rows + i) * ngrid);
-  }
-  uint32_t k[N];
-  int len = 0;
-  double sum = 0.0;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    k[i] = f32_key(v[i]);
-    if (k[i] != 0u) { ++len; sum = sum + (double)v[i]; }
-  }
-  if (env.any(len > 0)) {
-    sort_desc<N>(k);
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-      if (i < size) pool[(base + POOL_KEYS + i) * 32 + lane] = k[i];
-  }
-  pool[(base + POOL_SUM) * 32 + lane] = f64_lo(sum);
-  pool[(base + POOL_SUM + 1) * 32 + lane] = f64_hi(sum);
-  return len;
-}
-
-// number of keys of the instance strictly above the pivot key (keys descending)
-XMHW_HD int count_above(const uint32_t* pool, int lane, int base, int len, uint32_t pivot) {
-  int lo = 0, hi = len;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (pool[(base + POOL_KEYS + mid) * 32 + lane] > pivot) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
+template <int N> XMHW_HD void sort_desc(uint32_t* k);
+template <> XMHW_HD void sort_desc<8>(uint32_t* k) { XMHW_SORTNET_8 }
+template <> XMHW_HD void sort_desc<16>(uint32_t* k) { XMHW_SORTNET_16 }
+template <> XMHW_HD void sort_desc<24>(uint32_t* k) { XMHW_SORTNET_24 }
+template <> XMHW_HD void sort_desc<32>(uint32_t* k) { XMHW_SORTNET_32 }
 
 // numpy _lerp (lib/_function_base_impl.py): d = b - a in float32, result in
 // float64 with two roundings, no FMA (the .cu is compiled with --fmad=false).
@@ -192,118 +152,210 @@ XMHW_HD double lerp_q(float a, float b, double g) {
   return g >= 0.5 ? hi : lo;
 }
 
-// Persistent per-lane state of the doy sweep.
-struct SweepState {
-  int C;            // keys currently above the cut (sum of ptr over lists in use)
-  int n;            // valid samples in the window (sum of len)
-  uint32_t pivot;   // key of the smallest sample above the cut (cut value)
-};
+// number of keys of an instance strictly above the pivot key (keys descending)
+XMHW_HD int count_above(const uint32_t* pool, int lane, int base, int len, uint32_t pivot) {
+  int lo = 0, hi = len;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (pool[(base + POOL_KEYS + mid) * 32 + lane] > pivot) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
 
-// One sweep step for one lane: update the window (leave / enter), move the cut
-// to the rank numpy's linear quantile needs, return thresh and seas for this doy.
-//
-// Selection = k-th largest of a union of sorted lists.  Each list keeps ptr =
-// number of its keys above the cut; the cut is "consistent" (every key above it
-// >= every key below it).  A list entering the window gets ptr by binary search
-// against the current cut value, which keeps the cut consistent; then single
-// moves (drop the smallest key above / add the largest key below) restore
-// C == target.  Consecutive doys share 10 of 11 lists, so only a few moves are
-// needed (vs. sorting ~330 samples per doy).
+// Doy sweep of one lane (= one grid cell).  Selection = k-th largest of a union of
+// sorted lists: each list keeps ptr = number of its keys above the cut, the cut is
+// "consistent" (every key above it >= every key below it).  A list entering the
+// window gets ptr by comparison with the current cut value, which keeps the cut
+// consistent; then single moves (add the largest key below the cut / drop the
+// smallest key above it) restore C == target rank.  Consecutive doys share all but
+// one list, so a few moves replace a sort of ~330 samples per doy.  Each list
+// caches its two keys adjacent to the cut (cinc/cexc rows), so one scan over the
+// lists in use is one shared-memory load + compare/select per list.
 template <class Env>
-XMHW_HD void sweep_step(const Env& env, const ClimPlan& p, int s, SweepState& st, uint32_t* pool,
-                        int lane, const float* col, int64_t ngrid, bool ok,
-                        double& thresh, double& seas) {
-  for (int j = XMHW_LDG(p.leave_off + s); j < XMHW_LDG(p.leave_off + s + 1); ++j) {
-    uint32_t meta = pool[(XMHW_LDG(p.leave + j) + POOL_META) * 32 + lane];
-    st.C -= (int)((meta >> 8) & 0xffu);
-    st.n -= (int)(meta & 0xffu);
-  }
-  for (int j = XMHW_LDG(p.enter_off + s); j < XMHW_LDG(p.enter_off + s + 1); ++j) {
-    int e = XMHW_LDG(p.enter + j);
-    int id = e & 0x3fffffff;
-    int base = XMHW_LDG(p.inst_base + id);
-    int size = XMHW_LDG(p.inst_size + id);
-    int len;
-    if (e >> 30) {
-      const int32_t* rows = p.rows + XMHW_LDG(p.inst_row_off + id);
-      if (size <= 8) len = load_sort_store<8>(env, pool, lane, base, size, rows, col, ngrid, ok);
-      else if (size <= 16) len = load_sort_store<16>(env, pool, lane, base, size, rows, col, ngrid, ok);
-      else if (size <= 24) len = load_sort_store<24>(env, pool, lane, base, size, rows, col, ngrid, ok);
-      else len = load_sort_store<32>(env, pool, lane, base, size, rows, col, ngrid, ok);
-    } else {
-      len = (int)(pool[(base + POOL_META) * 32 + lane] & 0xffu);
-    }
-    int ptr = count_above(pool, lane, base, len, st.pivot);
-    pool[(base + POOL_META) * 32 + lane] = (uint32_t)len | ((uint32_t)ptr << 8);
-    st.C += ptr;
-    st.n += len;
-  }
-  const int u0 = XMHW_LDG(p.use_off + s), u1 = XMHW_LDG(p.use_off + s + 1);
-  const bool live = st.n > 0;
-  int target = 0;
-  double gamma = 0.0;
-  if (live) {
-    target = st.n - XMHW_LDG(p.q_lo + st.n);   // rank (1-based, from the top) of s[floor v]
-    gamma = XMHW_LDG(p.q_gamma + st.n);
-  }
-  if (!env.any(live)) { thresh = qnan(); seas = qnan(); return; }   // all-land warp
-  // phase 1: lanes with too few keys above the cut add the largest key below it
-  while (env.any(live && st.C < target)) {
-    uint32_t best = 0u; int bbase = -1; uint32_t bmeta = 0u;
-    for (int j = u0; j < u1; ++j) {
-      int base = XMHW_LDG(p.use + j);
-      uint32_t meta = pool[(base + POOL_META) * 32 + lane];
-      int len = (int)(meta & 0xffu), ptr = (int)((meta >> 8) & 0xffu);
-      uint32_t k = ptr < len ? pool[(base + POOL_KEYS + ptr) * 32 + lane] : 0u;
-      if (k > best) { best = k; bbase = base; bmeta = meta; }
-    }
-    if (live && st.C < target && bbase >= 0) {
-      pool[(bbase + POOL_META) * 32 + lane] = bmeta + 0x100u;
-      ++st.C;
+struct Sweeper {
+  const Env& env;
+  const ClimPlan& p;
+  uint32_t* pool;
+  const int lane;
+  const float* col;
+  const int64_t ngrid;
+  const bool ok;
+  int C, n;              // keys above the cut / valid samples, over the lists in use
+  uint32_t pivot;        // cut value (key of the smallest sample above the cut)
+  float pv[32];          // prefetched rows of the next instance to load
+  int pf;                // index into plan.enter of that instance (or total)
+  int total_enter;
+
+  XMHW_HD Sweeper(const Env& e, const ClimPlan& pl, uint32_t* po, int ln, const float* c, int64_t ng, bool k)
+      : env(e), p(pl), pool(po), lane(ln), col(c), ngrid(ng), ok(k), C(0), n(0), pivot(0xffffffffu) {}
+
+  XMHW_HD uint32_t& at(int row) { return pool[row * 32 + lane]; }
+
+  XMHW_HD void prefetch(int from) {
+    int j = from;
+    while (j < total_enter && !(XMHW_LDG(p.enter + j) >> 30)) ++j;
+    pf = j;
+    if (j >= total_enter) return;
+    const int id = XMHW_LDG(p.enter + j) & 0x3fffffff;
+    const int size = XMHW_LDG(p.inst_size + id);
+    const int32_t* rows = p.rows + XMHW_LDG(p.inst_row_off + id);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      pv[i] = bits_f32(0x7fc00000u);
+      if (i < size && ok) pv[i] = XMHW_LDG(col + (int64_t)XMHW_LDG(rows + i) * ngrid);
     }
   }
-  // phase 2: lanes with too many drop the smallest key above the cut; lanes on
-  // target read a = smallest key above the cut and b = next one up.
-  uint32_t ka = 0u, kb = 0u;
-  bool done = !live;
-  while (true) {
-    uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu; int b1 = -1; uint32_t meta1 = 0u;
-    for (int j = u0; j < u1; ++j) {
-      int base = XMHW_LDG(p.use + j);
-      uint32_t meta = pool[(base + POOL_META) * 32 + lane];
-      int ptr = (int)((meta >> 8) & 0xffu);
-      uint32_t k = ptr > 0 ? pool[(base + POOL_KEYS + ptr - 1) * 32 + lane] : 0xffffffffu;
-      if (k < m1) { m2 = m1; m1 = k; b1 = base; meta1 = meta; }
-      else if (k < m2) m2 = k;
+
+  // keys of the prefetched instance -> sorted block in the pool; returns (len, ptr)
+  template <int N>
+  XMHW_HD void consume(int base, int size, int& len, int& ptr) {
+    uint32_t k[32];
+    len = 0;
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      k[i] = f32_key(pv[i]);
+      if (k[i] != 0u) { ++len; sum = sum + (double)pv[i]; }
     }
-    if (!done) {
-      if (st.C > target) {
-        pool[(b1 + POOL_META) * 32 + lane] = meta1 - 0x100u;
-        --st.C;
-      } else {
-        int ptr1 = (int)((meta1 >> 8) & 0xffu);
-        uint32_t c2 = ptr1 >= 2 ? pool[(b1 + POOL_KEYS + ptr1 - 2) * 32 + lane] : 0xffffffffu;
-        ka = m1;
-        kb = target >= 2 ? (c2 < m2 ? c2 : m2) : m1;
-        done = true;
+    ptr = 0;
+    if (env.any(len > 0)) {
+      sort_desc<N>(k);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if (i < size) at(base + POOL_KEYS + i) = k[i];
+        ptr += k[i] > pivot;
       }
     }
-    if (!env.any(!done)) break;
+    at(base + POOL_SUM) = f64_lo(sum);
+    at(base + POOL_SUM + 1) = f64_hi(sum);
   }
-  if (live) {
-    st.pivot = ka;
-    thresh = lerp_q(key_f32(ka), key_f32(kb), gamma);
-    double sum = 0.0;
-    for (int j = u0; j < u1; ++j) {
-      int base = XMHW_LDG(p.use + j);
-      sum = sum + f64_from(pool[(base + POOL_SUM) * 32 + lane], pool[(base + POOL_SUM + 1) * 32 + lane]);
+
+  XMHW_HD void set_block(int base, int len, int ptr) {
+    at(base + POOL_META) = (uint32_t)len | ((uint32_t)ptr << 8);
+    at(base + POOL_CINC) = ptr > 0 ? at(base + POOL_KEYS + ptr - 1) : 0xffffffffu;
+    at(base + POOL_CEXC) = ptr < len ? at(base + POOL_KEYS + ptr) : 0u;
+  }
+
+  XMHW_HD void init() {
+    at(POOL_META) = 0u; at(POOL_SUM) = 0u; at(POOL_SUM + 1) = 0u;
+    at(POOL_CINC) = 0xffffffffu; at(POOL_CEXC) = 0u;
+    total_enter = XMHW_LDG(p.enter_off + p.nsteps);
+    prefetch(0);
+  }
+
+  XMHW_HD void step(int s, double& thresh, double& seas) {
+    for (int j = XMHW_LDG(p.leave_off + s); j < XMHW_LDG(p.leave_off + s + 1); ++j) {
+      uint32_t meta = at(XMHW_LDG(p.leave + j) + POOL_META);
+      C -= (int)((meta >> 8) & 0xffu);
+      n -= (int)(meta & 0xffu);
     }
-    seas = sum / (double)st.n;
-  } else {
-    thresh = qnan();
-    seas = qnan();
+    for (int j = XMHW_LDG(p.enter_off + s); j < XMHW_LDG(p.enter_off + s + 1); ++j) {
+      const int e = XMHW_LDG(p.enter + j);
+      const int id = e & 0x3fffffff;
+      const int base = XMHW_LDG(p.inst_base + id);
+      const int size = XMHW_LDG(p.inst_size + id);
+      int len, ptr;
+      if (e >> 30) {
+        if (size <= 8) consume<8>(base, size, len, ptr);
+        else if (size <= 16) consume<16>(base, size, len, ptr);
+        else if (size <= 24) consume<24>(base, size, len, ptr);
+        else consume<32>(base, size, len, ptr);
+        prefetch(j + 1);
+      } else {
+        len = (int)(at(base + POOL_META) & 0xffu);
+        ptr = count_above(pool, lane, base, len, pivot);
+      }
+      set_block(base, len, ptr);
+      C += ptr;
+      n += len;
+    }
+    // stage the base rows of the lists in use (padded to a multiple of 4 with the null list)
+    const int u0 = XMHW_LDG(p.use_off + s);
+    const int m = XMHW_LDG(p.use_off + s + 1) - u0;
+    const int m4 = (m + 3) & ~3;
+    uint32_t* ub = pool + p.pool_rows * 32;
+    env.stage(ub, p.use + u0, m, m4, lane);
+
+    const bool live = n > 0;
+    if (!env.any(live)) { thresh = qnan(); seas = qnan(); return; }   // all-land warp
+    int target = 0;
+    double gamma = 0.0;
+    if (live) {
+      target = n - XMHW_LDG(p.q_lo + n);   // rank (1-based, from the top) of s[floor v]
+      gamma = XMHW_LDG(p.q_gamma + n);
+    }
+    // phase 1: lanes with too few keys above the cut add the largest key below it
+    while (env.any(live && C < target)) {
+      uint32_t b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;
+      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (int j = 0; j < m4; j += 4) {
+        const int x0 = (int)ub[j], x1 = (int)ub[j + 1], x2 = (int)ub[j + 2], x3 = (int)ub[j + 3];
+        const uint32_t k0 = at(x0 + POOL_CEXC), k1 = at(x1 + POOL_CEXC), k2 = at(x2 + POOL_CEXC), k3 = at(x3 + POOL_CEXC);
+        if (k0 > b0) { b0 = k0; a0 = x0; }
+        if (k1 > b1) { b1 = k1; a1 = x1; }
+        if (k2 > b2) { b2 = k2; a2 = x2; }
+        if (k3 > b3) { b3 = k3; a3 = x3; }
+      }
+      if (b1 > b0) { b0 = b1; a0 = a1; }
+      if (b3 > b2) { b2 = b3; a2 = a3; }
+      if (b2 > b0) { b0 = b2; a0 = a2; }
+      if (live && C < target) {      // b0 > 0 is guaranteed: C < target <= n
+        const uint32_t meta = at(a0 + POOL_META);
+        const int len = (int)(meta & 0xffu), ptr = (int)((meta >> 8) & 0xffu) + 1;
+        at(a0 + POOL_META) = meta + 0x100u;
+        at(a0 + POOL_CINC) = b0;
+        at(a0 + POOL_CEXC) = ptr < len ? at(a0 + POOL_KEYS + ptr) : 0u;
+        ++C;
+      }
+    }
+    // phase 2: lanes with too many drop the smallest key above the cut
+    while (env.any(live && C > target)) {
+      uint32_t b0 = 0xffffffffu, b1 = 0xffffffffu, b2 = 0xffffffffu, b3 = 0xffffffffu;
+      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (int j = 0; j < m4; j += 4) {
+        const int x0 = (int)ub[j], x1 = (int)ub[j + 1], x2 = (int)ub[j + 2], x3 = (int)ub[j + 3];
+        const uint32_t k0 = at(x0 + POOL_CINC), k1 = at(x1 + POOL_CINC), k2 = at(x2 + POOL_CINC), k3 = at(x3 + POOL_CINC);
+        if (k0 < b0) { b0 = k0; a0 = x0; }
+        if (k1 < b1) { b1 = k1; a1 = x1; }
+        if (k2 < b2) { b2 = k2; a2 = x2; }
+        if (k3 < b3) { b3 = k3; a3 = x3; }
+      }
+      if (b1 < b0) { b0 = b1; a0 = a1; }
+      if (b3 < b2) { b2 = b3; a2 = a3; }
+      if (b2 < b0) { b0 = b2; a0 = a2; }
+      if (live && C > target) {
+        const uint32_t meta = at(a0 + POOL_META);
+        const int ptr = (int)((meta >> 8) & 0xffu) - 1;
+        at(a0 + POOL_META) = meta - 0x100u;
+        at(a0 + POOL_CEXC) = b0;
+        at(a0 + POOL_CINC) = ptr > 0 ? at(a0 + POOL_KEYS + ptr - 1) : 0xffffffffu;
+        --C;
+      }
+    }
+    // final scan: a = smallest key above the cut, b = next one up; f64 sum of the window
+    uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu;
+    int a1 = 0;
+    double sum = 0.0;
+    for (int j = 0; j < m4; ++j) {
+      const int x = (int)ub[j];
+      const uint32_t k = at(x + POOL_CINC);
+      if (k < m1) { m2 = m1; m1 = k; a1 = x; }
+      else if (k < m2) m2 = k;
+      sum = sum + f64_from(at(x + POOL_SUM), at(x + POOL_SUM + 1));
+    }
+    if (live) {
+      const int ptr1 = (int)((at(a1 + POOL_META) >> 8) & 0xffu);
+      const uint32_t c2 = ptr1 >= 2 ? at(a1 + POOL_KEYS + ptr1 - 2) : 0xffffffffu;
+      const uint32_t kb = target >= 2 ? (c2 < m2 ? c2 : m2) : m1;
+      pivot = m1;
+      thresh = lerp_q(key_f32(m1), key_f32(kb), gamma);
+      seas = sum / (double)n;
+    } else {
+      thresh = qnan();
+      seas = qnan();
+    }
   }
-}
+};
 
 // ---------------------------------------------------------------------------
 // event finding (identify.py:415-479 mhw_filter, :273-325 join_gaps)

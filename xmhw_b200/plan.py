@@ -28,7 +28,10 @@ from dataclasses import dataclass
 import numpy as np
 
 MAX_LIST = 32          # rows per instance = keys per register sorting network
-META_ROWS = 3          # meta word + f64 sum (2 words) per instance and lane
+META_ROWS = 5          # meta word, f64 sum (2 words), cinc, cexc per instance and lane
+NULL_ROWS = 5          # block 0 of the pool is the kernel's null list
+STAGE_ROWS = 2         # two rows after the pool: staged bases of the lists in use
+MAX_LISTS = 64
 LOAD_FLAG = 1 << 30
 MAX_GAP_STEPS = 2      # a class stays resident across holes of up to this many sweep steps
 
@@ -58,7 +61,7 @@ class ClimPlanHost:
     max_lists: int = 0
 
     def smem_bytes(self):
-        return self.pool_rows * 128
+        return (self.pool_rows + STAGE_ROWS) * 128
 
 
 def quantile_table(nmax, q):
@@ -125,7 +128,7 @@ def build_clim_plan(doy, ndoy, w, q):
             in_use[s].append(i)
 
     # static pool allocation (first fit over the sweep)
-    free = [(0, 1 << 30)]
+    free = [(NULL_ROWS, 1 << 30)]
     base = np.zeros(ninst, np.int32)
     pool_rows = 0
     release_at = [[] for _ in range(ndoy + 1)]
@@ -185,6 +188,8 @@ def build_clim_plan(doy, ndoy, w, q):
         use_off.append(len(use))
         prev_use = cur_set
 
+    if max_lists > MAX_LISTS:
+        raise NotImplementedError("more than %d sorted lists per window (windowHalfWidth too large)" % MAX_LISTS)
     sizes = np.array([len(it["rows"]) for it in insts], np.int32)
     row_off = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)
     rows = np.concatenate([it["rows"] for it in insts]).astype(np.int32)

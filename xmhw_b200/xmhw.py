@@ -1,0 +1,338 @@
+"""Drop-in public API: `threshold` and `detect` with the reference's signatures
+(xmhw/xmhw.py:38-51 and :310-323), same keyword meaning, same XmhwException conditions.
+
+    from xmhw_b200.xmhw import threshold, detect
+    clim = threshold(sst)                                   # Dataset{thresh, seas} (doy, lat, lon)
+    mhw  = detect(sst, clim['thresh'], clim['seas'])        # Dataset (events, lat, lon)
+
+Inputs may be `xarray.DataArray`s or `xmhw_b200.labeled.DataArray`s (xarray is not part
+of this image); outputs are xarray objects when xarray is importable and labeled ones
+otherwise.  The per-cell loops of the reference (xmhw.py:184-197, :440-454) are replaced
+by batched CUDA kernels (xmhw_b200.core); everything here is validation, layout
+(stack sorted non-time dims into `cell`, identify.py:520) and result assembly.
+"""
+import warnings
+
+import numpy as np
+
+from . import labeled
+from .exception import XmhwException
+from .features import EVENT_VARIABLES, FLOAT32_VARIABLES, flip_cold
+from .identify import add_doy, annotate_ds, get_calendar, land_check_shape
+
+DENSE_LIMIT_BYTES = 8 << 30
+
+
+def _coord(temp, name):
+    c = temp.coords[name] if name in getattr(temp, "coords", {}) else None
+    if c is None:
+        return None
+    return np.asarray(getattr(c, "values", c))
+
+
+def _unpack(temp, tdim):
+    """-> (data [T, ...sorted dims] float32, time values, sorted dims, their coords, attrs)"""
+    dims = list(temp.dims)
+    if tdim not in dims:
+        raise XmhwException(f"{tdim} dimension not present, default"
+                            + "is 'time' or pass as tdim='time_dimension_name'")
+    data = np.asarray(temp.values)
+    time = _coord(temp, tdim)
+    if time is None:
+        raise XmhwException(f"{tdim} coordinate values are required to build the day-of-year axis")
+    other = sorted(d for d in dims if d != tdim)
+    order = [dims.index(tdim)] + [dims.index(d) for d in other]
+    data = np.transpose(data, order)
+    if data.dtype != np.float32:
+        if data.dtype == np.float64:
+            warnings.warn("xmhw_b200 computes on float32 series; float64 input is rounded to float32")
+        data = data.astype(np.float32)
+    coords = {}
+    for d, n in zip(other, data.shape[1:]):
+        c = _coord(temp, d)
+        coords[d] = np.arange(n) if c is None else c
+    enc = getattr(getattr(temp, "coords", {}).get(tdim, None), "encoding", None) or getattr(temp, "encoding", {})
+    tattrs = getattr(getattr(temp, "coords", {}).get(tdim, None), "attrs", None) or {}
+    return np.ascontiguousarray(data), time, other, coords, dict(getattr(temp, "attrs", {})), enc, tattrs
+
+
+def _interp_gaps(ts, max_pad):
+    """Pre-step `interpolate_na(dim=tdim, max_gap=maxPadLength)` (xmhw.py:159-160, :409-410):
+    linear interpolation along time of NaN runs no longer than max_pad steps (host-side
+    pre-step; not part of the timed hot path)."""
+    T = ts.shape[0]
+    flat = ts.reshape(T, -1)
+    idx = np.arange(T)
+    for c in range(flat.shape[1]):
+        col = flat[:, c]
+        nan = np.isnan(col)
+        if not nan.any() or nan.all():
+            continue
+        good = ~nan
+        filled = np.interp(idx, idx[good], col[good]).astype(np.float32)
+        # only interior gaps of length <= max_pad
+        edges = np.diff(np.concatenate(([0], nan.view(np.int8), [0])))
+        starts, ends = np.nonzero(edges == 1)[0], np.nonzero(edges == -1)[0]
+        for s, e in zip(starts, ends):
+            if s > 0 and e < T and (e - s) <= max_pad:
+                col[s:e] = filled[s:e]
+    return ts
+
+
+def _wrap(ds, like):
+    if labeled.is_xarray(like):
+        try:
+            return labeled.to_xarray(ds)
+        except ImportError:
+            pass
+    return ds
+
+
+def _present(mask_nd):
+    """Index vectors of the coordinate values that survive `unstack` (xmhw.py:213-214):
+    rows/columns without any ocean cell vanish."""
+    keep = []
+    for ax in range(mask_nd.ndim):
+        other = tuple(a for a in range(mask_nd.ndim) if a != ax)
+        keep.append(np.nonzero(mask_nd.any(axis=other))[0] if other else np.nonzero(mask_nd)[0])
+    return keep
+
+
+def threshold(temp, tdim="time", climatologyPeriod=[None, None], pctile=90, windowHalfWidth=5,
+              smoothPercentile=True, smoothPercentileWidth=31, maxPadLength=None, coldSpells=False,
+              tstep=False, anynans=False, skipna=False):
+    """Calculate threshold and mean climatology (day-of-year) -- xmhw/xmhw.py:38-247.
+
+    Same parameters as the reference.  `skipna` has no effect on results (the reference drops
+    NaNs at identify.py:208 in either mode) and none on speed here.  Returns a Dataset with
+    `thresh` and `seas` on (doy, <sorted non-time dims>), float64.
+    """
+    import torch
+    from . import core
+
+    if smoothPercentileWidth % 2 == 0:                         # xmhw.py:103-104
+        raise XmhwException("smoothPercentileWidth should be odd")
+    data, time, other, coords, attrs, enc, tattrs = _unpack(temp, tdim)   # xmhw.py:105-109
+    if all(climatologyPeriod):                                 # xmhw.py:112-119
+        from .identify import _ymd
+        years = _ymd(time)[0]
+        sel = (years >= int(climatologyPeriod[0])) & (years <= int(climatologyPeriod[1]))
+        data, time = np.ascontiguousarray(data[sel]), time[sel]
+    point = data.ndim == 1                                     # xmhw.py:122-126
+    if not point:
+        land_check_shape(data.shape, [tdim] + other, tdim)     # identify.py:509-516
+    if get_calendar(time, enc, tattrs) == 360.0:               # xmhw.py:142-144
+        tstep = True
+    doy, ndoy = add_doy(time, keep_tstep=tstep)                # xmhw.py:145
+    grid_shape = data.shape[1:]
+    T = data.shape[0]
+    flat = data.reshape(T, -1)
+    if maxPadLength:                                           # xmhw.py:159-160
+        flat = _interp_gaps(flat.copy(), maxPadLength)
+    nan = np.isnan(flat)
+    ocean = ~nan.any(axis=0) if anynans else ~nan.all(axis=0)  # identify.py:522-525
+    if not point and not ocean.any():
+        raise XmhwException("All points of grid are either land or NaN")   # identify.py:527-528
+    if not torch.cuda.is_available():
+        raise RuntimeError("xmhw_b200 needs a CUDA device (there is no CPU path)")
+    ts = torch.from_numpy(np.ascontiguousarray(flat)).cuda()
+    if coldSpells:                                             # xmhw.py:153-154
+        ts = -ts
+    if anynans:                                                # dropped cells produce no output
+        ts[:, torch.from_numpy(~ocean).cuda()] = float("nan")
+    th, se = core.threshold_arrays(ts, doy, ndoy, pctile, windowHalfWidth, smoothPercentile,
+                                   smoothPercentileWidth, feb29=not tstep)
+    th_h, se_h = th.cpu().numpy(), se.cpu().numpy()
+    doy_coord = np.arange(1, ndoy + 1, dtype=np.int64)
+    if not point:
+        keep = _present(ocean.reshape(grid_shape))
+        th_h = th_h.reshape((ndoy,) + grid_shape)
+        se_h = se_h.reshape((ndoy,) + grid_shape)
+        for ax, k in enumerate(keep):
+            th_h = np.take(th_h, k, axis=ax + 1)
+            se_h = np.take(se_h, k, axis=ax + 1)
+        out_coords = {"doy": doy_coord}
+        for d, k in zip(other, keep):
+            c = coords[d][k]
+            srt = np.argsort(c, kind="stable")              # unstack returns sorted coordinate values
+            ax = other.index(d) + 1
+            th_h, se_h = np.take(th_h, srt, axis=ax), np.take(se_h, srt, axis=ax)
+            out_coords[d] = c[srt]
+        dims = ("doy",) + tuple(other)
+    else:
+        out_coords, dims = {"doy": doy_coord}, ("doy",)
+    # a doy without samples disappears from the reference's groupby output (identify.py:233)
+    present = ~np.isnan(th_h).all(axis=tuple(range(1, th_h.ndim))) if th_h.ndim > 1 else ~np.isnan(th_h)
+    if not present.all():
+        th_h, se_h = th_h[present], se_h[present]
+        out_coords["doy"] = doy_coord[present]
+    out_coords["quantile"] = np.float64(pctile / 100.0)
+    ds = labeled.Dataset(coords=out_coords)
+    ds["thresh"] = labeled.DataArray(th_h, dims, name="threshold")      # xmhw.py:215-216
+    ds["seas"] = labeled.DataArray(se_h, dims, name="seasonal")
+    annotate_ds(ds.attrs, {"ts": attrs}, "clim")
+    from .identify import _ymd
+    yrs = _ymd(time)[0]
+    params = f"""Threshold calculated using:
+    {pctile} percentile;
+    climatology period is {yrs[0]}-{yrs[-1]}';
+    window half width used for percentile is {windowHalfWidth}"""
+    if skipna:
+        params += """;
+            NaNs where skipped in percentile and mean calculations"""
+    if smoothPercentile:
+        params += f""";
+         width of moving average window to smooth percentile is
+         {smoothPercentileWidth}"""
+    if anynans:
+        params += """;
+            any grid point with even only 1 NaN along time
+            axis has been removed from calculation"""
+    ds.attrs["xmhw_parameters"] = params                       # xmhw.py:221-246
+    return _wrap(ds, temp)
+
+
+def _clim_to_grid(arr, other, grid_coords, grid_shape, ndoy, name):
+    """Bring a (doy, ...) climatology onto the full (doy, cell) grid of `temp` by coordinate
+    label (the reference matches cells positionally after land_check, xmhw.py:399-402)."""
+    dims = list(arr.dims)
+    if "doy" not in dims:
+        raise XmhwException(f"{name} must have a 'doy' dimension")
+    data = np.asarray(arr.values, np.float64)
+    o = sorted(d for d in dims if d != "doy")
+    if o != list(other):
+        raise XmhwException(f"{name} dimensions {o} do not match the series dimensions {list(other)}")
+    data = np.transpose(data, [dims.index("doy")] + [dims.index(d) for d in o])
+    doyc = _coord(arr, "doy")
+    full = np.full((ndoy,) + tuple(grid_shape), np.nan)
+    drow = (np.asarray(doyc, np.int64) - 1) if doyc is not None else np.arange(data.shape[0])
+    index = [drow]
+    for d in other:
+        c = _coord(arr, d)
+        if c is None:
+            index.append(np.arange(data.shape[len(index)]))
+            continue
+        pos = {v: i for i, v in enumerate(grid_coords[d].tolist())}
+        try:
+            index.append(np.array([pos[v] for v in c.tolist()], np.int64))
+        except KeyError:
+            raise XmhwException(f"{name} has {d} values that are not on the series grid")
+    full[np.ix_(*index)] = data
+    return full.reshape(ndoy, -1)
+
+
+def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, maxPadLength=None,
+           coldSpells=False, intermediate=False, anynans=False, tstep=False, compact=False):
+    """Apply the Hobday et al. (2016) marine heat wave definition -- xmhw/xmhw.py:310-518.
+
+    Same parameters as the reference plus `compact`: when True the result is the compact
+    event table (one row per event with its cell coordinates) instead of the reference's
+    dense (events, lat, lon) cube, which cannot exist at global scale.
+    """
+    import torch
+    from . import core
+
+    if maxGap >= minDuration:                                  # xmhw.py:373-377
+        raise XmhwException("Maximum gap between mhw events should"
+                            + " be smaller than event minimum duration")
+    if intermediate:
+        raise NotImplementedError("intermediate=True (per-timestep dataset, identify.py:404-411) is not built yet")
+    data, time, other, coords, attrs, enc, tattrs = _unpack(temp, tdim)
+    point = data.ndim == 1
+    if not point:
+        land_check_shape(data.shape, [tdim] + other, tdim)
+    doy, ndoy = add_doy(time, keep_tstep=tstep)                # xmhw.py:404
+    grid_shape = data.shape[1:]
+    T = data.shape[0]
+    flat = data.reshape(T, -1)
+    if maxPadLength:                                           # xmhw.py:409-410
+        flat = _interp_gaps(flat.copy(), maxPadLength)
+    nan = np.isnan(flat)
+    ocean = ~nan.any(axis=0) if anynans else ~nan.all(axis=0)
+    if not point and not ocean.any():
+        raise XmhwException("All points of grid are either land or NaN")
+    th_full = _clim_to_grid(th, other, coords, grid_shape, ndoy, "th")
+    se_full = _clim_to_grid(se, other, coords, grid_shape, ndoy, "se")
+    if not torch.cuda.is_available():
+        raise RuntimeError("xmhw_b200 needs a CUDA device (there is no CPU path)")
+    ts = torch.from_numpy(np.ascontiguousarray(flat)).cuda()
+    if coldSpells:                                             # xmhw.py:412-413
+        ts = -ts
+    if anynans:
+        ts[:, torch.from_numpy(~ocean).cuda()] = float("nan")
+    ev = core.detect_arrays(ts, doy, ndoy, torch.from_numpy(th_full).cuda(), torch.from_numpy(se_full).cuda(),
+                            minDuration, joinGaps, maxGap)
+    tab = ev.to_numpy()
+    n = len(tab["cell"])
+    cols = {"event": tab["index_start"].astype(np.float64)}
+    for f in ("index_start", "index_end", "index_peak", "duration", "category"):
+        cols[f] = tab[f].astype(np.float64)                    # integer-valued float64 in the reference
+    cols["category"][tab["category"] < 0] = np.nan
+    for f in ("duration_moderate", "duration_strong", "duration_severe", "duration_extreme"):
+        cols[f] = tab[f].astype(np.int64)
+    for f in core.EF_FIELDS:
+        cols[f] = tab[f].astype(np.float32) if f in FLOAT32_VARIABLES else tab[f]
+    time = np.asarray(time)
+    cols["time_start"], cols["time_end"] = time[tab["index_start"]], time[tab["index_end"]]
+    cols["time_peak"] = time[tab["index_peak"]]
+    if coldSpells:                                             # xmhw.py:481-482
+        cols = flip_cold(cols)
+    params = f"MHW detected using: {minDuration} days of minimum duration"
+    if joinGaps:
+        params += f""";
+            events separated by {maxGap} or less days were joined"""
+    if coldSpells:
+        params += """;
+                cold events were detected instead of heat events"""
+    if maxPadLength:
+        params += f""";
+            where original timeseries had missing values interpolation
+            was used to fill them. Gaps > {maxPadLength} days long were
+            left as NaNs;"""
+    if anynans:
+        params += """;
+            any grid point with even only 1 NaN along time
+            axis has been removed from calculation"""
+    cell_idx = np.unravel_index(tab["cell"], grid_shape) if not point else ()
+    if compact or point:
+        ds = labeled.Dataset(coords={"events": tab["index_start"] if point else np.arange(n)})
+        dim = ("events",) if point else ("row",)
+        if not point:
+            ds.coords = {"row": np.arange(n)}
+            for d, ix in zip(other, cell_idx):
+                ds[d] = labeled.DataArray(coords[d][ix], dim)
+        for v in EVENT_VARIABLES:
+            ds[v] = labeled.DataArray(cols[v], dim)
+    else:
+        keep = _present(ocean.reshape(grid_shape))
+        events = np.unique(tab["index_start"])
+        shape = (len(events),) + tuple(len(k) for k in keep)
+        nbytes = int(np.prod(shape)) * 8 * len(EVENT_VARIABLES)
+        if nbytes > DENSE_LIMIT_BYTES:
+            raise XmhwException("the dense (events, %s) result would need %.1f GB; call detect(..., compact=True) "
+                                "or split the grid (reference docs/dask.rst)" % (", ".join(other), nbytes / 1e9))
+        erow = np.searchsorted(events, tab["index_start"])
+        out_coords = {"events": events}
+        pos = []
+        for d, k, ix in zip(other, keep, cell_idx):
+            c = coords[d][k]
+            srt = np.argsort(c, kind="stable")
+            inv = np.empty(len(coords[d]), np.int64)
+            inv[k[srt]] = np.arange(len(k))
+            pos.append(inv[ix])
+            out_coords[d] = c[srt]
+        ds = labeled.Dataset(coords=out_coords)
+        dims = ("events",) + tuple(other)
+        for v in EVENT_VARIABLES:
+            col = cols[v]
+            if np.issubdtype(col.dtype, np.datetime64):
+                dense = np.full(shape, np.datetime64("NaT"), dtype=col.dtype)
+            elif col.dtype == object:
+                dense = np.full(shape, None, dtype=object)
+            else:
+                dense = np.full(shape, np.nan, dtype=np.float32 if col.dtype == np.float32 else np.float64)
+            dense[(erow,) + tuple(pos)] = col
+            ds[v] = labeled.DataArray(dense, dims)
+    annotate_ds(ds.attrs, {"ts": attrs}, "mhw")
+    ds.attrs["xmhw_parameters"] = params                       # xmhw.py:487-515
+    return _wrap(ds, temp)
