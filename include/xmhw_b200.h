@@ -73,7 +73,8 @@ typedef struct xmhw_clim_plan {
   int32_t nmax;                 /* q tables have nmax + 1 entries               */
   int32_t max_size;             /* largest list, <= 32                          */
   const int32_t* inst_base;     /* [ninst]                                      */
-  const int32_t* inst_size;     /* [ninst]                                      */
+  const int32_t* inst_size;     /* [ninst] time rows of the list (1..32)         */
+  const int32_t* inst_keep;     /* [ninst] key rows held in shared memory        */
   const int32_t* inst_row_off;  /* [ninst]                                      */
   const int32_t* rows;          /* time indices                                 */
   const int32_t* leave_off;     /* [nsteps+1]                                   */
@@ -82,8 +83,8 @@ typedef struct xmhw_clim_plan {
   const int32_t* enter;
   const int32_t* use_off;       /* [nsteps+1]                                   */
   const int32_t* use;
-  const int32_t* q_lo;          /* [nmax+1] floor((n-1) q)                      */
-  const double*  q_gamma;       /* [nmax+1] (n-1) q - floor                     */
+  const int32_t* step_rec;      /* [nsteps][32] fixed-size step records          */
+  double q;                     /* quantile in [0,1] (numpy 'linear': (n-1) q)   */
 } xmhw_clim_plan;
 
 int xmhw_abi_version(void);

@@ -12,9 +12,12 @@
 using namespace xmhw;
 
 struct HostEnv {
+  struct Vec { const int32_t* p; int n; };
   bool any(bool p) const { return p; }
-  void stage(uint32_t* ub, const int32_t* src, int m, int m4, int) const {
-    for (int i = 0; i < m4; ++i) ub[i] = i < m ? (uint32_t)src[i] : 0u;
+  Vec vload(const int32_t* src, int count, int) const { return Vec{src, count}; }
+  int32_t vget(const Vec& v, int i) const { return i < v.n ? v.p[i] : 0; }
+  void vstage(uint32_t* ub, const Vec& v, int m, int m4, int) const {
+    for (int i = 0; i < m4; ++i) ub[i] = i < m ? (uint32_t)v.p[i] : 0u;
   }
 };
 

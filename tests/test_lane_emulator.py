@@ -27,9 +27,9 @@ def _vp(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def sweep(em, ts, doy, ndoy, w, q):
+def sweep(em, ts, doy, ndoy, w, q, keep=None):
     lib, cabi = em
-    hp = P.build_clim_plan(doy, ndoy, w, q)
+    hp = P.build_clim_plan(doy, ndoy, w, q, keep=keep)
     s, keep = cabi.numpy_plan_struct(hp)
     ts = np.ascontiguousarray(ts, np.float32)
     T, ng = ts.shape
@@ -49,8 +49,11 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("keep", [16, 3, 1])
 @pytest.mark.parametrize("name,years,ncell,nan_ppm,w,pct", CASES, ids=[c[0] for c in CASES])
-def test_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct):
+def test_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct, keep):
+    """keep = key rows per list in shared memory; small values force the exact global-memory
+    tail path (tail_key / tail_count) on almost every move."""
     tm = S.daily_time(*years)
     doy = S.doy366(tm)
     assert np.array_equal(doy, O.add_doy(tm))
@@ -59,7 +62,7 @@ def test_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct):
         ts[100:300, 3] = np.nan
         ts[:, 5] = np.nan
         ts[700:, 7] = np.nan
-    hp, thr, se = sweep(em, ts, doy, 366, w, pct / 100.0)
+    hp, thr, se = sweep(em, ts, doy, 366, w, pct / 100.0, keep=keep)
     oth, ose = O.threshold(ts, doy, 366, pctile=pct, windowHalfWidth=w, smoothPercentile=False, tstep=True)
     assert bit_equal(thr, oth)
     assert np.nanmax(np.abs(se - ose), initial=0) <= 1e-12

@@ -31,16 +31,17 @@ class ClimPlanStruct(C.Structure):
     """Mirror of `xmhw_clim_plan` (include/xmhw_b200.h)."""
     _fields_ = [("nsteps", C.c_int32), ("pool_rows", C.c_int32), ("nmax", C.c_int32),
                 ("max_size", C.c_int32),
-                ("inst_base", C.c_void_p), ("inst_size", C.c_void_p), ("inst_row_off", C.c_void_p),
+                ("inst_base", C.c_void_p), ("inst_size", C.c_void_p), ("inst_keep", C.c_void_p),
+                ("inst_row_off", C.c_void_p),
                 ("rows", C.c_void_p),
                 ("leave_off", C.c_void_p), ("leave", C.c_void_p),
                 ("enter_off", C.c_void_p), ("enter", C.c_void_p),
                 ("use_off", C.c_void_p), ("use", C.c_void_p),
-                ("q_lo", C.c_void_p), ("q_gamma", C.c_void_p)]
+                ("step_rec", C.c_void_p), ("q", C.c_double)]
 
 
-PLAN_ARRAYS = ("inst_base", "inst_size", "inst_row_off", "rows", "leave_off", "leave",
-               "enter_off", "enter", "use_off", "use", "q_lo", "q_gamma")
+PLAN_ARRAYS = ("inst_base", "inst_size", "inst_keep", "inst_row_off", "rows", "leave_off", "leave",
+               "enter_off", "enter", "use_off", "use", "step_rec")
 
 _SIGNATURES = {
     "xmhw_abi_version": (C.c_int, []),
@@ -101,6 +102,7 @@ def plan_struct(host_plan, pointers):
     s = ClimPlanStruct()
     s.nsteps, s.pool_rows = host_plan.nsteps, host_plan.pool_rows
     s.nmax, s.max_size = host_plan.nmax, host_plan.max_size
+    s.q = float(host_plan.q)
     for name in PLAN_ARRAYS:
         setattr(s, name, pointers[name])
     return s

@@ -70,7 +70,7 @@ class DevicePlan:
 def device_plan(doy, ndoy, w, q, device):
     """Build (or fetch from cache) the climatology sweep plan on `device`."""
     doy = np.ascontiguousarray(doy, dtype=np.int64)
-    key = (hashlib.sha1(doy.tobytes()).hexdigest(), int(ndoy), int(w), float(q), str(device))
+    key = (hashlib.sha1(doy.tobytes()).hexdigest(), int(ndoy), int(w), float(q), str(device), _plan.default_keep(), _plan.default_pool_rows())
     hit = _plan_cache.get(key)
     if hit is not None:
         return hit

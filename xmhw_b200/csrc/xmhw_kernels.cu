@@ -18,11 +18,23 @@ namespace {
 using namespace xmhw;
 
 struct WarpEnv {
+  // small int vector spread over the lanes: entry i lives in lane (i & 31), word (i >> 5)
+  struct Vec { int32_t a, b; };
   __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
-  // warp-cooperative copy of the step's list bases into shared memory (0 = null list)
-  __device__ __forceinline__ void stage(uint32_t* ub, const int32_t* src, int m, int m4, int lane) const {
+  __device__ __forceinline__ Vec vload(const int32_t* src, int count, int lane) const {
+    Vec v;
+    v.a = lane < count ? __ldg(src + lane) : 0;
+    v.b = lane + 32 < count ? __ldg(src + lane + 32) : 0;
+    return v;
+  }
+  __device__ __forceinline__ int32_t vget(const Vec& v, int i) const {      // i is warp-uniform
+    return __shfl_sync(0xffffffffu, i < 32 ? v.a : v.b, i & 31);
+  }
+  // write the first m entries (padded with the null list 0 up to m4) to shared memory
+  __device__ __forceinline__ void vstage(uint32_t* ub, const Vec& v, int m, int m4, int lane) const {
     __syncwarp();
-    for (int i = lane; i < m4; i += 32) ub[i] = i < m ? (uint32_t)__ldg(src + i) : 0u;
+    if (lane < m4) ub[lane] = lane < m ? (uint32_t)v.a : 0u;
+    if (lane + 32 < m4) ub[lane + 32] = lane + 32 < m ? (uint32_t)v.b : 0u;
     __syncwarp();
   }
 };

@@ -21,8 +21,10 @@
 
 #ifdef __CUDACC__
 #define XMHW_HD __host__ __device__ __forceinline__
+#define XMHW_NOINLINE __host__ __device__ __noinline__
 #else
 #define XMHW_HD inline
+#define XMHW_NOINLINE inline
 #endif
 
 #include "sortnet_gen.h"
@@ -105,6 +107,7 @@ struct ClimPlan {
   int32_t max_size;              // largest instance (<= 32)
   const int32_t* inst_base;      // [ninst] first pool row of the instance block
   const int32_t* inst_size;      // [ninst] number of time rows (1..32)
+  const int32_t* inst_keep;      // [ninst] key rows held in shared memory (1..size)
   const int32_t* inst_row_off;   // [ninst] offset into rows[]
   const int32_t* rows;           // time indices
   const int32_t* leave_off;      // [nsteps+1]  -> leave[] (pool base rows)
@@ -113,20 +116,41 @@ struct ClimPlan {
   const int32_t* enter;
   const int32_t* use_off;        // [nsteps+1]  -> use[] (pool base rows)
   const int32_t* use;
-  const int32_t* q_lo;           // [nmax+1] floor((n-1) q)  (numpy 'linear')
-  const double* q_gamma;         // [nmax+1] fractional part
+  const int32_t* step_rec;       // [nsteps][32] fixed-size step records (see STEP_* below)
+  double q;                      // quantile in [0,1]; numpy 'linear': v = (n-1) * q
 };
 
+// Step record (32 int32 per sweep step, loaded with one coalesced warp load one step
+// ahead so no plan lookup sits on the critical path).  Steps with more than 4 leaving or
+// 4 entering lists (only the first step) set STEP_OVERFLOW and use the CSR arrays.
+enum { STEP_COUNTS = 0,      // n_leave | n_enter << 8 | n_use << 16 | overflow << 31
+       STEP_USE_OFF = 1,     // offset of this step's list bases in plan.use
+       STEP_LEAVE = 2,       // 4 words: pool base rows of the leaving lists
+       STEP_ENTER = 6,       // 4 x 2 words: (instance id | load flag << 30), (base | size << 16 | keep << 24)
+       STEP_NEXT_USE_OFF = 14, STEP_NEXT_NUSE = 15,   // the same two numbers of the next step
+       STEP_ENTER_OFF = 16,  // index of this step's first entry in plan.enter
+       STEP_WORDS = 32, STEP_MAX_INLINE = 4 };
+
 // Instance block layout in the pool (row = 32 words, word index = lane):
-//   row 0      meta: len | ptr << 8   (len = valid samples, ptr = #keys above the cut)
+//   row 0      meta: len | ptr << 6 | keep << 12 | instance id << 18
+//              (len = valid samples, ptr = #keys above the cut, keep = key rows held here)
 //   row 1, 2   f64 sum of the valid samples (lo, hi words)
 //   row 3      cinc: smallest key above the cut (key[ptr-1]), 0xffffffff if ptr == 0
 //   row 4      cexc: largest key below the cut (key[ptr]),    0 if ptr == len
-//   row 5 + r  r-th largest key (r < size); invalid samples are key 0 at the end
+//   row 5 + r  r-th largest key, r < keep <= size.  Only the top `keep` keys of a list
+//              live in shared memory (the cut of a high percentile stays near the top);
+//              a rank beyond them is re-derived exactly from the list's rows in global
+//              memory (tail_key), which is rare and keeps 2x more warps resident.
 // Block 0 of every pool is a "null list" (len 0) used to pad scans to multiples of 4;
 // the two rows after plan.pool_rows hold the staged base rows of the lists in use.
 enum { POOL_META = 0, POOL_SUM = 1, POOL_CINC = 3, POOL_CEXC = 4, POOL_KEYS = 5, POOL_NULL_ROWS = 5,
        POOL_STAGE_ROWS = 2, MAX_LISTS = 64 };
+
+XMHW_HD int meta_len(uint32_t m) { return (int)(m & 63u); }
+XMHW_HD int meta_ptr(uint32_t m) { return (int)((m >> 6) & 63u); }
+XMHW_HD int meta_keep(uint32_t m) { return (int)((m >> 12) & 63u); }
+XMHW_HD int meta_id(uint32_t m) { return (int)(m >> 18); }
+#define XMHW_META_PTR1 64u
 
 #ifdef __CUDA_ARCH__
 #define XMHW_LDG(p) __ldg(p)
@@ -152,14 +176,28 @@ XMHW_HD double lerp_q(float a, float b, double g) {
   return g >= 0.5 ? hi : lo;
 }
 
-// number of keys of an instance strictly above the pivot key (keys descending)
-XMHW_HD int count_above(const uint32_t* pool, int lane, int base, int len, uint32_t pivot) {
-  int lo = 0, hi = len;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (pool[(base + POOL_KEYS + mid) * 32 + lane] > pivot) lo = mid + 1; else hi = mid;
+// Exact key at descending rank r >= keep of one list, recomputed from its rows in global
+// memory; `top` is the key at rank keep-1 (still in the pool).  Slow path, out of line.
+XMHW_NOINLINE uint32_t tail_key(const int32_t* rows, int size, const float* col, int64_t ngrid, int r, uint32_t top) {
+  uint32_t x = top;
+  while (true) {
+    int cge = 0;
+    uint32_t nx = 0u;
+    for (int i = 0; i < size; ++i) {
+      const uint32_t k = f32_key(XMHW_LDG(col + (int64_t)XMHW_LDG(rows + i) * ngrid));
+      cge += k >= x;
+      if (k < x && k > nx) nx = k;
+    }
+    if (r < cge) return x;
+    if (nx == 0u) return 0u;
+    x = nx;
   }
-  return lo;
+}
+// number of keys of one list strictly above `piv` (slow path of count_above)
+XMHW_NOINLINE int tail_count(const int32_t* rows, int size, const float* col, int64_t ngrid, uint32_t piv) {
+  int c = 0;
+  for (int i = 0; i < size; ++i) c += f32_key(XMHW_LDG(col + (int64_t)XMHW_LDG(rows + i) * ngrid)) > piv;
+  return c;
 }
 
 // Doy sweep of one lane (= one grid cell).  Selection = k-th largest of a union of
@@ -171,8 +209,12 @@ XMHW_HD int count_above(const uint32_t* pool, int lane, int base, int len, uint3
 // one list, so a few moves replace a sort of ~330 samples per doy.  Each list
 // caches its two keys adjacent to the cut (cinc/cexc rows), so one scan over the
 // lists in use is one shared-memory load + compare/select per list.
+//
+// Env supplies the warp-level pieces: any(pred) vote and Vec = a small int vector
+// spread over the lanes (vload = one coalesced load, vget = broadcast of one entry).
 template <class Env>
 struct Sweeper {
+  typedef typename Env::Vec Vec;
   const Env& env;
   const ClimPlan& p;
   uint32_t* pool;
@@ -183,169 +225,288 @@ struct Sweeper {
   int C, n;              // keys above the cut / valid samples, over the lists in use
   uint32_t pivot;        // cut value (key of the smallest sample above the cut)
   float pv[32];          // prefetched rows of the next instance to load
-  int pf;                // index into plan.enter of that instance (or total)
   int total_enter;
+  Vec rec_next, use_next;   // step record / list bases of the next step (prefetched)
 
   XMHW_HD Sweeper(const Env& e, const ClimPlan& pl, uint32_t* po, int ln, const float* c, int64_t ng, bool k)
       : env(e), p(pl), pool(po), lane(ln), col(c), ngrid(ng), ok(k), C(0), n(0), pivot(0xffffffffu) {}
 
   XMHW_HD uint32_t& at(int row) { return pool[row * 32 + lane]; }
 
+  // issue the loads of the next instance that has to be loaded, entry index >= from
   XMHW_HD void prefetch(int from) {
     int j = from;
     while (j < total_enter && !(XMHW_LDG(p.enter + j) >> 30)) ++j;
-    pf = j;
     if (j >= total_enter) return;
     const int id = XMHW_LDG(p.enter + j) & 0x3fffffff;
     const int size = XMHW_LDG(p.inst_size + id);
-    const int32_t* rows = p.rows + XMHW_LDG(p.inst_row_off + id);
+    const Vec rv = env.vload(p.rows + XMHW_LDG(p.inst_row_off + id), size, lane);
+    // unconditional loads (entries past `size` read row 0 and are masked in consume), so the
+    // compiler keeps all of them in flight instead of waiting on each predicated result
+    if (size <= 8) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      pv[i] = bits_f32(0x7fc00000u);
-      if (i < size && ok) pv[i] = XMHW_LDG(col + (int64_t)XMHW_LDG(rows + i) * ngrid);
+      for (int i = 0; i < 8; ++i) pv[i] = XMHW_LDG(col + (int64_t)env.vget(rv, i) * ngrid);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pv[i] = XMHW_LDG(col + (int64_t)env.vget(rv, i) * ngrid);
     }
   }
 
-  // keys of the prefetched instance -> sorted block in the pool; returns (len, ptr)
+  // key at rank r of the list at `base` (0 when !need)
+  XMHW_HD uint32_t key_at(int base, uint32_t meta, int r, bool need) {
+    const int keep = meta_keep(meta);
+    const bool in = r < keep;
+    uint32_t k = 0u;
+    if (need && in) k = at(base + POOL_KEYS + r);
+    if (env.any(need && !in)) {
+      if (need && !in) {
+        const int id = meta_id(meta);
+        k = tail_key(p.rows + XMHW_LDG(p.inst_row_off + id), XMHW_LDG(p.inst_size + id), col, ngrid, r,
+                     at(base + POOL_KEYS + keep - 1));
+      }
+    }
+    return k;
+  }
+
+  XMHW_HD int count_above(int base, uint32_t meta, uint32_t piv) {
+    const int len = meta_len(meta), keep = meta_keep(meta);
+    int lo = 0, hi = len < keep ? len : keep;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (at(base + POOL_KEYS + mid) > piv) lo = mid + 1; else hi = mid;
+    }
+    if (lo == keep && keep < len) {
+      const int id = meta_id(meta);
+      lo = tail_count(p.rows + XMHW_LDG(p.inst_row_off + id), XMHW_LDG(p.inst_size + id), col, ngrid, piv);
+    }
+    return lo;
+  }
+
+  // keys of the prefetched instance -> sorted block in the pool
   template <int N>
-  XMHW_HD void consume(int base, int size, int& len, int& ptr) {
+  XMHW_HD void consume(int base, int id, int size, int keep, int& len, int& ptr) {
     uint32_t k[32];
     len = 0;
     double sum = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      k[i] = f32_key(pv[i]);
+      k[i] = (i < size && ok) ? f32_key(pv[i]) : 0u;
       if (k[i] != 0u) { ++len; sum = sum + (double)pv[i]; }
     }
     ptr = 0;
+    uint32_t cinc = 0xffffffffu, cexc = 0u;
     if (env.any(len > 0)) {
       sort_desc<N>(k);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        if (i < size) at(base + POOL_KEYS + i) = k[i];
-        ptr += k[i] > pivot;
+        if (i < keep) at(base + POOL_KEYS + i) = k[i];
+        const bool ab = k[i] > pivot;
+        ptr += ab;
+        if (ab) cinc = k[i]; else cexc = cexc > k[i] ? cexc : k[i];
       }
     }
     at(base + POOL_SUM) = f64_lo(sum);
     at(base + POOL_SUM + 1) = f64_hi(sum);
+    at(base + POOL_META) = (uint32_t)len | ((uint32_t)ptr << 6) | ((uint32_t)keep << 12) | ((uint32_t)id << 18);
+    at(base + POOL_CINC) = cinc;
+    at(base + POOL_CEXC) = cexc;
   }
 
-  XMHW_HD void set_block(int base, int len, int ptr) {
-    at(base + POOL_META) = (uint32_t)len | ((uint32_t)ptr << 8);
-    at(base + POOL_CINC) = ptr > 0 ? at(base + POOL_KEYS + ptr - 1) : 0xffffffffu;
-    at(base + POOL_CEXC) = ptr < len ? at(base + POOL_KEYS + ptr) : 0u;
+  XMHW_HD void leave_list(int base) {
+    const uint32_t meta = at(base + POOL_META);
+    C -= meta_ptr(meta);
+    n -= meta_len(meta);
+  }
+
+  XMHW_HD void enter_list(int e, int base, int size, int keep, int entry_index) {
+    const int id = e & 0x3fffffff;
+    int len, ptr;
+    if (e >> 30) {
+      if (size <= 8) consume<8>(base, id, size, keep, len, ptr);
+      else consume<32>(base, id, size, keep, len, ptr);
+      prefetch(entry_index + 1);
+    } else {          // list re-enters after a hole (Feb 29): pointer against the current cut
+      uint32_t meta = at(base + POOL_META);
+      len = meta_len(meta);
+      ptr = count_above(base, meta, pivot);
+      meta = (meta & ~(63u << 6)) | ((uint32_t)ptr << 6);
+      at(base + POOL_META) = meta;
+      const uint32_t ci = key_at(base, meta, ptr - 1, ptr > 0);
+      const uint32_t ce = key_at(base, meta, ptr, ptr < len);
+      at(base + POOL_CINC) = ptr > 0 ? ci : 0xffffffffu;
+      at(base + POOL_CEXC) = ce;
+    }
+    C += ptr;
+    n += len;
   }
 
   XMHW_HD void init() {
     at(POOL_META) = 0u; at(POOL_SUM) = 0u; at(POOL_SUM + 1) = 0u;
     at(POOL_CINC) = 0xffffffffu; at(POOL_CEXC) = 0u;
     total_enter = XMHW_LDG(p.enter_off + p.nsteps);
+    rec_next = env.vload(p.step_rec, STEP_WORDS, lane);
+    use_next = env.vload(p.use + XMHW_LDG(p.step_rec + STEP_USE_OFF),
+                         (XMHW_LDG(p.step_rec + STEP_COUNTS) >> 16) & 0x7f, lane);
     prefetch(0);
   }
 
   XMHW_HD void step(int s, double& thresh, double& seas) {
-    for (int j = XMHW_LDG(p.leave_off + s); j < XMHW_LDG(p.leave_off + s + 1); ++j) {
-      uint32_t meta = at(XMHW_LDG(p.leave + j) + POOL_META);
-      C -= (int)((meta >> 8) & 0xffu);
-      n -= (int)(meta & 0xffu);
+    const Vec rec = rec_next;
+    const Vec usev = use_next;
+    const uint32_t w0 = (uint32_t)env.vget(rec, STEP_COUNTS);
+    const int m = (int)((w0 >> 16) & 0x7fu);
+    if (s + 1 < p.nsteps) {     // everything the next step needs from the plan, one step ahead
+      rec_next = env.vload(p.step_rec + (s + 1) * STEP_WORDS, STEP_WORDS, lane);
+      use_next = env.vload(p.use + env.vget(rec, STEP_NEXT_USE_OFF), env.vget(rec, STEP_NEXT_NUSE), lane);
     }
-    for (int j = XMHW_LDG(p.enter_off + s); j < XMHW_LDG(p.enter_off + s + 1); ++j) {
-      const int e = XMHW_LDG(p.enter + j);
-      const int id = e & 0x3fffffff;
-      const int base = XMHW_LDG(p.inst_base + id);
-      const int size = XMHW_LDG(p.inst_size + id);
-      int len, ptr;
-      if (e >> 30) {
-        if (size <= 8) consume<8>(base, size, len, ptr);
-        else if (size <= 16) consume<16>(base, size, len, ptr);
-        else if (size <= 24) consume<24>(base, size, len, ptr);
-        else consume<32>(base, size, len, ptr);
-        prefetch(j + 1);
+    // leaving / entering lists: from the step record, or (first step) from the CSR arrays
+    const bool ovf = (w0 >> 31) != 0u;
+    const int l0 = ovf ? XMHW_LDG(p.leave_off + s) : 0;
+    const int n_leave = ovf ? XMHW_LDG(p.leave_off + s + 1) - l0 : (int)(w0 & 0xffu);
+    const int eoff = ovf ? XMHW_LDG(p.enter_off + s) : env.vget(rec, STEP_ENTER_OFF);
+    const int n_enter = ovf ? XMHW_LDG(p.enter_off + s + 1) - eoff : (int)((w0 >> 8) & 0xffu);
+    for (int j = 0; j < n_leave; ++j)
+      leave_list(ovf ? XMHW_LDG(p.leave + l0 + j) : env.vget(rec, (STEP_LEAVE + j) & 31));
+#pragma unroll 1
+    for (int j = 0; j < n_enter; ++j) {
+      int e, base, size, keep;
+      if (ovf) {
+        e = XMHW_LDG(p.enter + eoff + j);
+        const int id = e & 0x3fffffff;
+        base = XMHW_LDG(p.inst_base + id); size = XMHW_LDG(p.inst_size + id); keep = XMHW_LDG(p.inst_keep + id);
       } else {
-        len = (int)(at(base + POOL_META) & 0xffu);
-        ptr = count_above(pool, lane, base, len, pivot);
+        e = env.vget(rec, (STEP_ENTER + 2 * j) & 31);
+        const uint32_t pk = (uint32_t)env.vget(rec, (STEP_ENTER + 2 * j + 1) & 31);
+        base = (int)(pk & 0xffffu); size = (int)((pk >> 16) & 0xffu); keep = (int)(pk >> 24);
       }
-      set_block(base, len, ptr);
-      C += ptr;
-      n += len;
+      enter_list(e, base, size, keep, eoff + j);
     }
     // stage the base rows of the lists in use (padded to a multiple of 4 with the null list)
-    const int u0 = XMHW_LDG(p.use_off + s);
-    const int m = XMHW_LDG(p.use_off + s + 1) - u0;
     const int m4 = (m + 3) & ~3;
     uint32_t* ub = pool + p.pool_rows * 32;
-    env.stage(ub, p.use + u0, m, m4, lane);
+    env.vstage(ub, usev, m, m4, lane);
 
     const bool live = n > 0;
     if (!env.any(live)) { thresh = qnan(); seas = qnan(); return; }   // all-land warp
+    // numpy 'linear' quantile: v = (n-1) q, a = s[floor v], b = s[floor v + 1]; v >= n-1 -> max
     int target = 0;
     double gamma = 0.0;
     if (live) {
-      target = n - XMHW_LDG(p.q_lo + n);   // rank (1-based, from the top) of s[floor v]
-      gamma = XMHW_LDG(p.q_gamma + n);
+      const double nm1 = (double)(n - 1);
+      const double v = nm1 * p.q;
+      double fl = floor(v);
+      gamma = v - fl;
+      if (v >= nm1) { fl = nm1; gamma = 0.0; }
+      target = n - (int)fl;       // rank (1-based, from the top) of s[floor v]
     }
-    // phase 1: lanes with too few keys above the cut add the largest key below it
-    while (env.any(live && C < target)) {
-      uint32_t b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;
-      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      for (int j = 0; j < m4; j += 4) {
-        const int x0 = (int)ub[j], x1 = (int)ub[j + 1], x2 = (int)ub[j + 2], x3 = (int)ub[j + 3];
-        const uint32_t k0 = at(x0 + POOL_CEXC), k1 = at(x1 + POOL_CEXC), k2 = at(x2 + POOL_CEXC), k3 = at(x3 + POOL_CEXC);
-        if (k0 > b0) { b0 = k0; a0 = x0; }
-        if (k1 > b1) { b1 = k1; a1 = x1; }
-        if (k2 > b2) { b2 = k2; a2 = x2; }
-        if (k3 > b3) { b3 = k3; a3 = x3; }
+    // Walk: every iteration scans the lists in use once, tracking the two smallest keys
+    // above the cut (i1 <= i2, from lists bi1 != bi2) and the two largest keys below it
+    // (e1 >= e2).  A lane that is off target then makes up to TWO moves in its direction
+    // (the second-best candidate is either the other list's or the same list's next key),
+    // lanes on target do nothing; the scan of the last iteration (no lane off target)
+    // delivers a = i1 and the runner-up for b.
+    uint32_t i1, i2, e1, e2;
+    int bi1, bi2, be1, be2;
+    while (true) {
+      i1 = 0xffffffffu; i2 = 0xffffffffu; e1 = 0u; e2 = 0u;
+      bi1 = 0; bi2 = 0; be1 = 0; be2 = 0;
+#pragma unroll 2
+      for (int j = 0; j < m4; ++j) {
+        const int x = (int)ub[j];
+        const uint32_t ki = at(x + POOL_CINC), ke = at(x + POOL_CEXC);
+        if (ki < i2) {
+          const bool first = ki < i1;
+          i2 = first ? i1 : ki; bi2 = first ? bi1 : x;
+          if (first) { i1 = ki; bi1 = x; }
+        }
+        if (ke > e2) {
+          const bool first = ke > e1;
+          e2 = first ? e1 : ke; be2 = first ? be1 : x;
+          if (first) { e1 = ke; be1 = x; }
+        }
       }
-      if (b1 > b0) { b0 = b1; a0 = a1; }
-      if (b3 > b2) { b2 = b3; a2 = a3; }
-      if (b2 > b0) { b0 = b2; a0 = a2; }
-      if (live && C < target) {      // b0 > 0 is guaranteed: C < target <= n
-        const uint32_t meta = at(a0 + POOL_META);
-        const int len = (int)(meta & 0xffu), ptr = (int)((meta >> 8) & 0xffu) + 1;
-        at(a0 + POOL_META) = meta + 0x100u;
-        at(a0 + POOL_CINC) = b0;
-        at(a0 + POOL_CEXC) = ptr < len ? at(a0 + POOL_KEYS + ptr) : 0u;
-        ++C;
+      const int d = live ? C - target : 0;
+      if (!env.any(d != 0)) break;
+      // ---- drop the smallest keys above the cut (d > 0)
+      {
+        const bool mv = d > 0;
+        const uint32_t meta = at(bi1 + POOL_META);
+        const int pa = meta_ptr(meta);                          // >= 1 when mv
+        const uint32_t nxt = key_at(bi1, meta, pa - 2, mv && pa >= 2);      // next key up in the same list
+        const uint32_t nx = pa >= 2 ? nxt : 0xffffffffu;
+        const bool two = mv && d >= 2;
+        const bool same = two && nx <= i2;                      // second smallest is in the same list
+        const bool other = two && !same;
+        const uint32_t nn = key_at(bi1, meta, pa - 3, same && pa >= 3);
+        const uint32_t metab = at(bi2 + POOL_META);
+        const int pb = meta_ptr(metab);
+        const uint32_t nb = key_at(bi2, metab, pb - 2, other && pb >= 2);
+        if (mv) {
+          if (same) {
+            at(bi1 + POOL_META) = meta - 2u * XMHW_META_PTR1;
+            at(bi1 + POOL_CEXC) = nx;
+            at(bi1 + POOL_CINC) = pa >= 3 ? nn : 0xffffffffu;
+            C -= 2;
+          } else {
+            at(bi1 + POOL_META) = meta - XMHW_META_PTR1;
+            at(bi1 + POOL_CEXC) = i1;
+            at(bi1 + POOL_CINC) = nx;
+            C -= 1;
+            if (other) {
+              at(bi2 + POOL_META) = metab - XMHW_META_PTR1;
+              at(bi2 + POOL_CEXC) = i2;
+              at(bi2 + POOL_CINC) = pb >= 2 ? nb : 0xffffffffu;
+              C -= 1;
+            }
+          }
+        }
+      }
+      // ---- add the largest keys below the cut (d < 0)
+      {
+        const bool mv = d < 0;
+        const uint32_t meta = at(be1 + POOL_META);
+        const int pa = meta_ptr(meta), la = meta_len(meta);     // pa < la when mv
+        const uint32_t nxt = key_at(be1, meta, pa + 1, mv && pa + 1 < la);  // next key down in the same list
+        const bool two = mv && d <= -2;
+        const bool same = two && nxt >= e2 && pa + 1 < la;      // second largest is in the same list
+        const bool other = two && !same && e2 > 0u;
+        const uint32_t nn = key_at(be1, meta, pa + 2, same && pa + 2 < la);
+        const uint32_t metab = at(be2 + POOL_META);
+        const int pb = meta_ptr(metab), lb = meta_len(metab);
+        const uint32_t nb = key_at(be2, metab, pb + 1, other && pb + 1 < lb);
+        if (mv) {
+          if (same) {
+            at(be1 + POOL_META) = meta + 2u * XMHW_META_PTR1;
+            at(be1 + POOL_CINC) = nxt;
+            at(be1 + POOL_CEXC) = nn;
+            C += 2;
+          } else {
+            at(be1 + POOL_META) = meta + XMHW_META_PTR1;
+            at(be1 + POOL_CINC) = e1;
+            at(be1 + POOL_CEXC) = nxt;
+            C += 1;
+            if (other) {
+              at(be2 + POOL_META) = metab + XMHW_META_PTR1;
+              at(be2 + POOL_CINC) = e2;
+              at(be2 + POOL_CEXC) = nb;
+              C += 1;
+            }
+          }
+        }
       }
     }
-    // phase 2: lanes with too many drop the smallest key above the cut
-    while (env.any(live && C > target)) {
-      uint32_t b0 = 0xffffffffu, b1 = 0xffffffffu, b2 = 0xffffffffu, b3 = 0xffffffffu;
-      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      for (int j = 0; j < m4; j += 4) {
-        const int x0 = (int)ub[j], x1 = (int)ub[j + 1], x2 = (int)ub[j + 2], x3 = (int)ub[j + 3];
-        const uint32_t k0 = at(x0 + POOL_CINC), k1 = at(x1 + POOL_CINC), k2 = at(x2 + POOL_CINC), k3 = at(x3 + POOL_CINC);
-        if (k0 < b0) { b0 = k0; a0 = x0; }
-        if (k1 < b1) { b1 = k1; a1 = x1; }
-        if (k2 < b2) { b2 = k2; a2 = x2; }
-        if (k3 < b3) { b3 = k3; a3 = x3; }
-      }
-      if (b1 < b0) { b0 = b1; a0 = a1; }
-      if (b3 < b2) { b2 = b3; a2 = a3; }
-      if (b2 < b0) { b0 = b2; a0 = a2; }
-      if (live && C > target) {
-        const uint32_t meta = at(a0 + POOL_META);
-        const int ptr = (int)((meta >> 8) & 0xffu) - 1;
-        at(a0 + POOL_META) = meta - 0x100u;
-        at(a0 + POOL_CEXC) = b0;
-        at(a0 + POOL_CINC) = ptr > 0 ? at(a0 + POOL_KEYS + ptr - 1) : 0xffffffffu;
-        --C;
-      }
-    }
-    // final scan: a = smallest key above the cut, b = next one up; f64 sum of the window
-    uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu;
-    int a1 = 0;
+    // f64 sum of the window; a = i1 (smallest key above the cut), b = next one up
     double sum = 0.0;
     for (int j = 0; j < m4; ++j) {
       const int x = (int)ub[j];
-      const uint32_t k = at(x + POOL_CINC);
-      if (k < m1) { m2 = m1; m1 = k; a1 = x; }
-      else if (k < m2) m2 = k;
       sum = sum + f64_from(at(x + POOL_SUM), at(x + POOL_SUM + 1));
     }
+    const uint32_t m1 = i1, m2 = i2;
+    const uint32_t meta1 = at(bi1 + POOL_META);
+    const int ptr1 = meta_ptr(meta1);
+    const uint32_t c2r = key_at(bi1, meta1, ptr1 - 2, live && ptr1 >= 2);
     if (live) {
-      const int ptr1 = (int)((at(a1 + POOL_META) >> 8) & 0xffu);
-      const uint32_t c2 = ptr1 >= 2 ? at(a1 + POOL_KEYS + ptr1 - 2) : 0xffffffffu;
+      const uint32_t c2 = ptr1 >= 2 ? c2r : 0xffffffffu;
       const uint32_t kb = target >= 2 ? (c2 < m2 ? c2 : m2) : m1;
       pivot = m1;
       thresh = lerp_q(key_f32(m1), key_f32(kb), gamma);

@@ -44,6 +44,7 @@ class ClimPlanHost:
     max_size: int
     inst_base: np.ndarray
     inst_size: np.ndarray
+    inst_keep: np.ndarray
     inst_row_off: np.ndarray
     rows: np.ndarray
     leave_off: np.ndarray
@@ -52,8 +53,8 @@ class ClimPlanHost:
     enter: np.ndarray
     use_off: np.ndarray
     use: np.ndarray
-    q_lo: np.ndarray
-    q_gamma: np.ndarray
+    step_rec: np.ndarray
+    q: float
     # diagnostics
     n_instances: int = 0
     n_loads: int = 0
@@ -79,8 +80,28 @@ def quantile_table(nmax, q):
     return lo.astype(np.int32), gamma.astype(np.float64)
 
 
-def build_clim_plan(doy, ndoy, w, q):
+def default_keep():
+    """Key rows per list kept in shared memory (the rest is re-derived on demand)."""
+    import os
+    return int(os.environ.get("XMHW_B200_KEEP", "16"))
+
+
+# pool rows that let N = 8, 7, ... 1 single-warp blocks share one SM's 227 KB of shared
+# memory (1 KB per block is reserved by the system, 2 rows per pool are staging rows)
+POOL_ROW_STEPS = tuple((227 * 1024 // nw - 1024) // 128 - STAGE_ROWS for nw in range(8, 0, -1))
+
+
+def default_pool_rows():
+    """Row budget of the per-warp pool from the environment (0 = choose automatically)."""
+    import os
+    return int(os.environ.get("XMHW_B200_POOL_ROWS", "0"))
+
+
+def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
     """doy: int array [T] of 1-based labels in 1..ndoy; w: window half width; q in [0,1]."""
+    keep = default_keep() if keep is None else int(keep)
+    if not 1 <= keep <= MAX_LIST:
+        raise ValueError("keep must be in 1..32")
     doy = np.asarray(doy, dtype=np.int64)
     T = len(doy)
     if T == 0:
@@ -127,74 +148,129 @@ def build_clim_plan(doy, ndoy, w, q):
         for s in it["steps"]:
             in_use[s].append(i)
 
-    # static pool allocation (first fit over the sweep)
-    free = [(NULL_ROWS, 1 << 30)]
-    base = np.zeros(ninst, np.int32)
-    pool_rows = 0
-    release_at = [[] for _ in range(ndoy + 1)]
+    sizes_list = [len(it["rows"]) for it in insts]
+    keeps = [min(sz, keep) for sz in sizes_list]
+    budget = default_pool_rows() if max_rows is None else int(max_rows)
+    if budget <= 0:
+        # occupancy step that holds a REGULAR step with full `keep`; rare peaks (the split
+        # leap / non-leap lists around Feb 29) are squeezed into it by shrinking their keeps
+        alive = np.zeros(ndoy, np.int64)
+        for i, it in enumerate(insts):
+            alive[it["steps"][0]:it["steps"][-1] + 1] += keeps[i] + META_ROWS
+        regular = int(np.percentile(alive, 90)) + NULL_ROWS + 4
+        budget = next((b for b in POOL_ROW_STEPS if b >= regular), POOL_ROW_STEPS[-1])
 
-    def alloc(n):
-        nonlocal pool_rows
-        for k, (a, sz) in enumerate(free):
-            if sz >= n:
-                if sz == n:
-                    free.pop(k)
+    def allocate(keeps):
+        """Static first-fit allocation of the instance blocks over the sweep."""
+        free = [(NULL_ROWS, 1 << 30)]
+        base = np.zeros(ninst, np.int32)
+        state = {"rows": 0, "peak_step": 0}
+        release_at = [[] for _ in range(ndoy + 1)]
+
+        def alloc(n, s):
+            for k, (a, sz) in enumerate(free):
+                if sz >= n:
+                    if sz == n:
+                        free.pop(k)
+                    else:
+                        free[k] = (a + n, sz - n)
+                    if a + n > state["rows"]:
+                        state["rows"], state["peak_step"] = a + n, s
+                    return a
+            raise RuntimeError("pool exhausted")
+
+        def release(a, n):
+            free.append((a, n))
+            free.sort()
+            merged = []
+            for seg in free:
+                if merged and merged[-1][0] + merged[-1][1] == seg[0]:
+                    merged[-1] = (merged[-1][0], merged[-1][1] + seg[1])
                 else:
-                    free[k] = (a + n, sz - n)
-                pool_rows = max(pool_rows, a + n)
-                return a
-        raise RuntimeError("pool exhausted")
+                    merged.append(seg)
+            free[:] = merged
 
-    def release(a, n):
-        free.append((a, n))
-        free.sort()
-        merged = []
-        for seg in free:
-            if merged and merged[-1][0] + merged[-1][1] == seg[0]:
-                merged[-1] = (merged[-1][0], merged[-1][1] + seg[1])
-            else:
-                merged.append(seg)
-        free[:] = merged
+        leave_off, leave, enter_off, enter, use_off, use = [0], [], [0], [], [0], []
+        prev_use = set()
+        loaded = set()
+        n_loads = rows_loaded = max_lists = 0
+        for s in range(ndoy):
+            for (a, n) in release_at[s]:
+                release(a, n)
+            cur = in_use[s]
+            cur_set = set(cur)
+            for i in sorted(prev_use - cur_set):
+                leave.append(int(base[i]))
+            for i in cur:
+                if i in prev_use:
+                    continue
+                if i not in loaded:
+                    n = keeps[i] + META_ROWS
+                    base[i] = alloc(n, s)
+                    release_at[insts[i]["steps"][-1] + 1].append((int(base[i]), n))
+                    loaded.add(i)
+                    enter.append(i | LOAD_FLAG)
+                    n_loads += 1
+                    rows_loaded += sizes_list[i]
+                else:
+                    enter.append(i)
+            for i in cur:
+                use.append(int(base[i]))
+            max_lists = max(max_lists, len(cur))
+            leave_off.append(len(leave))
+            enter_off.append(len(enter))
+            use_off.append(len(use))
+            prev_use = cur_set
+        return (base, state["rows"], state["peak_step"], leave_off, leave, enter_off, enter, use_off, use,
+                n_loads, rows_loaded, max_lists)
 
-    leave_off, leave, enter_off, enter, use_off, use = [0], [], [0], [], [0], []
-    prev_use = set()
-    loaded = set()
-    n_loads = rows_loaded = max_lists = 0
-    for s in range(ndoy):
-        for (a, n) in release_at[s]:
-            release(a, n)
-        cur = in_use[s]
-        cur_set = set(cur)
-        for i in sorted(prev_use - cur_set):
-            leave.append(int(base[i]))
-        for i in cur:
-            if i in prev_use:
-                continue
-            if i not in loaded:
-                n = len(insts[i]["rows"]) + META_ROWS
-                base[i] = alloc(n)
-                release_at[insts[i]["steps"][-1] + 1].append((int(base[i]), n))
-                loaded.add(i)
-                enter.append(i | LOAD_FLAG)
-                n_loads += 1
-                rows_loaded += len(insts[i]["rows"])
-            else:
-                enter.append(i)
-        for i in cur:
-            use.append(int(base[i]))
-        max_lists = max(max_lists, len(cur))
-        leave_off.append(len(leave))
-        enter_off.append(len(enter))
-        use_off.append(len(use))
-        prev_use = cur_set
+    # shrink the lists alive at the peak step until the pool fits the row budget
+    for _ in range(4096):
+        (base, pool_rows, peak_step, leave_off, leave, enter_off, enter, use_off, use,
+         n_loads, rows_loaded, max_lists) = allocate(keeps)
+        if pool_rows <= budget:
+            break
+        lo_s, hi_s = max(0, peak_step - 1), min(ndoy - 1, peak_step + 1)
+        live = sorted({i for s in range(lo_s, hi_s + 1) for i in in_use[s]}, key=lambda i: -keeps[i])
+        shrunk = False
+        for i in live[:max(1, len(live) // 2)]:
+            if keeps[i] > 2:
+                keeps[i] -= 1
+                shrunk = True
+        if not shrunk:
+            break
 
     if max_lists > MAX_LISTS:
         raise NotImplementedError("more than %d sorted lists per window (windowHalfWidth too large)" % MAX_LISTS)
+    if ninst >= (1 << 14):
+        raise NotImplementedError("too many sorted lists (%d) for the pool meta word" % ninst)
     sizes = np.array([len(it["rows"]) for it in insts], np.int32)
     row_off = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)
     rows = np.concatenate([it["rows"] for it in insts]).astype(np.int32)
     nmax = max(1, max(sum(int(sizes[i]) for i in in_use[s]) for s in range(ndoy)))
-    q_lo, q_gamma = quantile_table(nmax, q)
+    # fixed-size step records (csrc/xmhw_lane.h STEP_*)
+    rec = np.zeros((ndoy, 32), np.int64)
+    keeps_arr = np.asarray(keeps, np.int64)
+    for s in range(ndoy):
+        nl = leave_off[s + 1] - leave_off[s]
+        ne = enter_off[s + 1] - enter_off[s]
+        nu = use_off[s + 1] - use_off[s]
+        ovf = nl > 4 or ne > 4
+        rec[s, 0] = (0 if ovf else nl) | ((0 if ovf else ne) << 8) | (nu << 16) | ((1 << 31) if ovf else 0)
+        rec[s, 1] = use_off[s]
+        if not ovf:
+            for j in range(nl):
+                rec[s, 2 + j] = leave[leave_off[s] + j]
+            for j in range(ne):
+                e = enter[enter_off[s] + j]
+                i = e & (LOAD_FLAG - 1)
+                rec[s, 6 + 2 * j] = e
+                rec[s, 7 + 2 * j] = int(base[i]) | (int(sizes[i]) << 16) | (int(keeps_arr[i]) << 24)
+        if s + 1 < ndoy:
+            rec[s, 14] = use_off[s + 1]
+            rec[s, 15] = use_off[s + 2] - use_off[s + 1]
+        rec[s, 16] = enter_off[s]
+    step_rec = rec.astype(np.uint32).view(np.int32).reshape(-1)
 
     def arr(x):
         a = np.asarray(x, np.int32)
@@ -202,9 +278,10 @@ def build_clim_plan(doy, ndoy, w, q):
 
     return ClimPlanHost(
         nsteps=ndoy, pool_rows=int(pool_rows), nmax=int(nmax), max_size=int(sizes.max()),
-        inst_base=base, inst_size=sizes, inst_row_off=row_off, rows=rows,
+        inst_base=base, inst_size=sizes, inst_keep=np.asarray(keeps, np.int32),
+        inst_row_off=row_off, rows=rows,
         leave_off=arr(leave_off), leave=arr(leave), enter_off=arr(enter_off), enter=arr(enter),
-        use_off=arr(use_off), use=arr(use), q_lo=q_lo, q_gamma=q_gamma,
+        use_off=arr(use_off), use=arr(use), step_rec=step_rec, q=float(q),
         n_instances=ninst, n_loads=n_loads, rows_loaded=rows_loaded, max_lists=max_lists)
 
 
