@@ -72,9 +72,12 @@ typedef struct xmhw_clim_plan {
   int32_t pool_rows;            /* shared-memory rows (128 B) per 32-cell warp  */
   int32_t nmax;                 /* q tables have nmax + 1 entries               */
   int32_t max_size;             /* largest list, <= 32                          */
+  int32_t scratch_rows;         /* global scratch rows (128 B) per 32-cell warp  */
+  int32_t reserved_;
   const int32_t* inst_base;     /* [ninst]                                      */
   const int32_t* inst_size;     /* [ninst] time rows of the list (1..32)         */
   const int32_t* inst_keep;     /* [ninst] key rows held in shared memory        */
+  const int32_t* inst_sbase;    /* [ninst] first scratch row of the keys past keep */
   const int32_t* inst_row_off;  /* [ninst]                                      */
   const int32_t* rows;          /* time indices                                 */
   const int32_t* leave_off;     /* [nsteps+1]                                   */
@@ -92,15 +95,21 @@ const char* xmhw_strerror(int code);
 
 /* identify.py:184-270 window_roll + calculate_thresh + calculate_seas (before the
  * Feb-29 rule and smoothing) for every grid cell.
- * ts [T][ngrid] f32 -> thresh_raw, seas_raw [nsteps][ngrid] f64 (NaN = no sample). */
+ * ts [T][ngrid] f32 -> thresh_raw, seas_raw [nsteps][ngrid] f64 (NaN = no sample).
+ * scratch: caller-owned workspace of ceil(ngrid/32) * plan->scratch_rows * 128 bytes
+ * (sorted list tails; stays L2-resident while a warp needs it).                       */
 int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan* plan,
-                        double* thresh_raw, double* seas_raw, void* stream);
+                        double* thresh_raw, double* seas_raw, uint32_t* scratch, void* stream);
 
 /* identify.py:137-151 feb29 (if feb29 != 0: doy 60 <- mean of doys 59,60,61) then
  * identify.py:154-181 runavg (circular centred mean, odd smooth_width; <= 1 = off).
  * raw, out [ndoy][ngrid] f64, out must not alias raw.                           */
 int xmhw_clim_finish_f64(const double* raw, double* out, int32_t ndoy, int64_t ngrid,
                          int32_t feb29, int32_t smooth_width, void* stream);
+/* same for thresh and seas in one call (one fused launch for the default width 31) */
+int xmhw_clim_finish2_f64(const double* thresh_raw, double* thresh_out, const double* seas_raw,
+                          double* seas_out, int32_t ndoy, int64_t ngrid, int32_t feb29,
+                          int32_t smooth_width, void* stream);
 
 /* identify.py:367-372: bthresh = ts > thresh[doy] (strict, float64 compare, NaN -> false).
  * doy_ptr [ndoy+1], doy_tidx [T]: CSR of time indices per doy label.

@@ -26,10 +26,11 @@ extern "C" {
 int emul_clim_sweep(const float* ts, int64_t T, int64_t ngrid, const ClimPlan* plan, double* thr, double* seas) {
   (void)T;
   std::vector<uint32_t> pool((size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 32);
+  std::vector<uint32_t> scratch((size_t)(plan->scratch_rows + 1) * 32);
   HostEnv env;
   for (int64_t cell = 0; cell < ngrid; ++cell) {
     const int lane = (int)(cell & 31);
-    Sweeper<HostEnv> sw(env, *plan, pool.data(), lane, ts + cell, ngrid, true);
+    Sweeper<HostEnv> sw(env, *plan, pool.data(), scratch.data(), lane, ts + cell, ngrid, true);
     sw.init();
     for (int s = 0; s < plan->nsteps; ++s) {
       double a, b;

@@ -17,16 +17,17 @@ def run(nlat, nlon, y0, y1, land_frac=0.33, reps=2):
     nocean = ngrid - (int(land.sum()) if land is not None else 0)
     print(f"== {nlat}x{nlon} T={T} ngrid={ngrid} ocean={nocean} bytes={T*ngrid*4/1e9:.2f} GB")
     dp = core.device_plan(doy, 366, 5, 0.9, ts.device)
-    print("plan: pool_rows", dp.host.pool_rows, "smem KB", dp.host.smem_bytes()/1024, "max_lists", dp.host.max_lists)
+    print("plan: scratch_rows", dp.host.scratch_rows, "pool_rows", dp.host.pool_rows, "smem KB", dp.host.smem_bytes()/1024, "max_lists", dp.host.max_lists)
     st = torch.cuda.current_stream().cuda_stream
     for r in range(reps):
         raw_t = torch.empty((366, ngrid), dtype=torch.float64, device="cuda"); raw_s = torch.empty_like(raw_t)
         out_t = torch.empty_like(raw_t); out_s = torch.empty_like(raw_t)
         e0 = ev()
-        check(lib.xmhw_clim_sweep_f32(ts.data_ptr(), T, ngrid, dp.struct, raw_t.data_ptr(), raw_s.data_ptr(), st), "sweep")
+        scratch = torch.empty(max(1, ((ngrid + 31) // 32) * dp.host.scratch_rows * 32), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize(); e0 = ev()
+        check(lib.xmhw_clim_sweep_f32(ts.data_ptr(), T, ngrid, dp.struct, raw_t.data_ptr(), raw_s.data_ptr(), scratch.data_ptr(), st), "sweep")
         e1 = ev()
-        check(lib.xmhw_clim_finish_f64(raw_t.data_ptr(), out_t.data_ptr(), 366, ngrid, 1, 31, st), "fin")
-        check(lib.xmhw_clim_finish_f64(raw_s.data_ptr(), out_s.data_ptr(), 366, ngrid, 1, 31, st), "fin")
+        check(lib.xmhw_clim_finish2_f64(raw_t.data_ptr(), out_t.data_ptr(), raw_s.data_ptr(), out_s.data_ptr(), 366, ngrid, 1, 31, st), "fin")
         e2 = ev()
         del raw_t, raw_s
         ptr, tidx, doy32 = core._doy_tables(doy, 366, ts.device)

@@ -30,8 +30,9 @@ _f64p = C.POINTER(C.c_double)
 class ClimPlanStruct(C.Structure):
     """Mirror of `xmhw_clim_plan` (include/xmhw_b200.h)."""
     _fields_ = [("nsteps", C.c_int32), ("pool_rows", C.c_int32), ("nmax", C.c_int32),
-                ("max_size", C.c_int32),
+                ("max_size", C.c_int32), ("scratch_rows", C.c_int32), ("reserved_", C.c_int32),
                 ("inst_base", C.c_void_p), ("inst_size", C.c_void_p), ("inst_keep", C.c_void_p),
+                ("inst_sbase", C.c_void_p),
                 ("inst_row_off", C.c_void_p),
                 ("rows", C.c_void_p),
                 ("leave_off", C.c_void_p), ("leave", C.c_void_p),
@@ -40,16 +41,18 @@ class ClimPlanStruct(C.Structure):
                 ("step_rec", C.c_void_p), ("q", C.c_double)]
 
 
-PLAN_ARRAYS = ("inst_base", "inst_size", "inst_keep", "inst_row_off", "rows", "leave_off", "leave",
+PLAN_ARRAYS = ("inst_base", "inst_size", "inst_keep", "inst_sbase", "inst_row_off", "rows", "leave_off", "leave",
                "enter_off", "enter", "use_off", "use", "step_rec")
 
 _SIGNATURES = {
     "xmhw_abi_version": (C.c_int, []),
     "xmhw_strerror": (C.c_char_p, [C.c_int]),
     "xmhw_clim_sweep_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlanStruct),
-                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_clim_finish_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
                                        C.c_int32, C.c_void_p]),
+    "xmhw_clim_finish2_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                                        C.c_int32, C.c_int32, C.c_void_p]),
     "xmhw_exceed_mask_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_events_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
@@ -103,6 +106,7 @@ def plan_struct(host_plan, pointers):
     s.nsteps, s.pool_rows = host_plan.nsteps, host_plan.pool_rows
     s.nmax, s.max_size = host_plan.nmax, host_plan.max_size
     s.q = float(host_plan.q)
+    s.scratch_rows = int(host_plan.scratch_rows)
     for name in PLAN_ARRAYS:
         setattr(s, name, pointers[name])
     return s

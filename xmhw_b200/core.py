@@ -26,7 +26,7 @@ _plan_cache = {}
 # bracketed by CUDA events on the launch stream and (name, start, end) is appended.
 TRACE = None
 LAUNCHES = {"n": 0}
-_KERNELS_PER_CALL = {"xmhw_exclusive_scan_i32": 3}
+_KERNELS_PER_CALL = {"xmhw_exclusive_scan_i32": 3}      # finish2: 1 (width 31) or 2 launches
 
 
 def _call(name, *args):
@@ -127,15 +127,17 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
         st = _stream()
         raw_t = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
         raw_s = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
-        _call("xmhw_clim_sweep_f32", _ptr(ts), T, ngrid, dp.struct, _ptr(raw_t), _ptr(raw_s), st)
+        ncg = (ngrid + 31) // 32
+        scratch = torch.empty(max(1, ncg * dp.host.scratch_rows * 32), dtype=torch.int32, device=ts.device)
+        _call("xmhw_clim_sweep_f32", _ptr(ts), T, ngrid, dp.struct, _ptr(raw_t), _ptr(raw_s), _ptr(scratch), st)
         W = int(smoothPercentileWidth) if smoothPercentile else 1
         do_feb = bool(feb29) and ndoy >= 61
         if W <= 1 and not do_feb:
             return (raw_t, raw_s, raw_t, raw_s) if return_raw else (raw_t, raw_s)
         out_t = torch.empty_like(raw_t)
         out_s = torch.empty_like(raw_s)
-        for raw, out in ((raw_t, out_t), (raw_s, out_s)):
-            _call("xmhw_clim_finish_f64", _ptr(raw), _ptr(out), ndoy, ngrid, int(do_feb), W, st)
+        _call("xmhw_clim_finish2_f64", _ptr(raw_t), _ptr(out_t), _ptr(raw_s), _ptr(out_s), ndoy, ngrid,
+              int(do_feb), W, st)
     return (out_t, out_s, raw_t, raw_s) if return_raw else (out_t, out_s)
 
 

@@ -49,14 +49,14 @@ static_assert((int)XMHW_EI_COUNT == (int)EI_COUNT && (int)XMHW_EF_COUNT == (int)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) clim_sweep_kernel(ClimPlan p, const float* __restrict__ ts,
                                                         int64_t ngrid, double* __restrict__ thr,
-                                                        double* __restrict__ seas) {
+                                                        double* __restrict__ seas, uint32_t* __restrict__ scratch) {
   extern __shared__ uint32_t pool[];
   const int lane = threadIdx.x;
   const int64_t cell = (int64_t)blockIdx.x * 32 + lane;
   const bool ok = cell < ngrid;
   const float* col = ts + (ok ? cell : 0);
   WarpEnv env;
-  Sweeper<WarpEnv> sw(env, p, pool, lane, col, ngrid, ok);
+  Sweeper<WarpEnv> sw(env, p, pool, scratch + (size_t)blockIdx.x * p.scratch_rows * 32, lane, col, ngrid, ok);
   sw.init();
   for (int s = 0; s < p.nsteps; ++s) {
     double a, b;
@@ -114,6 +114,37 @@ __global__ void clim_finish_kernel(const double* __restrict__ raw, double* __res
       slot = slot + 1 == W ? 0 : slot + 1;
     }
     out[(int64_t)d * ngrid + cell] = acc / (double)W;
+  }
+}
+
+// Register-ring variant for a compile-time width (the default 31): the doy loop is
+// unrolled by W so every ring slot is a statically indexed register; same left-to-right
+// f64 summation order as the generic kernel, ~5x fewer instructions per output.
+template <int W>
+__global__ void __launch_bounds__(128) clim_finish_reg_kernel(const double* __restrict__ raw0, double* __restrict__ out0,
+                                                              const double* __restrict__ raw1, double* __restrict__ out1,
+                                                              int ndoy, int64_t ngrid, int feb29) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ngrid) return;
+  const double* __restrict__ raw = blockIdx.y ? raw1 : raw0;
+  double* __restrict__ out = blockIdx.y ? out1 : out0;
+  constexpr int h = (W - 1) / 2;
+  double ring[W];
+#pragma unroll
+  for (int i = 0; i < W - 1; ++i)
+    ring[i] = finish_value(raw, ngrid, cell, ndoy, feb29, (((i - h) % ndoy) + ndoy) % ndoy);
+  for (int d0 = 0; d0 < ndoy; d0 += W) {
+#pragma unroll
+    for (int r = 0; r < W; ++r) {
+      const int d = d0 + r;
+      if (d < ndoy) {
+        ring[(r + W - 1) % W] = finish_value(raw, ngrid, cell, ndoy, feb29, (d + h) % ndoy);
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc = acc + ring[(r + k) % W];
+        out[(int64_t)d * ngrid + cell] = acc / (double)W;
+      }
+    }
   }
 }
 
@@ -279,7 +310,7 @@ __global__ void scan_apply(const int32_t* __restrict__ in, int64_t n, const int6
 // ---------------------------------------------------------------------------
 // K4  per-event statistics: one thread = one event.
 // ---------------------------------------------------------------------------
-__global__ void event_stats_kernel(const float* __restrict__ ts, int64_t T, int64_t ngrid,
+__global__ void __launch_bounds__(128) event_stats_kernel(const float* __restrict__ ts, int64_t T, int64_t ngrid,
                                    const int32_t* __restrict__ doy, const double* __restrict__ thr,
                                    const double* __restrict__ seas, int64_t nev, int64_t cap,
                                    int32_t* __restrict__ ei, double* __restrict__ ef) {
@@ -352,8 +383,9 @@ const char* xmhw_strerror(int code) {
 }
 
 int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan* plan,
-                        double* thresh_raw, double* seas_raw, void* stream) {
+                        double* thresh_raw, double* seas_raw, uint32_t* scratch, void* stream) {
   if (!ts || !plan || !thresh_raw || !seas_raw || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
+  if (plan->scratch_rows < 0 || (plan->scratch_rows > 0 && !scratch)) return XMHW_E_ARG;
   if (plan->nsteps <= 0 || plan->pool_rows <= 0 || plan->max_size > 32 || plan->nmax <= 0) return XMHW_E_PLAN;
   const size_t smem = (size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 128;
   if (smem > 227 * 1024) return XMHW_E_SMEM;
@@ -362,7 +394,7 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
   ClimPlan p;
   memcpy(&p, plan, sizeof(p));
   const int64_t ncg = (ngrid + 31) / 32;
-  clim_sweep_kernel<<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw);
+  clim_sweep_kernel<<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw, scratch);
   return cuda_status();
 }
 
@@ -378,6 +410,23 @@ int xmhw_clim_finish_f64(const double* raw, double* out, int32_t ndoy, int64_t n
   clim_finish_kernel<<<(unsigned)((ngrid + nt - 1) / nt), nt, smem, (cudaStream_t)stream>>>(
       raw, out, ndoy, ngrid, feb29, smooth_width);
   return cuda_status();
+}
+
+int xmhw_clim_finish2_f64(const double* thresh_raw, double* thresh_out, const double* seas_raw, double* seas_out,
+                          int32_t ndoy, int64_t ngrid, int32_t feb29, int32_t smooth_width, void* stream) {
+  if (!thresh_raw || !thresh_out || !seas_raw || !seas_out || thresh_raw == thresh_out || seas_raw == seas_out ||
+      ndoy <= 0 || ngrid <= 0) return XMHW_E_ARG;
+  if (smooth_width > 1 && smooth_width % 2 == 0) return XMHW_E_ARG;
+  if (smooth_width == 31) {
+    const int nt = 128;
+    dim3 grid((unsigned)((ngrid + nt - 1) / nt), 2);
+    clim_finish_reg_kernel<31><<<grid, nt, 0, (cudaStream_t)stream>>>(thresh_raw, thresh_out, seas_raw, seas_out,
+                                                                      ndoy, ngrid, feb29);
+    return cuda_status();
+  }
+  int rc = xmhw_clim_finish_f64(thresh_raw, thresh_out, ndoy, ngrid, feb29, smooth_width, stream);
+  if (rc) return rc;
+  return xmhw_clim_finish_f64(seas_raw, seas_out, ndoy, ngrid, feb29, smooth_width, stream);
 }
 
 int xmhw_exceed_mask_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy_ptr,

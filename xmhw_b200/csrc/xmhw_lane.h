@@ -105,9 +105,12 @@ struct ClimPlan {
   int32_t pool_rows;             // shared-memory rows (32 words each) per warp
   int32_t nmax;                  // max samples per window (size of q tables - 1)
   int32_t max_size;              // largest instance (<= 32)
+  int32_t scratch_rows;          // global scratch rows (32 words each) per warp
+  int32_t reserved_;
   const int32_t* inst_base;      // [ninst] first pool row of the instance block
   const int32_t* inst_size;      // [ninst] number of time rows (1..32)
   const int32_t* inst_keep;      // [ninst] key rows held in shared memory (1..size)
+  const int32_t* inst_sbase;     // [ninst] first global scratch row of the keys past `keep`
   const int32_t* inst_row_off;   // [ninst] offset into rows[]
   const int32_t* rows;           // time indices
   const int32_t* leave_off;      // [nsteps+1]  -> leave[] (pool base rows)
@@ -126,21 +129,21 @@ struct ClimPlan {
 enum { STEP_COUNTS = 0,      // n_leave | n_enter << 8 | n_use << 16 | overflow << 31
        STEP_USE_OFF = 1,     // offset of this step's list bases in plan.use
        STEP_LEAVE = 2,       // 4 words: pool base rows of the leaving lists
-       STEP_ENTER = 6,       // 4 x 2 words: (instance id | load flag << 30), (base | size << 16 | keep << 24)
-       STEP_NEXT_USE_OFF = 14, STEP_NEXT_NUSE = 15,   // the same two numbers of the next step
-       STEP_ENTER_OFF = 16,  // index of this step's first entry in plan.enter
+       STEP_ENTER = 6,       // 4 x 3 words: (instance id | load flag << 30), (base | size << 16 | keep << 24), scratch base
+       STEP_NEXT_USE_OFF = 18, STEP_NEXT_NUSE = 19,   // the same two numbers of the next step
+       STEP_ENTER_OFF = 20,  // index of this step's first entry in plan.enter
        STEP_WORDS = 32, STEP_MAX_INLINE = 4 };
 
 // Instance block layout in the pool (row = 32 words, word index = lane):
-//   row 0      meta: len | ptr << 6 | keep << 12 | instance id << 18
+//   row 0      meta: len | ptr << 6 | keep << 12 | scratch base row << 18
 //              (len = valid samples, ptr = #keys above the cut, keep = key rows held here)
 //   row 1, 2   f64 sum of the valid samples (lo, hi words)
 //   row 3      cinc: smallest key above the cut (key[ptr-1]), 0xffffffff if ptr == 0
 //   row 4      cexc: largest key below the cut (key[ptr]),    0 if ptr == len
 //   row 5 + r  r-th largest key, r < keep <= size.  Only the top `keep` keys of a list
-//              live in shared memory (the cut of a high percentile stays near the top);
-//              a rank beyond them is re-derived exactly from the list's rows in global
-//              memory (tail_key), which is rare and keeps 2x more warps resident.
+//              live in shared memory; the sorted remainder is parked in a per-warp global
+//              scratch (L2-resident, one load per access), so `keep` can be small and
+//              many more warps stay resident per SM (the sweep is latency-chained).
 // Block 0 of every pool is a "null list" (len 0) used to pad scans to multiples of 4;
 // the two rows after plan.pool_rows hold the staged base rows of the lists in use.
 enum { POOL_META = 0, POOL_SUM = 1, POOL_CINC = 3, POOL_CEXC = 4, POOL_KEYS = 5, POOL_NULL_ROWS = 5,
@@ -149,7 +152,7 @@ enum { POOL_META = 0, POOL_SUM = 1, POOL_CINC = 3, POOL_CEXC = 4, POOL_KEYS = 5,
 XMHW_HD int meta_len(uint32_t m) { return (int)(m & 63u); }
 XMHW_HD int meta_ptr(uint32_t m) { return (int)((m >> 6) & 63u); }
 XMHW_HD int meta_keep(uint32_t m) { return (int)((m >> 12) & 63u); }
-XMHW_HD int meta_id(uint32_t m) { return (int)(m >> 18); }
+XMHW_HD int meta_sbase(uint32_t m) { return (int)(m >> 18); }
 #define XMHW_META_PTR1 64u
 
 #ifdef __CUDA_ARCH__
@@ -176,30 +179,6 @@ XMHW_HD double lerp_q(float a, float b, double g) {
   return g >= 0.5 ? hi : lo;
 }
 
-// Exact key at descending rank r >= keep of one list, recomputed from its rows in global
-// memory; `top` is the key at rank keep-1 (still in the pool).  Slow path, out of line.
-XMHW_NOINLINE uint32_t tail_key(const int32_t* rows, int size, const float* col, int64_t ngrid, int r, uint32_t top) {
-  uint32_t x = top;
-  while (true) {
-    int cge = 0;
-    uint32_t nx = 0u;
-    for (int i = 0; i < size; ++i) {
-      const uint32_t k = f32_key(XMHW_LDG(col + (int64_t)XMHW_LDG(rows + i) * ngrid));
-      cge += k >= x;
-      if (k < x && k > nx) nx = k;
-    }
-    if (r < cge) return x;
-    if (nx == 0u) return 0u;
-    x = nx;
-  }
-}
-// number of keys of one list strictly above `piv` (slow path of count_above)
-XMHW_NOINLINE int tail_count(const int32_t* rows, int size, const float* col, int64_t ngrid, uint32_t piv) {
-  int c = 0;
-  for (int i = 0; i < size; ++i) c += f32_key(XMHW_LDG(col + (int64_t)XMHW_LDG(rows + i) * ngrid)) > piv;
-  return c;
-}
-
 // Doy sweep of one lane (= one grid cell).  Selection = k-th largest of a union of
 // sorted lists: each list keeps ptr = number of its keys above the cut, the cut is
 // "consistent" (every key above it >= every key below it).  A list entering the
@@ -218,6 +197,7 @@ struct Sweeper {
   const Env& env;
   const ClimPlan& p;
   uint32_t* pool;
+  uint32_t* scratch;     // this warp's global scratch rows (sorted keys past `keep`)
   const int lane;
   const float* col;
   const int64_t ngrid;
@@ -228,8 +208,8 @@ struct Sweeper {
   int total_enter;
   Vec rec_next, use_next;   // step record / list bases of the next step (prefetched)
 
-  XMHW_HD Sweeper(const Env& e, const ClimPlan& pl, uint32_t* po, int ln, const float* c, int64_t ng, bool k)
-      : env(e), p(pl), pool(po), lane(ln), col(c), ngrid(ng), ok(k), C(0), n(0), pivot(0xffffffffu) {}
+  XMHW_HD Sweeper(const Env& e, const ClimPlan& pl, uint32_t* po, uint32_t* sc, int ln, const float* c, int64_t ng, bool k)
+      : env(e), p(pl), pool(po), scratch(sc), lane(ln), col(c), ngrid(ng), ok(k), C(0), n(0), pivot(0xffffffffu) {}
 
   XMHW_HD uint32_t& at(int row) { return pool[row * 32 + lane]; }
 
@@ -255,36 +235,24 @@ struct Sweeper {
   // key at rank r of the list at `base` (0 when !need)
   XMHW_HD uint32_t key_at(int base, uint32_t meta, int r, bool need) {
     const int keep = meta_keep(meta);
-    const bool in = r < keep;
     uint32_t k = 0u;
-    if (need && in) k = at(base + POOL_KEYS + r);
-    if (env.any(need && !in)) {
-      if (need && !in) {
-        const int id = meta_id(meta);
-        k = tail_key(p.rows + XMHW_LDG(p.inst_row_off + id), XMHW_LDG(p.inst_size + id), col, ngrid, r,
-                     at(base + POOL_KEYS + keep - 1));
-      }
-    }
+    if (need) k = r < keep ? at(base + POOL_KEYS + r) : scratch[(size_t)(meta_sbase(meta) + r - keep) * 32 + lane];
     return k;
   }
 
+  // number of keys of the list strictly above `piv` (keys descending)
   XMHW_HD int count_above(int base, uint32_t meta, uint32_t piv) {
-    const int len = meta_len(meta), keep = meta_keep(meta);
-    int lo = 0, hi = len < keep ? len : keep;
+    int lo = 0, hi = meta_len(meta);
     while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (at(base + POOL_KEYS + mid) > piv) lo = mid + 1; else hi = mid;
-    }
-    if (lo == keep && keep < len) {
-      const int id = meta_id(meta);
-      lo = tail_count(p.rows + XMHW_LDG(p.inst_row_off + id), XMHW_LDG(p.inst_size + id), col, ngrid, piv);
+      const int mid = (lo + hi) >> 1;
+      if (key_at(base, meta, mid, true) > piv) lo = mid + 1; else hi = mid;
     }
     return lo;
   }
 
   // keys of the prefetched instance -> sorted block in the pool
   template <int N>
-  XMHW_HD void consume(int base, int id, int size, int keep, int& len, int& ptr) {
+  XMHW_HD void consume(int base, int sbase, int size, int keep, int& len, int& ptr) {
     uint32_t k[32];
     len = 0;
     double sum = 0.0;
@@ -300,6 +268,7 @@ struct Sweeper {
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         if (i < keep) at(base + POOL_KEYS + i) = k[i];
+        else if (i < size) scratch[(size_t)(sbase + i - keep) * 32 + lane] = k[i];
         const bool ab = k[i] > pivot;
         ptr += ab;
         if (ab) cinc = k[i]; else cexc = cexc > k[i] ? cexc : k[i];
@@ -307,7 +276,7 @@ struct Sweeper {
     }
     at(base + POOL_SUM) = f64_lo(sum);
     at(base + POOL_SUM + 1) = f64_hi(sum);
-    at(base + POOL_META) = (uint32_t)len | ((uint32_t)ptr << 6) | ((uint32_t)keep << 12) | ((uint32_t)id << 18);
+    at(base + POOL_META) = (uint32_t)len | ((uint32_t)ptr << 6) | ((uint32_t)keep << 12) | ((uint32_t)sbase << 18);
     at(base + POOL_CINC) = cinc;
     at(base + POOL_CEXC) = cexc;
   }
@@ -318,12 +287,11 @@ struct Sweeper {
     n -= meta_len(meta);
   }
 
-  XMHW_HD void enter_list(int e, int base, int size, int keep, int entry_index) {
-    const int id = e & 0x3fffffff;
+  XMHW_HD void enter_list(int e, int base, int size, int keep, int sbase, int entry_index) {
     int len, ptr;
     if (e >> 30) {
-      if (size <= 8) consume<8>(base, id, size, keep, len, ptr);
-      else consume<32>(base, id, size, keep, len, ptr);
+      if (size <= 8) consume<8>(base, sbase, size, keep, len, ptr);
+      else consume<32>(base, sbase, size, keep, len, ptr);
       prefetch(entry_index + 1);
     } else {          // list re-enters after a hole (Feb 29): pointer against the current cut
       uint32_t meta = at(base + POOL_META);
@@ -369,17 +337,19 @@ struct Sweeper {
       leave_list(ovf ? XMHW_LDG(p.leave + l0 + j) : env.vget(rec, (STEP_LEAVE + j) & 31));
 #pragma unroll 1
     for (int j = 0; j < n_enter; ++j) {
-      int e, base, size, keep;
+      int e, base, size, keep, sbase;
       if (ovf) {
         e = XMHW_LDG(p.enter + eoff + j);
         const int id = e & 0x3fffffff;
         base = XMHW_LDG(p.inst_base + id); size = XMHW_LDG(p.inst_size + id); keep = XMHW_LDG(p.inst_keep + id);
+        sbase = XMHW_LDG(p.inst_sbase + id);
       } else {
-        e = env.vget(rec, (STEP_ENTER + 2 * j) & 31);
-        const uint32_t pk = (uint32_t)env.vget(rec, (STEP_ENTER + 2 * j + 1) & 31);
+        e = env.vget(rec, (STEP_ENTER + 3 * j) & 31);
+        const uint32_t pk = (uint32_t)env.vget(rec, (STEP_ENTER + 3 * j + 1) & 31);
+        sbase = env.vget(rec, (STEP_ENTER + 3 * j + 2) & 31);
         base = (int)(pk & 0xffffu); size = (int)((pk >> 16) & 0xffu); keep = (int)(pk >> 24);
       }
-      enter_list(e, base, size, keep, eoff + j);
+      enter_list(e, base, size, keep, sbase, eoff + j);
     }
     // stage the base rows of the lists in use (padded to a multiple of 4 with the null list)
     const int m4 = (m + 3) & ~3;
@@ -574,6 +544,8 @@ enum EvF64 { EF_INT_MAX = 0, EF_INT_MEAN, EF_INT_CUM, EF_INT_VAR,
              EF_ABS_MAX, EF_ABS_MEAN, EF_ABS_CUM, EF_ABS_VAR,
              EF_RATE_ONSET, EF_RATE_DECLINE, EF_COUNT };
 
+enum { EV_BATCH = 4 };
+
 // NaN-skipping running moments (pandas groupby mean/sum/var(ddof=1) skip NaN;
 // Welford update like pandas' group_var).
 struct Moments {
@@ -610,32 +582,46 @@ XMHW_HD void event_stats(const float* col, const double* th, const double* se, c
     int d = XMHW_LDG(doy + s - 1) - 1;
     prev_anom = (double)XMHW_LDG(col + (int64_t)(s - 1) * ngrid) - XMHW_LDG(se + (int64_t)d * ngrid);
   }
-  for (int t = s; t <= e; ++t) {
-    int d = XMHW_LDG(doy + t) - 1;
-    double x = (double)XMHW_LDG(col + (int64_t)t * ngrid);
-    double thr = XMHW_LDG(th + (int64_t)d * ngrid);
-    double sea = XMHW_LDG(se + (int64_t)d * ngrid);
-    double relS = x - sea;                 // features.py:52
-    double relT = x - thr;                 // :53
-    double ths = thr - sea;                // :54
-    double norm = relT / ths;              // :57
-    double sev = relS / -(ths);            // :59-61
-    double cat = floor(1.0 + norm);        // :62
-    if (anom_first != anom_first && prev_anom == prev_anom) anom_first = prev_anom;   // first non-null anom_plus
-    if (t > s && relS == relS) anom_last = relS;     // anom_minus of day t-1 is anom[t]
-    if (relS == relS) {
-      if (relS_first != relS_first) relS_first = relS;
-      relS_last = relS;
-      if (relS > smax) { smax = relS; peak = t; t_at_peak = relT; x_at_peak = x; }   // first max (:120)
+  // days are processed in batches of EV_BATCH with all loads of a batch issued first
+  // (memory-level parallelism; the per-day arithmetic is a serial f64 chain)
+  for (int t0 = s; t0 <= e; t0 += EV_BATCH) {
+    float xs[EV_BATCH];
+    double thb[EV_BATCH], seb[EV_BATCH];
+#pragma unroll
+    for (int i = 0; i < EV_BATCH; ++i) {
+      const int tt = t0 + i <= e ? t0 + i : e;           // clamped: loads stay unconditional
+      const int dd = XMHW_LDG(doy + tt) - 1;
+      xs[i] = XMHW_LDG(col + (int64_t)tt * ngrid);
+      thb[i] = XMHW_LDG(th + (int64_t)dd * ngrid);
+      seb[i] = XMHW_LDG(se + (int64_t)dd * ngrid);
     }
-    if (sev == sev) { have_v = true; if (sev > vmax) vmax = sev; }
-    if (cat == cat) {
-      have_cat = true;
-      if (cat > catmax) catmax = cat;
-      nmod += cat == 1.0; nstr += cat == 2.0; nsev += cat == 3.0; next += cat >= 4.0;   // :63-66
+#pragma unroll
+    for (int i = 0; i < EV_BATCH; ++i) {
+      const int t = t0 + i;
+      if (t > e) break;
+      const double x = (double)xs[i], thr = thb[i], sea = seb[i];
+      double relS = x - sea;                 // features.py:52
+      double relT = x - thr;                 // :53
+      double ths = thr - sea;                // :54
+      double norm = relT / ths;              // :57
+      double sev = relS / -(ths);            // :59-61
+      double cat = floor(1.0 + norm);        // :62
+      if (anom_first != anom_first && prev_anom == prev_anom) anom_first = prev_anom;   // first non-null anom_plus
+      if (t > s && relS == relS) anom_last = relS;     // anom_minus of day t-1 is anom[t]
+      if (relS == relS) {
+        if (relS_first != relS_first) relS_first = relS;
+        relS_last = relS;
+        if (relS > smax) { smax = relS; peak = t; t_at_peak = relT; x_at_peak = x; }   // first max (:120)
+      }
+      if (sev == sev) { have_v = true; if (sev > vmax) vmax = sev; }
+      if (cat == cat) {
+        have_cat = true;
+        if (cat > catmax) catmax = cat;
+        nmod += cat == 1.0; nstr += cat == 2.0; nsev += cat == 3.0; next += cat >= 4.0;   // :63-66
+      }
+      mS.add(relS); mV.add(sev); mT.add(relT); mA.add(x);
+      prev_anom = relS;
     }
-    mS.add(relS); mV.add(sev); mT.add(relT); mA.add(x);
-    prev_anom = relS;
   }
   if (e + 1 <= T - 1) {       // anom_minus of the last event day
     int d = XMHW_LDG(doy + e + 1) - 1;

@@ -42,9 +42,11 @@ class ClimPlanHost:
     pool_rows: int
     nmax: int
     max_size: int
+    scratch_rows: int
     inst_base: np.ndarray
     inst_size: np.ndarray
     inst_keep: np.ndarray
+    inst_sbase: np.ndarray
     inst_row_off: np.ndarray
     rows: np.ndarray
     leave_off: np.ndarray
@@ -83,12 +85,12 @@ def quantile_table(nmax, q):
 def default_keep():
     """Key rows per list kept in shared memory (the rest is re-derived on demand)."""
     import os
-    return int(os.environ.get("XMHW_B200_KEEP", "16"))
+    return int(os.environ.get("XMHW_B200_KEEP", "6"))
 
 
-# pool rows that let N = 8, 7, ... 1 single-warp blocks share one SM's 227 KB of shared
+# pool rows that let N = 20, 19, ... 1 single-warp blocks share one SM's 227 KB of shared
 # memory (1 KB per block is reserved by the system, 2 rows per pool are staging rows)
-POOL_ROW_STEPS = tuple((227 * 1024 // nw - 1024) // 128 - STAGE_ROWS for nw in range(8, 0, -1))
+POOL_ROW_STEPS = tuple((227 * 1024 // nw - 1024) // 128 - STAGE_ROWS for nw in range(20, 0, -1))
 
 
 def default_pool_rows():
@@ -242,8 +244,38 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
 
     if max_lists > MAX_LISTS:
         raise NotImplementedError("more than %d sorted lists per window (windowHalfWidth too large)" % MAX_LISTS)
-    if ninst >= (1 << 14):
-        raise NotImplementedError("too many sorted lists (%d) for the pool meta word" % ninst)
+    # global scratch rows for the sorted keys past `keep` (same lifetime as the pool block)
+    sfree = [(0, 1 << 30)]
+    sbase = np.zeros(ninst, np.int32)
+    scratch_rows = 0
+    srel = [[] for _ in range(ndoy + 1)]
+    for s in range(ndoy):
+        for (a, n) in srel[s]:
+            sfree.append((a, n))
+            sfree.sort()
+            merged = []
+            for seg in sfree:
+                if merged and merged[-1][0] + merged[-1][1] == seg[0]:
+                    merged[-1] = (merged[-1][0], merged[-1][1] + seg[1])
+                else:
+                    merged.append(seg)
+            sfree[:] = merged
+        for e in enter[enter_off[s]:enter_off[s + 1]]:
+            if not e & LOAD_FLAG:
+                continue
+            i = e & (LOAD_FLAG - 1)
+            n = sizes_list[i] - keeps[i]
+            if n <= 0:
+                continue
+            for k, (a, sz) in enumerate(sfree):
+                if sz >= n:
+                    sfree[k] = (a + n, sz - n)
+                    sbase[i] = a
+                    scratch_rows = max(scratch_rows, a + n)
+                    break
+            srel[insts[i]["steps"][-1] + 1].append((int(sbase[i]), n))
+    if scratch_rows >= (1 << 14):
+        raise NotImplementedError("scratch too large for the pool meta word")
     sizes = np.array([len(it["rows"]) for it in insts], np.int32)
     row_off = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)
     rows = np.concatenate([it["rows"] for it in insts]).astype(np.int32)
@@ -264,12 +296,13 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
             for j in range(ne):
                 e = enter[enter_off[s] + j]
                 i = e & (LOAD_FLAG - 1)
-                rec[s, 6 + 2 * j] = e
-                rec[s, 7 + 2 * j] = int(base[i]) | (int(sizes[i]) << 16) | (int(keeps_arr[i]) << 24)
+                rec[s, 6 + 3 * j] = e
+                rec[s, 7 + 3 * j] = int(base[i]) | (int(sizes[i]) << 16) | (int(keeps_arr[i]) << 24)
+                rec[s, 8 + 3 * j] = int(sbase[i])
         if s + 1 < ndoy:
-            rec[s, 14] = use_off[s + 1]
-            rec[s, 15] = use_off[s + 2] - use_off[s + 1]
-        rec[s, 16] = enter_off[s]
+            rec[s, 18] = use_off[s + 1]
+            rec[s, 19] = use_off[s + 2] - use_off[s + 1]
+        rec[s, 20] = enter_off[s]
     step_rec = rec.astype(np.uint32).view(np.int32).reshape(-1)
 
     def arr(x):
@@ -277,8 +310,8 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
         return a if a.size else np.zeros(1, np.int32)
 
     return ClimPlanHost(
-        nsteps=ndoy, pool_rows=int(pool_rows), nmax=int(nmax), max_size=int(sizes.max()),
-        inst_base=base, inst_size=sizes, inst_keep=np.asarray(keeps, np.int32),
+        nsteps=ndoy, pool_rows=int(pool_rows), nmax=int(nmax), max_size=int(sizes.max()), scratch_rows=int(scratch_rows),
+        inst_base=base, inst_size=sizes, inst_keep=np.asarray(keeps, np.int32), inst_sbase=sbase,
         inst_row_off=row_off, rows=rows,
         leave_off=arr(leave_off), leave=arr(leave), enter_off=arr(enter_off), enter=arr(enter),
         use_off=arr(use_off), use=arr(use), step_rec=step_rec, q=float(q),
