@@ -203,7 +203,7 @@ def run_ours(args):
     # roofline of the dominant kernel (climatology sweep): algorithmic bytes / measured duration
     peak, peak_src = hbm_peak()
     sweep_ms = float(np.mean(per_kernel["xmhw_clim_sweep_f32"]))
-    sweep_bytes = ngrid * T * 4 + nocean * 2 * 366 * 8
+    sweep_bytes = ngrid * T * 4 + nocean * 2 * 366 * 8       # DESIGN.md 3.1
     ach = sweep_bytes / (sweep_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -219,8 +219,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         del ts
         torch.cuda.empty_cache()
+        cap = int(nev * 1.05) + 1024
         out = {"thresh": torch.empty((366, ngrid), dtype=torch.float64, pin_memory=True),
-               "seas": torch.empty((366, ngrid), dtype=torch.float64, pin_memory=True)}
+               "seas": torch.empty((366, ngrid), dtype=torch.float64, pin_memory=True),
+               "nvalid": torch.empty(ngrid, dtype=torch.int32, pin_memory=True),
+               "ev_i32": torch.empty((core.EI_COUNT, cap), dtype=torch.int32, pin_memory=True),
+               "ev_f64": torch.empty((core.EF_COUNT, cap), dtype=torch.float64, pin_memory=True)}
         core.threshold_detect_host(host, doy, 366, device=dev, out=out)      # warm-up
         barrier()
         t0 = time.perf_counter()

@@ -1,0 +1,78 @@
+"""CPU-side tests of the public API layer: argument validation raises the reference's
+XmhwException for the reference's conditions BEFORE any launch, calendar / doy helpers,
+labelled containers, synthetic generator determinism."""
+import numpy as np
+import pytest
+
+from oracle import xmhw_oracle as O
+from xmhw_b200 import identify, labeled, synth
+from xmhw_b200.exception import XmhwException
+from xmhw_b200.xmhw import detect, threshold
+
+
+def _cube(T=40, ny=3, nx=4):
+    time = np.arange(np.datetime64("2001-01-01"), np.datetime64("2001-01-01") + np.timedelta64(T, "D"))
+    data = np.random.default_rng(0).normal(15, 1, (T, ny, nx)).astype(np.float32)
+    return labeled.DataArray(data, ("time", "lat", "lon"),
+                             {"time": time, "lat": np.arange(ny) * 0.25, "lon": np.arange(nx) * 0.25})
+
+
+def test_threshold_validation():
+    da = _cube()
+    with pytest.raises(XmhwException):            # xmhw.py:103-104
+        threshold(da, smoothPercentileWidth=30)
+    with pytest.raises(XmhwException):            # xmhw.py:105-109
+        threshold(da, tdim="t")
+    land = labeled.DataArray(np.full((40, 3, 4), np.nan, np.float32), da.dims, da.coords)
+    with pytest.raises(XmhwException):            # identify.py:527-528
+        threshold(land)
+    empty = labeled.DataArray(np.zeros((40, 0, 4), np.float32), da.dims,
+                              {"time": da.coords["time"], "lat": np.zeros(0), "lon": da.coords["lon"]})
+    with pytest.raises(XmhwException):            # identify.py:514-516
+        threshold(empty)
+    with pytest.raises(XmhwException):            # identify.py:61-66 incomplete years with tstep
+        threshold(_cube(T=400), tstep=True)
+
+
+def test_detect_validation():
+    da = _cube()
+    th = labeled.DataArray(np.zeros((366, 3, 4)), ("doy", "lat", "lon"),
+                           {"doy": np.arange(1, 367), "lat": da.coords["lat"], "lon": da.coords["lon"]})
+    with pytest.raises(XmhwException):            # xmhw.py:373-377
+        detect(da, th, th, maxGap=5, minDuration=5)
+    with pytest.raises(XmhwException):
+        detect(da, th, th, tdim="t")
+
+
+def test_add_doy_and_calendar(oisst):
+    doy, ndoy = identify.add_doy(oisst["time"])
+    assert ndoy == 366 and np.array_equal(doy, O.add_doy(oisst["time"]))
+    t5 = np.arange(np.datetime64("2001-01-01"), np.datetime64("2003-01-01"), np.timedelta64(5, "D"))[:146]
+    doy5, n5 = identify.add_doy(t5, keep_tstep=True)
+    assert n5 == 73 and np.array_equal(doy5, np.tile(np.arange(1, 74), 2))
+    assert identify.get_calendar(t5, {"calendar": "360_day"}) == 360
+    assert identify.get_calendar(t5, None, {"calendar": "noleap"}) == 365
+    assert identify.get_calendar(t5) == 365.25
+    assert identify.get_calendar(t5, {"calendar": "360"}) == 360      # identify.py:125-126
+
+
+def test_synth_is_deterministic_and_shardable():
+    tm = synth.daily_time(2001, 2002)
+    sea = synth.season_table(tm)
+    a = synth.synth_sst(len(tm), 64, sea)
+    b = np.concatenate([synth.synth_sst(len(tm), 32, sea, cell0=0), synth.synth_sst(len(tm), 32, sea, cell0=32)], 1)
+    assert np.array_equal(a, b)                      # a shard can be generated on its own
+    assert np.allclose(a * 100, np.rint(a * 100), atol=1e-3)        # 0.01 degC quantisation
+    m = synth.land_mask(40, 80)
+    assert m[-1].all() and m[:, -1].all() and 0.25 < m.mean() < 0.45
+    assert np.array_equal(synth.doy366(tm), O.add_doy(tm))
+
+
+def test_flip_cold():
+    # test_features.py:90-100
+    from xmhw_b200.features import flip_cold
+    y = np.array([1.0, 2.0, np.nan])
+    out = flip_cold({"intensity_sum_dummy": y.copy(), "intensity_var_dummy": y.copy(), "dummy": y.copy()})
+    assert np.array_equal(out["intensity_sum_dummy"], -y, equal_nan=True)
+    assert np.array_equal(out["intensity_var_dummy"], y, equal_nan=True)
+    assert np.array_equal(out["dummy"], y, equal_nan=True)

@@ -1,0 +1,89 @@
+"""GPU tests of the drop-in API (xmhw_b200.xmhw.threshold / detect) on labelled arrays:
+reference test cube end to end against the oracle and the golden climatology files."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def api():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xmhw_b200 import labeled, xmhw
+    return xmhw, labeled
+
+
+def test_oisst_end_to_end(api, oisst, clim_gold):
+    xmhw, labeled = api
+    from oracle import xmhw_oracle as O
+    da = labeled.DataArray(oisst["sst"], ("time", "lat", "lon"),
+                           {"time": oisst["time"], "lat": oisst["lat"], "lon": oisst["lon"]})
+    clim = xmhw.threshold(da)
+    th, se = clim["thresh"], clim["seas"]
+    assert th.dims == ("doy", "lat", "lon") and th.values.dtype == np.float64
+    ocean = ~np.isnan(oisst["sst"]).all(0)
+    assert th.shape == (366, int(ocean.any(1).sum()), int(ocean.any(0).sum()))
+    # golden points [1,2] and [5,3] (test_xmhw.py:24-66) -> positions in the land-trimmed grid
+    lat_keep, lon_keep = np.nonzero(ocean.any(1))[0], np.nonzero(ocean.any(0))[0]
+    smooth, _ = clim_gold
+    for (iy, ix), n in (((1, 2), "1"), ((5, 3), "2")):
+        jy, jx = int(np.searchsorted(lat_keep, iy)), int(np.searchsorted(lon_keep, ix))
+        np.testing.assert_almost_equal(th.values[82:, jy, jx], smooth["thresh" + n][82:], decimal=6)
+        np.testing.assert_almost_equal(se.values[82:, jy, jx], smooth["seas" + n][82:], decimal=4)
+    mhw = xmhw.detect(da, th, se)
+    assert mhw["intensity_max"].dims == ("events", "lat", "lon")
+    doy = O.add_doy(oisst["time"])
+    flat = oisst["sst"].reshape(len(doy), -1)
+    oth, ose = O.threshold(flat, doy, 366)
+    exp = O.detect(flat, doy, oth, ose)
+    assert int(np.sum(~np.isnan(mhw["event"].values))) == len(exp["cell"])
+    jy, jx = int(np.searchsorted(lat_keep, 1)), int(np.searchsorted(lon_keep, 2))
+    col = mhw["index_start"].values[:, jy, jx]
+    assert col[~np.isnan(col)].tolist() == [1, 75, 99, 114, 138, 172, 225, 613, 709]
+    assert mhw["time_start"].values.dtype.kind == "M"
+    comp = xmhw.detect(da, th, se, compact=True)
+    assert len(comp["event"].values) == len(exp["cell"])
+    np.testing.assert_allclose(np.sort(comp["intensity_cumulative"].values), np.sort(exp["intensity_cumulative"]),
+                               rtol=1e-9)
+
+
+def test_point_series_and_cold_spells(api, oisst):
+    """BASELINE config 1: single-point series (xmhw.py:122-126 point path) + coldSpells sign rules."""
+    xmhw, labeled = api
+    from oracle import xmhw_oracle as O
+    ts = oisst["sst"][:, 1, 2]
+    da = labeled.DataArray(ts, ("time",), {"time": oisst["time"]})
+    clim = xmhw.threshold(da)
+    doy = O.add_doy(oisst["time"])
+    oth, ose = O.threshold(ts, doy, 366)
+    assert np.array_equal(clim["thresh"].values, oth[:, 0]) and clim["thresh"].dims == ("doy",)
+    mhw = xmhw.detect(da, clim["thresh"], clim["seas"])
+    assert mhw["index_start"].values.tolist() == [1, 75, 99, 114, 138, 172, 225, 613, 709]
+    cold = xmhw.threshold(da, coldSpells=True, pctile=90)
+    oth_c, ose_c = O.threshold(-ts, doy, 366)
+    assert np.array_equal(cold["thresh"].values, oth_c[:, 0])          # returned for the flipped series
+    mc = xmhw.detect(da, cold["thresh"], cold["seas"], coldSpells=True)
+    exp = O.detect(-ts, doy, oth_c, ose_c)
+    assert mc["index_start"].values.tolist() == exp["index_start"].tolist()
+    np.testing.assert_allclose(mc["intensity_max"].values, -exp["intensity_max"])     # flipped back
+    np.testing.assert_allclose(mc["intensity_var"].values, exp["intensity_var"])      # "_var" not flipped
+    np.testing.assert_allclose(mc["rate_onset"].values, exp["rate_onset"])
+
+
+def test_climatology_period_and_anynans(api, oisst):
+    xmhw, labeled = api
+    from oracle import xmhw_oracle as O
+    sst = oisst["sst"].copy()
+    sst[5, 1, 2] = np.nan                 # one NaN -> the cell is dropped with anynans=True
+    da = labeled.DataArray(sst, ("time", "lat", "lon"), {"time": oisst["time"], "lat": oisst["lat"], "lon": oisst["lon"]})
+    clim = xmhw.threshold(da, anynans=True, climatologyPeriod=[2003, 2003], smoothPercentile=False)
+    sel = oisst["time"] < np.datetime64("2004-01-01")
+    doy = O.add_doy(oisst["time"][sel])
+    flat = sst[sel].reshape(int(sel.sum()), -1)
+    keep = ~np.isnan(flat).any(0)
+    oth, _ = O.threshold(flat, doy, 366, smoothPercentile=False)
+    got = clim["thresh"].values
+    assert got.shape[0] == 365                     # doy 60 has no sample in 2003: dropped like the groupby does
+    assert int(np.sum(~np.isnan(got[0]))) == int(keep.sum())

@@ -258,9 +258,19 @@ def threshold_detect_host(ts_host, doy, ndoy, pctile=90, windowHalfWidth=5, smoo
             res["thresh"], res["seas"] = out["thresh"], out["seas"]
         else:
             res["thresh"], res["seas"] = th.cpu(), se.cpu()
-        res["nvalid"] = ev.nvalid.cpu()
-        res["ev_i32"] = ev.i32[:, :ev.n].cpu()
-        res["ev_f64"] = ev.f64[:, :ev.n].cpu()
+        if out is not None and "ev_i32" in out and out["ev_i32"].shape[1] >= ev.n:
+            # preallocated pinned event buffers [EI_COUNT, cap] / [EF_COUNT, cap]
+            out["ev_i32"][:, :ev.n].copy_(ev.i32[:, :ev.n], non_blocking=True)
+            out["ev_f64"][:, :ev.n].copy_(ev.f64[:, :ev.n], non_blocking=True)
+            res["ev_i32"], res["ev_f64"] = out["ev_i32"][:, :ev.n], out["ev_f64"][:, :ev.n]
+        else:
+            res["ev_i32"] = ev.i32[:, :ev.n].cpu()
+            res["ev_f64"] = ev.f64[:, :ev.n].cpu()
+        if out is not None and "nvalid" in out:
+            out["nvalid"].copy_(ev.nvalid, non_blocking=True)
+            res["nvalid"] = out["nvalid"]
+        else:
+            res["nvalid"] = ev.nvalid.cpu()
         torch.cuda.current_stream().synchronize()
     res["n_events"] = ev.n
     res["h2d_bytes"] = T * ngrid * 4
