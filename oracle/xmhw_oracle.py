@@ -201,12 +201,19 @@ def threshold(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercentile=True
         x = ts[idx]
         thresh[d - 1] = quantile_linear(x, q)
         seas[d - 1] = seasonal_mean(x)
-    if not tstep and ndoy >= 61:
-        thresh[59] = feb29(thresh)
-        seas[59] = feb29(seas)
+    # a doy that never occurs in the series is absent from the reference's groupby output:
+    # feb29 / runavg act on the compacted doy axis (identify.py:233-241, :175-180)
+    present = np.isin(np.arange(1, ndoy + 1), np.unique(doy))
+    t_c, s_c = thresh[present], seas[present]
+    if not tstep and ndoy >= 61 and present[58:61].all():
+        i60 = int(np.sum(present[:59]))
+        sub = np.stack([t_c[i60 - 1], t_c[i60], t_c[i60 + 1]]), np.stack([s_c[i60 - 1], s_c[i60], s_c[i60 + 1]])
+        t_c[i60] = feb29(np.concatenate([np.full((58,) + sub[0].shape[1:], np.nan), sub[0]]))
+        s_c[i60] = feb29(np.concatenate([np.full((58,) + sub[1].shape[1:], np.nan), sub[1]]))
     if smoothPercentile:
-        thresh = runavg(thresh, smoothPercentileWidth)
-        seas = runavg(seas, smoothPercentileWidth)
+        t_c = runavg(t_c, smoothPercentileWidth)
+        s_c = runavg(s_c, smoothPercentileWidth)
+    thresh[present], seas[present] = t_c, s_c
     return thresh, seas
 
 

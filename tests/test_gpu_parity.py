@@ -221,3 +221,17 @@ def test_regional_properties(core):
     sub = {k: v[sel] for k, v in got.items()}
     sub["cell"] = np.searchsorted(cells, sub["cell"])
     assert_events_match(sub, exp, _float_fields())
+
+
+def test_series_without_leap_year(core):
+    """doy 60 never occurs (2001-2003): absent from the reference's groupby output, so feb29 /
+    runavg act on the compacted 365-doy axis and doy 60 comes back NaN."""
+    from xmhw_b200 import synth
+    O = _oracle()
+    time = synth.daily_time(2001, 2003)
+    doy = synth.doy366(time)
+    ts_h = synth.synth_sst(len(time), 40, synth.season_table(time))
+    ts, th, se, th_h, se_h = _clim_check(core, ts_h, doy, 366)
+    assert np.isnan(th_h[59]).all() and not np.isnan(th_h[58]).any()
+    ev = core.detect_arrays(ts, doy, 366, th, se)
+    assert_events_match(ev.to_numpy(), O.detect(ts_h, doy, th_h, se_h), _float_fields())

@@ -105,6 +105,11 @@ def _doy_tables(doy, ndoy, device):
     return hit
 
 
+def _relabel_keeps_feb(labels):
+    """feb29 uses positions 59,60,61: valid after compaction only if labels 1..61 are all present."""
+    return len(labels) >= 61 and bool((labels[:61] == np.arange(1, 62)).all())
+
+
 def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercentile=True,
                      smoothPercentileWidth=31, feb29=True, return_raw=False):
     """Climatological threshold and seasonal mean for every cell of ts.
@@ -122,6 +127,22 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
         raise ValueError("doy must have one label per time step")
     if smoothPercentile and smoothPercentileWidth % 2 == 0:
         raise ValueError("smoothPercentileWidth should be odd")
+    # A doy label that never occurs (doy 60 in a series without a leap year) does not exist in
+    # the reference's groupby output, so feb29/runavg act on the compacted doy axis
+    # (identify.py:233-241, :175-180): relabel to 1..n, run, scatter back with NaN rows.
+    labels = np.unique(np.asarray(doy))
+    if len(labels) < ndoy and not return_raw:
+        sub = threshold_arrays(ts, np.searchsorted(labels, doy) + 1, len(labels), pctile, windowHalfWidth,
+                               smoothPercentile, smoothPercentileWidth,
+                               feb29=bool(feb29) and ndoy >= 61 and bool(np.isin([59, 60, 61], labels).all())
+                               and _relabel_keeps_feb(labels))
+        rows = torch.from_numpy(labels - 1).to(ts.device)
+        outs = []
+        for a in sub:
+            full = torch.full((ndoy, ngrid), float("nan"), dtype=torch.float64, device=ts.device)
+            full[rows] = a
+            outs.append(full)
+        return tuple(outs)
     with torch.cuda.device(ts.device):
         dp = device_plan(doy, ndoy, windowHalfWidth, pctile / 100.0, ts.device)
         st = _stream()

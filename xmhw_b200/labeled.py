@@ -47,6 +47,11 @@ class Dataset:
         return self.data_vars[k]
 
     def __setitem__(self, k, v):
+        # a variable carries the coordinates of its own dimensions (like xarray)
+        if isinstance(v, DataArray):
+            for d in v.dims:
+                if d not in v.coords and d in self.coords and np.ndim(self.coords[d]) == 1:
+                    v.coords[d] = self.coords[d]
         self.data_vars[k] = v
 
     def __contains__(self, k):

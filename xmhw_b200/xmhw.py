@@ -160,6 +160,7 @@ def threshold(temp, tdim="time", climatologyPeriod=[None, None], pctile=90, wind
             out_coords[d] = c[srt]
         dims = ("doy",) + tuple(other)
     else:
+        th_h, se_h = th_h[:, 0], se_h[:, 0]
         out_coords, dims = {"doy": doy_coord}, ("doy",)
     # a doy without samples disappears from the reference's groupby output (identify.py:233)
     present = ~np.isnan(th_h).all(axis=tuple(range(1, th_h.ndim))) if th_h.ndim > 1 else ~np.isnan(th_h)
