@@ -281,8 +281,10 @@ def threshold_detect_host(ts_host, doy, ndoy, pctile=90, windowHalfWidth=5, smoo
             res["thresh"], res["seas"] = th.cpu(), se.cpu()
         if out is not None and "ev_i32" in out and out["ev_i32"].shape[1] >= ev.n:
             # preallocated pinned event buffers [EI_COUNT, cap] / [EF_COUNT, cap]
-            out["ev_i32"][:, :ev.n].copy_(ev.i32[:, :ev.n], non_blocking=True)
-            out["ev_f64"][:, :ev.n].copy_(ev.f64[:, :ev.n], non_blocking=True)
+            for k in range(EI_COUNT):       # row by row: every copy is one contiguous DMA
+                out["ev_i32"][k, :ev.n].copy_(ev.i32[k, :ev.n], non_blocking=True)
+            for k in range(EF_COUNT):
+                out["ev_f64"][k, :ev.n].copy_(ev.f64[k, :ev.n], non_blocking=True)
             res["ev_i32"], res["ev_f64"] = out["ev_i32"][:, :ev.n], out["ev_f64"][:, :ev.n]
         else:
             res["ev_i32"] = ev.i32[:, :ev.n].cpu()

@@ -137,16 +137,18 @@ enum { STEP_COUNTS = 0,      // n_leave | n_enter << 8 | n_use << 16 | overflow 
 // Instance block layout in the pool (row = 32 words, word index = lane):
 //   row 0      meta: len | ptr << 6 | keep << 12 | scratch base row << 18
 //              (len = valid samples, ptr = #keys above the cut, keep = key rows held here)
-//   row 1, 2   f64 sum of the valid samples (lo, hi words)
-//   row 3      cinc: smallest key above the cut (key[ptr-1]), 0xffffffff if ptr == 0
-//   row 4      cexc: largest key below the cut (key[ptr]),    0 if ptr == len
-//   row 5 + r  r-th largest key, r < keep <= size.  Only the top `keep` keys of a list
+//   row 1      cinc: smallest key above the cut (key[ptr-1]), 0xffffffff if ptr == 0
+//   row 2      cexc: largest key below the cut (key[ptr]),    0 if ptr == len
+//   row 3 + r  r-th largest key, r < keep <= size.  Only the top `keep` keys of a list
 //              live in shared memory; the sorted remainder is parked in a per-warp global
 //              scratch (L2-resident, one load per access), so `keep` can be small and
 //              many more warps stay resident per SM (the sweep is latency-chained).
+// Scratch block of a list (rows of 32 words): row 0, 1 = f64 sum of its valid samples
+// (lo, hi words), row 2 + i = key of rank keep + i.  Scratch rows 0, 1 of every warp are
+// the null list's sum (0.0).
 // Block 0 of every pool is a "null list" (len 0) used to pad scans to multiples of 4;
 // the two rows after plan.pool_rows hold the staged base rows of the lists in use.
-enum { POOL_META = 0, POOL_SUM = 1, POOL_CINC = 3, POOL_CEXC = 4, POOL_KEYS = 5, POOL_NULL_ROWS = 5,
+enum { POOL_META = 0, POOL_CINC = 1, POOL_CEXC = 2, POOL_KEYS = 3, POOL_NULL_ROWS = 3, SCR_SUM = 0, SCR_KEYS = 2,
        POOL_STAGE_ROWS = 2, MAX_LISTS = 64 };
 
 XMHW_HD int meta_len(uint32_t m) { return (int)(m & 63u); }
@@ -236,7 +238,7 @@ struct Sweeper {
   XMHW_HD uint32_t key_at(int base, uint32_t meta, int r, bool need) {
     const int keep = meta_keep(meta);
     uint32_t k = 0u;
-    if (need) k = r < keep ? at(base + POOL_KEYS + r) : scratch[(size_t)(meta_sbase(meta) + r - keep) * 32 + lane];
+    if (need) k = r < keep ? at(base + POOL_KEYS + r) : scratch[(size_t)(meta_sbase(meta) + SCR_KEYS + r - keep) * 32 + lane];
     return k;
   }
 
@@ -268,14 +270,14 @@ struct Sweeper {
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         if (i < keep) at(base + POOL_KEYS + i) = k[i];
-        else if (i < size) scratch[(size_t)(sbase + i - keep) * 32 + lane] = k[i];
+        else if (i < size) scratch[(size_t)(sbase + SCR_KEYS + i - keep) * 32 + lane] = k[i];
         const bool ab = k[i] > pivot;
         ptr += ab;
         if (ab) cinc = k[i]; else cexc = cexc > k[i] ? cexc : k[i];
       }
     }
-    at(base + POOL_SUM) = f64_lo(sum);
-    at(base + POOL_SUM + 1) = f64_hi(sum);
+    scratch[(size_t)(sbase + SCR_SUM) * 32 + lane] = f64_lo(sum);
+    scratch[(size_t)(sbase + SCR_SUM + 1) * 32 + lane] = f64_hi(sum);
     at(base + POOL_META) = (uint32_t)len | ((uint32_t)ptr << 6) | ((uint32_t)keep << 12) | ((uint32_t)sbase << 18);
     at(base + POOL_CINC) = cinc;
     at(base + POOL_CEXC) = cexc;
@@ -309,8 +311,8 @@ struct Sweeper {
   }
 
   XMHW_HD void init() {
-    at(POOL_META) = 0u; at(POOL_SUM) = 0u; at(POOL_SUM + 1) = 0u;
-    at(POOL_CINC) = 0xffffffffu; at(POOL_CEXC) = 0u;
+    at(POOL_META) = 0u; at(POOL_CINC) = 0xffffffffu; at(POOL_CEXC) = 0u;
+    scratch[SCR_SUM * 32 + lane] = 0u; scratch[(SCR_SUM + 1) * 32 + lane] = 0u;
     total_enter = XMHW_LDG(p.enter_off + p.nsteps);
     rec_next = env.vload(p.step_rec, STEP_WORDS, lane);
     use_next = env.vload(p.use + XMHW_LDG(p.step_rec + STEP_USE_OFF),
@@ -398,7 +400,7 @@ struct Sweeper {
       const int d = live ? C - target : 0;
       if (!env.any(d != 0)) break;
       // ---- drop the smallest keys above the cut (d > 0)
-      {
+      if (env.any(d > 0)) {
         const bool mv = d > 0;
         const uint32_t meta = at(bi1 + POOL_META);
         const int pa = meta_ptr(meta);                          // >= 1 when mv
@@ -432,7 +434,7 @@ struct Sweeper {
         }
       }
       // ---- add the largest keys below the cut (d < 0)
-      {
+      if (env.any(d < 0)) {
         const bool mv = d < 0;
         const uint32_t meta = at(be1 + POOL_META);
         const int pa = meta_ptr(meta), la = meta_len(meta);     // pa < la when mv
@@ -468,8 +470,8 @@ struct Sweeper {
     // f64 sum of the window; a = i1 (smallest key above the cut), b = next one up
     double sum = 0.0;
     for (int j = 0; j < m4; ++j) {
-      const int x = (int)ub[j];
-      sum = sum + f64_from(at(x + POOL_SUM), at(x + POOL_SUM + 1));
+      const size_t sb = (size_t)meta_sbase(at((int)ub[j] + POOL_META)) * 32 + lane;
+      sum = sum + f64_from(scratch[sb + SCR_SUM * 32], scratch[sb + (SCR_SUM + 1) * 32]);
     }
     const uint32_t m1 = i1, m2 = i2;
     const uint32_t meta1 = at(bi1 + POOL_META);

@@ -28,8 +28,9 @@ from dataclasses import dataclass
 import numpy as np
 
 MAX_LIST = 32          # rows per instance = keys per register sorting network
-META_ROWS = 5          # meta word, f64 sum (2 words), cinc, cexc per instance and lane
-NULL_ROWS = 5          # block 0 of the pool is the kernel's null list
+META_ROWS = 3          # meta word, cinc, cexc per instance and lane
+NULL_ROWS = 3          # block 0 of the pool is the kernel's null list
+SCRATCH_HEAD = 2       # scratch rows per instance before its tail keys: f64 sum (lo, hi)
 STAGE_ROWS = 2         # two rows after the pool: staged bases of the lists in use
 MAX_LISTS = 64
 LOAD_FLAG = 1 << 30
@@ -245,9 +246,9 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
     if max_lists > MAX_LISTS:
         raise NotImplementedError("more than %d sorted lists per window (windowHalfWidth too large)" % MAX_LISTS)
     # global scratch rows for the sorted keys past `keep` (same lifetime as the pool block)
-    sfree = [(0, 1 << 30)]
+    sfree = [(SCRATCH_HEAD, 1 << 30)]       # rows 0,1 = sum of the null list
     sbase = np.zeros(ninst, np.int32)
-    scratch_rows = 0
+    scratch_rows = SCRATCH_HEAD
     srel = [[] for _ in range(ndoy + 1)]
     for s in range(ndoy):
         for (a, n) in srel[s]:
@@ -264,9 +265,7 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
             if not e & LOAD_FLAG:
                 continue
             i = e & (LOAD_FLAG - 1)
-            n = sizes_list[i] - keeps[i]
-            if n <= 0:
-                continue
+            n = SCRATCH_HEAD + max(0, sizes_list[i] - keeps[i])
             for k, (a, sz) in enumerate(sfree):
                 if sz >= n:
                     sfree[k] = (a + n, sz - n)
