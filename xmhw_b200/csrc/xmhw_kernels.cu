@@ -47,7 +47,7 @@ static_assert((int)XMHW_EI_COUNT == (int)EI_COUNT && (int)XMHW_EF_COUNT == (int)
 // Shared memory per warp: plan.pool_rows rows of 32 words (sorted lists of the
 // current +-w window, their f64 sums and per-lane cut pointers).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) clim_sweep_kernel(ClimPlan p, const float* __restrict__ ts,
+__global__ void __launch_bounds__(32, 20) clim_sweep_kernel(ClimPlan p, const float* __restrict__ ts,
                                                         int64_t ngrid, double* __restrict__ thr,
                                                         double* __restrict__ seas, uint32_t* __restrict__ scratch) {
   extern __shared__ uint32_t pool[];

@@ -382,7 +382,7 @@ struct Sweeper {
     while (true) {
       i1 = 0xffffffffu; i2 = 0xffffffffu; e1 = 0u; e2 = 0u;
       bi1 = 0; bi2 = 0; be1 = 0; be2 = 0;
-#pragma unroll 2
+#pragma unroll 4
       for (int j = 0; j < m4; ++j) {
         const int x = (int)ub[j];
         const uint32_t ki = at(x + POOL_CINC), ke = at(x + POOL_CEXC);
