@@ -138,6 +138,11 @@ int xmhw_event_stats_f32(const float* ts, int64_t T, int64_t ngrid, const int32_
                          const double* thresh, const double* seas, int64_t nev, int64_t cap,
                          int32_t* ev_i32, double* ev_f64, void* stream);
 
+/* Strided 2-D copy (cudaMemcpy2DAsync) used to move a column block of the (time, cell) host
+ * array to / from the device: kind 0 = host->device, 1 = device->host, 2 = device->device. */
+int xmhw_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                      int64_t width_bytes, int64_t height, int32_t kind, void* stream);
+
 /* Deterministic synthetic SST: seasonal cycle + AR(1) noise rounded to
  * 0.01 degC, NaN on land; bit-identical to xmhw_b200/synth.py on the host.
  * season [T + 366] f64 host-computed sine table, land [ngrid] u8 (1 = land).    */

@@ -235,3 +235,24 @@ def test_series_without_leap_year(core):
     assert np.isnan(th_h[59]).all() and not np.isnan(th_h[58]).any()
     ev = core.detect_arrays(ts, doy, 366, th, se)
     assert_events_match(ev.to_numpy(), O.detect(ts_h, doy, th_h, se_h), _float_fields())
+
+
+def test_host_buffer_entry_point(core):
+    """threshold_detect_host (pinned host series in, host results out, column blocks pipelined on
+    three streams) gives exactly the single-shot device result."""
+    from xmhw_b200 import synth
+    time = synth.daily_time(1995, 2004)
+    doy = synth.doy366(time)
+    land = synth.land_mask(5, 40).ravel()
+    ts_h = synth.synth_sst(len(time), 200, synth.season_table(time), land=land, nan_ppm=3000)
+    host = torch.from_numpy(ts_h).pin_memory()
+    res = core.threshold_detect_host(host, doy, 366, slabs=3)
+    ts = torch.from_numpy(ts_h).cuda()
+    th, se = core.threshold_arrays(ts, doy, 366)
+    ev = core.detect_arrays(ts, doy, 366, th, se)
+    assert np.array_equal(res["thresh"].numpy(), th.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(res["seas"].numpy(), se.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(res["nvalid"].numpy(), ev.nvalid.cpu().numpy())
+    assert res["n_events"] == ev.n
+    assert np.array_equal(res["ev_i32"].numpy(), ev.i32[:, :ev.n].cpu().numpy())
+    assert np.array_equal(res["ev_f64"].numpy(), ev.f64[:, :ev.n].cpu().numpy(), equal_nan=True)

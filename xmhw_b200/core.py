@@ -254,48 +254,89 @@ def synth_sst_device(T, ngrid, season, land=None, cell0=0, seed=None, nan_ppm=0,
 
 def threshold_detect_host(ts_host, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercentile=True,
                           smoothPercentileWidth=31, feb29=True, minDuration=5, joinGaps=True, maxGap=2,
-                          device="cuda", out=None):
-    """Host-buffer entry point (what the reference-side binding calls): `ts_host` is a
-    (pinned) host float32 tensor/array [T, ngrid]; the series is copied to the device,
-    threshold + detect run there, and thresh/seas/event table are copied back to host
-    memory.  Returns dict(thresh, seas, nvalid, events) of host arrays plus byte counts.
-    `out` may hold preallocated pinned result tensors ('thresh', 'seas') to reuse."""
+                          device="cuda", out=None, slabs=8):
+    """Host-buffer entry point (what the reference-side binding calls): `ts_host` is a pinned
+    host float32 tensor [T, ngrid].  The grid is cut into `slabs` column blocks; the strided
+    host->device copy of block i+1, threshold + detect of block i and the device->host copy of
+    the results of block i-1 overlap on three streams (cells are independent, so blocks are).
+    Returns dict(thresh, seas [ndoy, ngrid] host, nvalid, ev_i32, ev_f64, n_events, byte counts);
+    `out` may hold preallocated pinned result tensors (thresh, seas, nvalid, ev_i32, ev_f64)."""
     dev = torch.device(device)
     if isinstance(ts_host, np.ndarray):
         ts_host = torch.from_numpy(ts_host)
-    if ts_host.dtype != torch.float32 or ts_host.dim() != 2:
-        raise TypeError("ts_host must be float32 [T, ngrid]")
+    if ts_host.dtype != torch.float32 or ts_host.dim() != 2 or not ts_host.is_contiguous():
+        raise TypeError("ts_host must be a contiguous float32 [T, ngrid] host tensor")
     T, ngrid = ts_host.shape
+    out = {} if out is None else out
+    pin = ts_host.is_pinned()
+
+    def host_buf(name, shape, dtype):
+        if name in out and tuple(out[name].shape[:1]) == tuple(shape[:1]) and out[name].shape[-1] >= shape[-1]:
+            return out[name]
+        return torch.empty(shape, dtype=dtype, pin_memory=pin)
+
+    th_h = host_buf("thresh", (ndoy, ngrid), torch.float64)
+    se_h = host_buf("seas", (ndoy, ngrid), torch.float64)
+    nv_h = host_buf("nvalid", (ngrid,), torch.int32)
+    w = -(-ngrid // max(1, int(slabs)))
+    w = -(-w // 32) * 32
+    ranges = [(a, min(ngrid, a + w)) for a in range(0, ngrid, w)]
+    ev_parts = []
     with torch.cuda.device(dev):
-        ts = torch.empty((T, ngrid), dtype=torch.float32, device=dev)
-        ts.copy_(ts_host, non_blocking=True)
-        th, se = threshold_arrays(ts, doy, ndoy, pctile, windowHalfWidth, smoothPercentile,
-                                  smoothPercentileWidth, feb29)
-        ev = detect_arrays(ts, doy, ndoy, th, se, minDuration, joinGaps, maxGap)
-        res = {}
-        if out is not None and "thresh" in out:
-            out["thresh"].copy_(th, non_blocking=True)
-            out["seas"].copy_(se, non_blocking=True)
-            res["thresh"], res["seas"] = out["thresh"], out["seas"]
-        else:
-            res["thresh"], res["seas"] = th.cpu(), se.cpu()
-        if out is not None and "ev_i32" in out and out["ev_i32"].shape[1] >= ev.n:
-            # preallocated pinned event buffers [EI_COUNT, cap] / [EF_COUNT, cap]
-            for k in range(EI_COUNT):       # row by row: every copy is one contiguous DMA
-                out["ev_i32"][k, :ev.n].copy_(ev.i32[k, :ev.n], non_blocking=True)
-            for k in range(EF_COUNT):
-                out["ev_f64"][k, :ev.n].copy_(ev.f64[k, :ev.n], non_blocking=True)
-            res["ev_i32"], res["ev_f64"] = out["ev_i32"][:, :ev.n], out["ev_f64"][:, :ev.n]
-        else:
-            res["ev_i32"] = ev.i32[:, :ev.n].cpu()
-            res["ev_f64"] = ev.f64[:, :ev.n].cpu()
-        if out is not None and "nvalid" in out:
-            out["nvalid"].copy_(ev.nvalid, non_blocking=True)
-            res["nvalid"] = out["nvalid"]
-        else:
-            res["nvalid"] = ev.nvalid.cpu()
-        torch.cuda.current_stream().synchronize()
-    res["n_events"] = ev.n
-    res["h2d_bytes"] = T * ngrid * 4
-    res["d2h_bytes"] = 2 * ndoy * ngrid * 8 + ngrid * 4 + ev.n * (EI_COUNT * 4 + EF_COUNT * 8)
-    return res
+        main = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        bufs = [torch.empty((T, w), dtype=torch.float32, device=dev) for _ in range(2)]
+        free_ev = [None, None]
+        loaded = {}
+
+        def start_load(i):
+            a, b = ranges[i]
+            with torch.cuda.stream(s_in):
+                if free_ev[i % 2] is not None:
+                    s_in.wait_event(free_ev[i % 2])
+                dst = bufs[i % 2][:, :b - a] if b - a == w else bufs[i % 2].view(-1)[:T * (b - a)].view(T, b - a)
+                check(lib.xmhw_copy2d_async(_ptr(dst), (b - a) * 4, ts_host.data_ptr() + a * 4, ngrid * 4,
+                                            (b - a) * 4, T, 0, s_in.cuda_stream), "xmhw_copy2d_async")
+                e = torch.cuda.Event()
+                e.record(s_in)
+                loaded[i] = (dst, e)
+
+        start_load(0)
+        keep_alive = []
+        for i, (a, b) in enumerate(ranges):
+            if i + 1 < len(ranges):
+                start_load(i + 1)
+            ts, e = loaded.pop(i)
+            main.wait_event(e)
+            th, se = threshold_arrays(ts, doy, ndoy, pctile, windowHalfWidth, smoothPercentile,
+                                      smoothPercentileWidth, feb29)
+            ev = detect_arrays(ts, doy, ndoy, th, se, minDuration, joinGaps, maxGap)
+            done = torch.cuda.Event()
+            done.record(main)
+            free_ev[i % 2] = done
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                for src, dst in ((th, th_h), (se, se_h)):
+                    check(lib.xmhw_copy2d_async(dst.data_ptr() + a * 8, ngrid * 8, _ptr(src), (b - a) * 8,
+                                                (b - a) * 8, ndoy, 1, s_out.cuda_stream), "xmhw_copy2d_async")
+                nv_h[a:b].copy_(ev.nvalid, non_blocking=True)
+            ev_parts.append((a, ev))
+            keep_alive.append((th, se))
+        nev = sum(e.n for _, e in ev_parts)
+        ei_h = host_buf("ev_i32", (EI_COUNT, nev), torch.int32)
+        ef_h = host_buf("ev_f64", (EF_COUNT, nev), torch.float64)
+        with torch.cuda.stream(s_out):
+            pos = 0
+            for a, e in ev_parts:
+                if e.n:
+                    e.i32[0, :e.n] += a                     # global cell ids
+                    for k in range(EI_COUNT):
+                        ei_h[k, pos:pos + e.n].copy_(e.i32[k, :e.n], non_blocking=True)
+                    for k in range(EF_COUNT):
+                        ef_h[k, pos:pos + e.n].copy_(e.f64[k, :e.n], non_blocking=True)
+                pos += e.n
+        s_out.synchronize()
+        main.synchronize()
+    return {"thresh": th_h, "seas": se_h, "nvalid": nv_h, "ev_i32": ei_h[:, :nev], "ev_f64": ef_h[:, :nev],
+            "n_events": nev, "h2d_bytes": T * ngrid * 4,
+            "d2h_bytes": 2 * ndoy * ngrid * 8 + ngrid * 4 + nev * (EI_COUNT * 4 + EF_COUNT * 8)}

@@ -486,6 +486,17 @@ int xmhw_event_stats_f32(const float* ts, int64_t T, int64_t ngrid, const int32_
   return cuda_status();
 }
 
+int xmhw_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width_bytes,
+                      int64_t height, int32_t kind, void* stream) {
+  if (!dst || !src || width_bytes <= 0 || height <= 0 || dst_pitch < width_bytes || src_pitch < width_bytes)
+    return XMHW_E_ARG;
+  const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost
+                                                                           : cudaMemcpyDeviceToDevice;
+  cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width_bytes,
+                                    (size_t)height, k, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 int xmhw_synth_sst_f32(float* ts, int64_t T, int64_t ngrid, int64_t cell0, const uint8_t* land,
                        const double* season, uint64_t seed, double rho, double sigma, double noise_scale,
                        uint32_t nan_per_million, void* stream) {
