@@ -186,25 +186,26 @@ __global__ void __launch_bounds__(EXC_WARPS * 32) exceed_kernel(
   uint32_t* mrow = mask + cg * T;
   const int d0 = (int)((int64_t)ndoy * chunk / nchunk), d1 = (int)((int64_t)ndoy * (chunk + 1) / nchunk);
   int cnt = 0;
+  const uint32_t ng32 = (uint32_t)ngrid;          // row offset t * ngrid as one 32x32->64 multiply
   for (int d = d0; d < d1; ++d) {
     const double th = ok ? thresh[(int64_t)d * ngrid + cell] : qnan();
-    const float thr = __double2float_rd(th);
+    // NaN threshold or out-of-grid lane -> +inf: nothing exceeds; ts > th (f64) == ts > rd_f32(th)
+    const float thr = (th == th) ? __double2float_rd(th) : __int_as_float(0x7f800000);
     const int j1 = doy_ptr[d + 1];
     for (int j = doy_ptr[d]; j < j1; j += EXC_BATCH) {
       float v[EXC_BATCH];
-      int t[EXC_BATCH];
+      uint32_t t[EXC_BATCH];
 #pragma unroll
       for (int i = 0; i < EXC_BATCH; ++i) {
-        t[i] = j + i < j1 ? doy_tidx[j + i] : -1;
-        v[i] = (t[i] >= 0 && ok) ? __ldg(col + (int64_t)t[i] * ngrid) : __uint_as_float(0x7fc00000u);
+        t[i] = (uint32_t)__ldg(doy_tidx + min(j + i, j1 - 1));        // tail rows repeat the last one
+        v[i] = __ldg(col + (uint64_t)t[i] * ng32);
       }
 #pragma unroll
       for (int i = 0; i < EXC_BATCH; ++i) {
-        if (t[i] >= 0) {
-          cnt += v[i] == v[i];
-          uint32_t bits = __ballot_sync(0xffffffffu, v[i] > thr);
-          if (lane == 0) mrow[t[i]] = bits;
-        }
+        const bool act = j + i < j1;                                  // warp-uniform
+        cnt += act && v[i] == v[i];
+        const uint32_t bits = __ballot_sync(0xffffffffu, v[i] > thr);
+        if (lane == 0 && act) mrow[t[i]] = bits;
       }
     }
   }
@@ -447,7 +448,8 @@ int xmhw_clim_finish2_f64(const double* thresh_raw, double* thresh_out, const do
 int xmhw_exceed_mask_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy_ptr,
                          const int32_t* doy_tidx, int32_t ndoy, const double* thresh, uint32_t* mask,
                          int32_t* nvalid, void* stream) {
-  if (!ts || !doy_ptr || !doy_tidx || !thresh || !mask || !nvalid || T <= 0 || ngrid <= 0 || ndoy <= 0)
+  if (!ts || !doy_ptr || !doy_tidx || !thresh || !mask || !nvalid || T <= 0 || ngrid <= 0 || ndoy <= 0 ||
+      ngrid > 0xffffffffll || T > 0x7fffffffll)
     return XMHW_E_ARG;
   const int64_t ncg = (ngrid + 31) / 32;
   // enough warps to fill the machine: 148 SMs x 64 warps; split the doy axis on small grids
