@@ -146,16 +146,29 @@ __global__ void __launch_bounds__(128) clim_finish_reg_kernel(const double* __re
 #pragma unroll
   for (int i = 0; i < W - 1; ++i)
     ring[i] = finish_value(raw, ngrid, cell, ndoy, feb29, (((i - h) % ndoy) + ndoy) % ndoy);
+  // Two consecutive outputs per inner step: their left-to-right sums are independent
+  // dependency chains (each ~W x FP64-add latency), interleaving them doubles the ILP.
   for (int d0 = 0; d0 < ndoy; d0 += W) {
 #pragma unroll
-    for (int r = 0; r < W; ++r) {
+    for (int r = 0; r < W; r += 2) {
       const int d = d0 + r;
       if (d < ndoy) {
+        const bool two = r + 1 < W && d + 1 < ndoy;
         ring[(r + W - 1) % W] = finish_value(raw, ngrid, cell, ndoy, feb29, (d + h) % ndoy);
-        double acc = 0.0;
+        double nxt = 0.0;                       // value entering the window of d + 1 (slot r)
+        if (two) nxt = finish_value(raw, ngrid, cell, ndoy, feb29, (d + 1 + h) % ndoy);
+        double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < W; ++k) acc = acc + ring[(r + k) % W];
-        out[(int64_t)d * ngrid + cell] = acc / (double)W;
+        for (int k = 0; k < W; ++k) {
+          acc0 = acc0 + ring[(r + k) % W];
+          if (k >= 1) acc1 = acc1 + ring[(r + k) % W];
+        }
+        acc1 = acc1 + nxt;
+        out[(int64_t)d * ngrid + cell] = acc0 / (double)W;
+        if (two) {
+          out[(int64_t)(d + 1) * ngrid + cell] = acc1 / (double)W;
+          ring[r % W] = nxt;
+        }
       }
     }
   }
@@ -210,6 +223,70 @@ __global__ void __launch_bounds__(EXC_WARPS * 32) exceed_kernel(
     }
   }
   if (ok && cnt) atomicAdd(nvalid + cell, cnt);
+}
+
+// Wide variant (grid a multiple of 4 cells, 16-byte aligned rows): one lane = 4 adjacent cells
+// (float4), one warp = 128 cells = 512 contiguous bytes per row -- 4x fewer DRAM row
+// activations and load instructions per byte than the 128-byte variant.  The 4 exceedance
+// bits of a lane are merged over 8-lane groups into the 4 mask words of the 4 cell groups.
+__global__ void __launch_bounds__(EXC_WARPS * 32) exceed4_kernel(
+    const float* __restrict__ ts, int64_t T, int64_t ngrid, const int32_t* __restrict__ doy_ptr,
+    const int32_t* __restrict__ doy_tidx, int ndoy, int nchunk, const double* __restrict__ thresh,
+    uint32_t* __restrict__ mask, int32_t* __restrict__ nvalid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * EXC_WARPS + (threadIdx.x >> 5);
+  const int64_t nsg = (ngrid + 127) / 128;                  // super-groups of 128 cells
+  const int64_t sg = w / nchunk;
+  const int chunk = (int)(w % nchunk);
+  if (sg >= nsg) return;
+  const int64_t cell = sg * 128 + 4 * lane;                 // first of this lane's 4 cells
+  const bool ok = cell < ngrid;                             // ngrid % 4 == 0: all 4 or none
+  const float* col = ts + (ok ? cell : 0);
+  const int64_t cg = sg * 4 + (lane >> 3);                  // 32-cell group of this lane's cells
+  uint32_t* mrow = mask + cg * T;
+  const bool writer = (lane & 7) == 0 && cg < (ngrid + 31) / 32;
+  const int sh = 4 * (lane & 7);
+  const int d0 = (int)((int64_t)ndoy * chunk / nchunk), d1 = (int)((int64_t)ndoy * (chunk + 1) / nchunk);
+  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  const uint32_t ng32 = (uint32_t)ngrid;
+  const float inf = __int_as_float(0x7f800000);
+  for (int d = d0; d < d1; ++d) {
+    float thr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double th = ok ? thresh[(int64_t)d * ngrid + cell + k] : qnan();
+      thr[k] = (th == th) ? __double2float_rd(th) : inf;
+    }
+    const int j1 = doy_ptr[d + 1];
+    for (int j = doy_ptr[d]; j < j1; j += EXC_BATCH) {
+      float4 v[EXC_BATCH];
+      uint32_t t[EXC_BATCH];
+#pragma unroll
+      for (int i = 0; i < EXC_BATCH; ++i) {
+        t[i] = (uint32_t)__ldg(doy_tidx + min(j + i, j1 - 1));
+        v[i] = __ldg(reinterpret_cast<const float4*>(col + (uint64_t)t[i] * ng32));
+      }
+#pragma unroll
+      for (int i = 0; i < EXC_BATCH; ++i) {
+        const bool act = j + i < j1;
+        c0 += act && v[i].x == v[i].x; c1 += act && v[i].y == v[i].y;
+        c2 += act && v[i].z == v[i].z; c3 += act && v[i].w == v[i].w;
+        uint32_t x = ((uint32_t)(v[i].x > thr[0]) | ((uint32_t)(v[i].y > thr[1]) << 1) |
+                      ((uint32_t)(v[i].z > thr[2]) << 2) | ((uint32_t)(v[i].w > thr[3]) << 3)) << sh;
+        if (!ok) x = 0u;
+        x |= __shfl_xor_sync(0xffffffffu, x, 1);
+        x |= __shfl_xor_sync(0xffffffffu, x, 2);
+        x |= __shfl_xor_sync(0xffffffffu, x, 4);
+        if (writer && act) mrow[t[i]] = x;
+      }
+    }
+  }
+  if (ok) {
+    if (c0) atomicAdd(nvalid + cell, c0);
+    if (c1) atomicAdd(nvalid + cell + 1, c1);
+    if (c2) atomicAdd(nvalid + cell + 2, c2);
+    if (c3) atomicAdd(nvalid + cell + 3, c3);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -456,6 +533,15 @@ int xmhw_exceed_mask_f32(const float* ts, int64_t T, int64_t ngrid, const int32_
   int nchunk = (int)((148 * 64 * 2 + ncg - 1) / ncg);
   if (nchunk < 1) nchunk = 1;
   if (nchunk > ndoy) nchunk = ndoy;
+  if (ngrid % 4 == 0 && ((uintptr_t)ts & 15) == 0) {
+    const int64_t nsg = (ngrid + 127) / 128;
+    int nc4 = (int)((148 * 64 * 2 + nsg - 1) / nsg);
+    nc4 = nc4 < 1 ? 1 : (nc4 > ndoy ? ndoy : nc4);
+    const int64_t nw4 = nsg * nc4;
+    exceed4_kernel<<<(unsigned)((nw4 + EXC_WARPS - 1) / EXC_WARPS), EXC_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        ts, T, ngrid, doy_ptr, doy_tidx, ndoy, nc4, thresh, mask, nvalid);
+    return cuda_status();
+  }
   const int64_t nwarp = ncg * nchunk;
   exceed_kernel<<<(unsigned)((nwarp + EXC_WARPS - 1) / EXC_WARPS), EXC_WARPS * 32, 0, (cudaStream_t)stream>>>(
       ts, T, ngrid, doy_ptr, doy_tidx, ndoy, nchunk, thresh, mask, nvalid);
