@@ -281,7 +281,7 @@ def threshold_detect_host(ts_host, doy, ndoy, pctile=90, windowHalfWidth=5, smoo
     w = -(-ngrid // max(1, int(slabs)))
     w = -(-w // 32) * 32
     ranges = [(a, min(ngrid, a + w)) for a in range(0, ngrid, w)]
-    ev_parts = []
+    ev_parts, ev_parts_all = [], []
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream()
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
@@ -303,6 +303,20 @@ def threshold_detect_host(ts_host, doy, ndoy, pctile=90, windowHalfWidth=5, smoo
 
         start_load(0)
         keep_alive = []
+        # event tables stream to the host per block when the caller preallocated them (their
+        # final size is only known at the end); otherwise they are copied after the last block
+        stream_ev = "ev_i32" in out and "ev_f64" in out
+        pos = 0
+
+        def copy_events(a, e, pos):
+            if e.n:
+                for k in range(EI_COUNT):                   # row by row: contiguous DMAs
+                    ei_h[k, pos:pos + e.n].copy_(e.i32[k, :e.n], non_blocking=True)
+                for k in range(EF_COUNT):
+                    ef_h[k, pos:pos + e.n].copy_(e.f64[k, :e.n], non_blocking=True)
+
+        if stream_ev:
+            ei_h, ef_h = out["ev_i32"], out["ev_f64"]
         for i, (a, b) in enumerate(ranges):
             if i + 1 < len(ranges):
                 start_load(i + 1)
@@ -311,30 +325,36 @@ def threshold_detect_host(ts_host, doy, ndoy, pctile=90, windowHalfWidth=5, smoo
             th, se = threshold_arrays(ts, doy, ndoy, pctile, windowHalfWidth, smoothPercentile,
                                       smoothPercentileWidth, feb29)
             ev = detect_arrays(ts, doy, ndoy, th, se, minDuration, joinGaps, maxGap)
+            if ev.n:
+                ev.i32[0, :ev.n] += a                        # block-local -> global cell ids
             done = torch.cuda.Event()
             done.record(main)
             free_ev[i % 2] = done
+            if stream_ev and pos + ev.n > ei_h.shape[1]:
+                stream_ev = False                            # preallocated table too small: defer
+                ev_parts = ev_parts_all[:]
             with torch.cuda.stream(s_out):
                 s_out.wait_event(done)
                 for src, dst in ((th, th_h), (se, se_h)):
                     check(lib.xmhw_copy2d_async(dst.data_ptr() + a * 8, ngrid * 8, _ptr(src), (b - a) * 8,
                                                 (b - a) * 8, ndoy, 1, s_out.cuda_stream), "xmhw_copy2d_async")
                 nv_h[a:b].copy_(ev.nvalid, non_blocking=True)
-            ev_parts.append((a, ev))
+                if stream_ev:
+                    copy_events(a, ev, pos)
+            ev_parts_all.append((a, ev))
+            if not stream_ev:
+                ev_parts.append((a, ev))
+            pos += ev.n
             keep_alive.append((th, se))
-        nev = sum(e.n for _, e in ev_parts)
-        ei_h = host_buf("ev_i32", (EI_COUNT, nev), torch.int32)
-        ef_h = host_buf("ev_f64", (EF_COUNT, nev), torch.float64)
-        with torch.cuda.stream(s_out):
-            pos = 0
-            for a, e in ev_parts:
-                if e.n:
-                    e.i32[0, :e.n] += a                     # global cell ids
-                    for k in range(EI_COUNT):
-                        ei_h[k, pos:pos + e.n].copy_(e.i32[k, :e.n], non_blocking=True)
-                    for k in range(EF_COUNT):
-                        ef_h[k, pos:pos + e.n].copy_(e.f64[k, :e.n], non_blocking=True)
-                pos += e.n
+        nev = pos
+        if not stream_ev:
+            ei_h = host_buf("ev_i32", (EI_COUNT, nev), torch.int32)
+            ef_h = host_buf("ev_f64", (EF_COUNT, nev), torch.float64)
+            with torch.cuda.stream(s_out):
+                p2 = 0
+                for a, e in ev_parts:
+                    copy_events(a, e, p2)
+                    p2 += e.n
         s_out.synchronize()
         main.synchronize()
     return {"thresh": th_h, "seas": se_h, "nvalid": nv_h, "ev_i32": ei_h[:, :nev], "ev_f64": ef_h[:, :nev],
