@@ -477,6 +477,7 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
                         double* thresh_raw, double* seas_raw, uint32_t* scratch, void* stream) {
   if (!ts || !plan || !thresh_raw || !seas_raw || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
   if (plan->scratch_rows < 0 || (plan->scratch_rows > 0 && !scratch)) return XMHW_E_ARG;
+  if (ngrid > 0xffffffffll || T > 0x7fffffffll) return XMHW_E_ARG;
   if (plan->nsteps <= 0 || plan->pool_rows <= 0 || plan->max_size > 32 || plan->nmax <= 0) return XMHW_E_PLAN;
   const size_t smem = (size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 128;
   if (smem * SWEEP_WARPS > 227 * 1024) return XMHW_E_SMEM;

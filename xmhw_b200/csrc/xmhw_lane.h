@@ -225,12 +225,13 @@ struct Sweeper {
     const Vec rv = env.vload(p.rows + XMHW_LDG(p.inst_row_off + id), size, lane);
     // unconditional loads (entries past `size` read row 0 and are masked in consume), so the
     // compiler keeps all of them in flight instead of waiting on each predicated result
+    const uint32_t ng32 = (uint32_t)ngrid;      // row offset as one 32x32->64 multiply (ngrid < 2^32)
     if (size <= 8) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pv[i] = XMHW_LDG(col + (int64_t)env.vget(rv, i) * ngrid);
+      for (int i = 0; i < 8; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(uint32_t)env.vget(rv, i) * ng32);
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) pv[i] = XMHW_LDG(col + (int64_t)env.vget(rv, i) * ngrid);
+      for (int i = 0; i < 32; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(uint32_t)env.vget(rv, i) * ng32);
     }
   }
 
@@ -260,17 +261,22 @@ struct Sweeper {
     double sum = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      k[i] = (i < size && ok) ? f32_key(pv[i]) : 0u;
-      if (k[i] != 0u) { ++len; sum = sum + (double)pv[i]; }
+      const float v = pv[i];
+      const uint32_t b = f32_bits(v);
+      const bool valid = (i < size) && ok && (v == v);
+      k[i] = valid ? (b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u)) : 0u;
+      if (valid) { ++len; sum = sum + (double)v; }
     }
     ptr = 0;
     uint32_t cinc = 0xffffffffu, cexc = 0u;
     if (env.any(len > 0)) {
       sort_desc<N>(k);
+      uint32_t* const srow = pool + (base + POOL_KEYS) * 32 + lane;
+      uint32_t* const grow = scratch + ((size_t)(sbase + SCR_KEYS) - (size_t)keep) * 32 + lane;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        if (i < keep) at(base + POOL_KEYS + i) = k[i];
-        else if (i < size) scratch[(size_t)(sbase + SCR_KEYS + i - keep) * 32 + lane] = k[i];
+        if (i < keep) srow[i * 32] = k[i];                  // top `keep` keys: shared memory
+        if (i >= keep && i < size) grow[i * 32] = k[i];     // sorted remainder: global scratch
         const bool ab = k[i] > pivot;
         ptr += ab;
         if (ab) cinc = k[i]; else cexc = cexc > k[i] ? cexc : k[i];
