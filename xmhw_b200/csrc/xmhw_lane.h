@@ -326,6 +326,35 @@ struct Sweeper {
     prefetch(0);
   }
 
+  // One pass over the lists in use: the two smallest keys above the cut (i1 <= i2, lists
+  // bi1 != bi2) and / or the two largest keys below it (e1 >= e2, lists be1 != be2).
+  template <bool INC, bool EXC>
+  XMHW_HD void scan(const uint32_t* ub, int m4, uint32_t& i1, uint32_t& i2, int& bi1, int& bi2,
+                    uint32_t& e1, uint32_t& e2, int& be1, int& be2) {
+    if (INC) { i1 = 0xffffffffu; i2 = 0xffffffffu; bi1 = 0; bi2 = 0; }
+    if (EXC) { e1 = 0u; e2 = 0u; be1 = 0; be2 = 0; }
+#pragma unroll 4
+    for (int j = 0; j < m4; ++j) {
+      const int x = (int)ub[j];
+      if (INC) {
+        const uint32_t ki = at(x + POOL_CINC);
+        if (ki < i2) {
+          const bool first = ki < i1;
+          i2 = first ? i1 : ki; bi2 = first ? bi1 : x;
+          if (first) { i1 = ki; bi1 = x; }
+        }
+      }
+      if (EXC) {
+        const uint32_t ke = at(x + POOL_CEXC);
+        if (ke > e2) {
+          const bool first = ke > e1;
+          e2 = first ? e1 : ke; be2 = first ? be1 : x;
+          if (first) { e1 = ke; be1 = x; }
+        }
+      }
+    }
+  }
+
   XMHW_HD void step(int s, double& thresh, double& seas) {
     const Vec rec = rec_next;
     const Vec usev = use_next;
@@ -383,30 +412,19 @@ struct Sweeper {
     // (the second-best candidate is either the other list's or the same list's next key),
     // lanes on target do nothing; the scan of the last iteration (no lane off target)
     // delivers a = i1 and the runner-up for b.
-    uint32_t i1, i2, e1, e2;
-    int bi1, bi2, be1, be2;
+    uint32_t i1 = 0xffffffffu, i2 = 0xffffffffu, e1 = 0u, e2 = 0u;
+    int bi1 = 0, bi2 = 0, be1 = 0, be2 = 0;
+    int d = live ? C - target : 0;
     while (true) {
-      i1 = 0xffffffffu; i2 = 0xffffffffu; e1 = 0u; e2 = 0u;
-      bi1 = 0; bi2 = 0; be1 = 0; be2 = 0;
-#pragma unroll 4
-      for (int j = 0; j < m4; ++j) {
-        const int x = (int)ub[j];
-        const uint32_t ki = at(x + POOL_CINC), ke = at(x + POOL_CEXC);
-        if (ki < i2) {
-          const bool first = ki < i1;
-          i2 = first ? i1 : ki; bi2 = first ? bi1 : x;
-          if (first) { i1 = ki; bi1 = x; }
-        }
-        if (ke > e2) {
-          const bool first = ke > e1;
-          e2 = first ? e1 : ke; be2 = first ? be1 : x;
-          if (first) { e1 = ke; be1 = x; }
-        }
-      }
-      const int d = live ? C - target : 0;
-      if (!env.any(d != 0)) break;
+      // only the directions some lane still needs are scanned; the last scan (no lane off
+      // target) is a "drop"-side scan because a and b are the two smallest keys above the cut
+      const bool any_dn = env.any(d > 0), any_up = env.any(d < 0);
+      if (any_up && any_dn) scan<true, true>(ub, m4, i1, i2, bi1, bi2, e1, e2, be1, be2);
+      else if (any_up) scan<false, true>(ub, m4, i1, i2, bi1, bi2, e1, e2, be1, be2);
+      else scan<true, false>(ub, m4, i1, i2, bi1, bi2, e1, e2, be1, be2);
+      if (!any_up && !any_dn) break;
       // ---- drop the smallest keys above the cut (d > 0)
-      if (env.any(d > 0)) {
+      if (any_dn) {
         const bool mv = d > 0;
         const uint32_t meta = at(bi1 + POOL_META);
         const int pa = meta_ptr(meta);                          // >= 1 when mv
@@ -440,7 +458,7 @@ struct Sweeper {
         }
       }
       // ---- add the largest keys below the cut (d < 0)
-      if (env.any(d < 0)) {
+      if (any_up) {
         const bool mv = d < 0;
         const uint32_t meta = at(be1 + POOL_META);
         const int pa = meta_ptr(meta), la = meta_len(meta);     // pa < la when mv
@@ -472,6 +490,7 @@ struct Sweeper {
           }
         }
       }
+      d = live ? C - target : 0;
     }
     // f64 sum of the window; a = i1 (smallest key above the cut), b = next one up
     double sum = 0.0;
