@@ -21,16 +21,14 @@ struct HostEnv {
   }
 };
 
-extern "C" {
-
-int emul_clim_sweep(const float* ts, int64_t T, int64_t ngrid, const ClimPlan* plan, double* thr, double* seas) {
-  (void)T;
+template <int MAXN>
+static void sweep_cells(const float* ts, int64_t ngrid, const ClimPlan* plan, double* thr, double* seas) {
   std::vector<uint32_t> pool((size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 32);
   std::vector<uint32_t> scratch((size_t)(plan->scratch_rows + 1) * 32);
   HostEnv env;
   for (int64_t cell = 0; cell < ngrid; ++cell) {
     const int lane = (int)(cell & 31);
-    Sweeper<HostEnv> sw(env, *plan, pool.data(), scratch.data(), lane, ts + cell, ngrid, true);
+    Sweeper<HostEnv, MAXN> sw(env, *plan, pool.data(), scratch.data(), lane, ts + cell, ngrid, true);
     sw.init();
     for (int s = 0; s < plan->nsteps; ++s) {
       double a, b;
@@ -39,6 +37,14 @@ int emul_clim_sweep(const float* ts, int64_t T, int64_t ngrid, const ClimPlan* p
       seas[(int64_t)s * ngrid + cell] = b;
     }
   }
+}
+
+extern "C" {
+
+int emul_clim_sweep(const float* ts, int64_t T, int64_t ngrid, const ClimPlan* plan, double* thr, double* seas) {
+  (void)T;
+  if (plan->max_size <= 32) sweep_cells<32>(ts, ngrid, plan, thr, seas);
+  else sweep_cells<48>(ts, ngrid, plan, thr, seas);
   return 0;
 }
 

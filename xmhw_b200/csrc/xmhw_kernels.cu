@@ -47,37 +47,27 @@ static_assert((int)XMHW_EI_COUNT == (int)EI_COUNT && (int)XMHW_EF_COUNT == (int)
 // Shared memory per warp: plan.pool_rows rows of 32 words (sorted lists of the
 // current +-w window, their f64 sums and per-lane cut pointers).
 // ---------------------------------------------------------------------------
-#ifndef XMHW_SWEEP_WARPS
-#define XMHW_SWEEP_WARPS 1
-#endif
-constexpr int SWEEP_WARPS = XMHW_SWEEP_WARPS;
-
-__global__ void __launch_bounds__(32 * SWEEP_WARPS, 20 / SWEEP_WARPS) clim_sweep_kernel(
+// MAXN = keys per sorted list: 32 (series of <= 32 years: one list per calendar day, ~96
+// registers, 20 warps/SM) or 48 (longer series; larger register sorting networks, fewer warps).
+template <int MAXN>
+__global__ void __launch_bounds__(32, MAXN == 32 ? 20 : 10) clim_sweep_kernel(
     ClimPlan p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr, double* __restrict__ seas,
     uint32_t* __restrict__ scratch) {
-  extern __shared__ uint32_t smem_pool[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t cg = (int64_t)blockIdx.x * SWEEP_WARPS + warp;
-  const int64_t ncg = (ngrid + 31) / 32;
-  const bool wok = cg < ncg;
-  const int64_t cell = (wok ? cg : ncg - 1) * 32 + lane;
-  const bool ok = wok && cell < ngrid;
+  extern __shared__ uint32_t pool[];
+  const int lane = threadIdx.x;
+  const int64_t cell = (int64_t)blockIdx.x * 32 + lane;
+  const bool ok = cell < ngrid;
   const float* col = ts + (ok ? cell : 0);
-  uint32_t* pool = smem_pool + (size_t)warp * (p.pool_rows + POOL_STAGE_ROWS) * 32;
   WarpEnv env;
-  Sweeper<WarpEnv> sw(env, p, pool, scratch + (size_t)(wok ? cg : ncg - 1) * p.scratch_rows * 32, lane, col, ngrid, ok);
-  if (SWEEP_WARPS == 1 || wok) sw.init();
+  Sweeper<WarpEnv, MAXN> sw(env, p, pool, scratch + (size_t)blockIdx.x * p.scratch_rows * 32, lane, col, ngrid, ok);
+  sw.init();
   for (int s = 0; s < p.nsteps; ++s) {
     double a, b;
-    if (SWEEP_WARPS == 1 || wok) {
-      sw.step(s, a, b);
-      if (ok) {
-        thr[(int64_t)s * ngrid + cell] = a;
-        seas[(int64_t)s * ngrid + cell] = b;
-      }
+    sw.step(s, a, b);
+    if (ok) {
+      thr[(int64_t)s * ngrid + cell] = a;
+      seas[(int64_t)s * ngrid + cell] = b;
     }
-    // multi-warp blocks step together so that the warps of an SM share instruction-cache lines
-    if (SWEEP_WARPS > 1) __syncthreads();
   }
 }
 
@@ -478,17 +468,22 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
   if (!ts || !plan || !thresh_raw || !seas_raw || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
   if (plan->scratch_rows < 0 || (plan->scratch_rows > 0 && !scratch)) return XMHW_E_ARG;
   if (ngrid > 0xffffffffll || T > 0x7fffffffll) return XMHW_E_ARG;
-  if (plan->nsteps <= 0 || plan->pool_rows <= 0 || plan->max_size > 32 || plan->nmax <= 0) return XMHW_E_PLAN;
+  if (plan->nsteps <= 0 || plan->pool_rows <= 0 || plan->max_size > 48 || plan->nmax <= 0) return XMHW_E_PLAN;
   const size_t smem = (size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 128;
-  if (smem * SWEEP_WARPS > 227 * 1024) return XMHW_E_SMEM;
-  cudaError_t e = cudaFuncSetAttribute(clim_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(smem * SWEEP_WARPS));
-  if (e != cudaSuccess) return (int)e;
+  if (smem > 227 * 1024) return XMHW_E_SMEM;
   ClimPlan p;
   memcpy(&p, plan, sizeof(p));
   const int64_t ncg = (ngrid + 31) / 32;
-  clim_sweep_kernel<<<(unsigned)((ncg + SWEEP_WARPS - 1) / SWEEP_WARPS), 32 * SWEEP_WARPS, smem * SWEEP_WARPS,
-                      (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw, scratch);
+  cudaError_t e;
+  if (plan->max_size <= 32) {
+    e = cudaFuncSetAttribute(clim_sweep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    clim_sweep_kernel<32><<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw, scratch);
+  } else {
+    e = cudaFuncSetAttribute(clim_sweep_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    clim_sweep_kernel<48><<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw, scratch);
+  }
   return cuda_status();
 }
 

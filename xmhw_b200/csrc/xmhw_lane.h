@@ -170,6 +170,8 @@ template <> XMHW_HD void sort_desc<8>(uint32_t* k) { XMHW_SORTNET_8 }
 template <> XMHW_HD void sort_desc<16>(uint32_t* k) { XMHW_SORTNET_16 }
 template <> XMHW_HD void sort_desc<24>(uint32_t* k) { XMHW_SORTNET_24 }
 template <> XMHW_HD void sort_desc<32>(uint32_t* k) { XMHW_SORTNET_32 }
+template <> XMHW_HD void sort_desc<40>(uint32_t* k) { XMHW_SORTNET_40 }
+template <> XMHW_HD void sort_desc<48>(uint32_t* k) { XMHW_SORTNET_48 }
 
 // numpy _lerp (lib/_function_base_impl.py): d = b - a in float32, result in
 // float64 with two roundings, no FMA (the .cu is compiled with --fmad=false).
@@ -193,7 +195,7 @@ XMHW_HD double lerp_q(float a, float b, double g) {
 //
 // Env supplies the warp-level pieces: any(pred) vote and Vec = a small int vector
 // spread over the lanes (vload = one coalesced load, vget = broadcast of one entry).
-template <class Env>
+template <class Env, int MAXN = 32>
 struct Sweeper {
   typedef typename Env::Vec Vec;
   const Env& env;
@@ -206,7 +208,7 @@ struct Sweeper {
   const bool ok;
   int C, n;              // keys above the cut / valid samples, over the lists in use
   uint32_t pivot;        // cut value (key of the smallest sample above the cut)
-  float pv[32];          // prefetched rows of the next instance to load
+  float pv[MAXN];        // prefetched rows of the next instance to load (MAXN = 32 or 48 keys per list)
   int total_enter;
   Vec rec_next, use_next;   // step record / list bases of the next step (prefetched)
 
@@ -222,16 +224,19 @@ struct Sweeper {
     if (j >= total_enter) return;
     const int id = XMHW_LDG(p.enter + j) & 0x3fffffff;
     const int size = XMHW_LDG(p.inst_size + id);
-    const Vec rv = env.vload(p.rows + XMHW_LDG(p.inst_row_off + id), size, lane);
+    const Vec rv = env.vload(p.rows + XMHW_LDG(p.inst_row_off + id), size, lane);   // up to 64 entries
     // unconditional loads (entries past `size` read row 0 and are masked in consume), so the
     // compiler keeps all of them in flight instead of waiting on each predicated result
     const uint32_t ng32 = (uint32_t)ngrid;      // row offset as one 32x32->64 multiply (ngrid < 2^32)
     if (size <= 8) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(uint32_t)env.vget(rv, i) * ng32);
-    } else {
+    } else if (MAXN == 32 || size <= 32) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(uint32_t)env.vget(rv, i) * ng32);
+    } else {
+#pragma unroll
+      for (int i = 0; i < MAXN; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(uint32_t)env.vget(rv, i) * ng32);
     }
   }
 
@@ -256,7 +261,7 @@ struct Sweeper {
   // keys of the prefetched instance -> sorted block in the pool
   template <int N>
   XMHW_HD void consume(int base, int sbase, int size, int keep, int& len, int& ptr) {
-    uint32_t k[32];
+    uint32_t k[N];
     len = 0;
     double sum = 0.0;
 #pragma unroll
@@ -299,7 +304,9 @@ struct Sweeper {
     int len, ptr;
     if (e >> 30) {
       if (size <= 8) consume<8>(base, sbase, size, keep, len, ptr);
-      else consume<32>(base, sbase, size, keep, len, ptr);
+      else if (MAXN == 32 || size <= 32) consume<32>(base, sbase, size, keep, len, ptr);
+      else if (size <= 40) consume<(MAXN > 32 ? 40 : 32)>(base, sbase, size, keep, len, ptr);
+      else consume<(MAXN > 32 ? 48 : 32)>(base, sbase, size, keep, len, ptr);
       prefetch(entry_index + 1);
     } else {          // list re-enters after a hole (Feb 29): pointer against the current cut
       uint32_t meta = at(base + POOL_META);

@@ -27,7 +27,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-MAX_LIST = 32          # rows per instance = keys per register sorting network
+MAX_LIST = 32          # rows per instance = keys per register sorting network (short series)
+MAX_LIST_LONG = 48     # ... when a calendar day has more than 32 samples (series > 32 years)
 META_ROWS = 3          # meta word, cinc, cexc per instance and lane
 NULL_ROWS = 3          # block 0 of the pool is the kernel's null list
 SCRATCH_HEAD = 2       # scratch rows per instance before its tail keys: f64 sum (lo, hi)
@@ -125,7 +126,9 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
                 "windows wider than one year are not supported")
         classes.setdefault(sig, []).append(tp)
 
-    # instances: (rows, sorted step list) split into visits and into <= MAX_LIST pieces
+    # instances: (rows, sorted step list) split into visits and into <= max_list pieces; one
+    # 48-key list per calendar day (wider register sorting network) beats two 32-key lists
+    max_list = MAX_LIST if max(len(r) for r in classes.values()) <= MAX_LIST else MAX_LIST_LONG
     insts = []   # dict(rows=array, steps=list)
     for sig, rws in classes.items():
         steps = [d - 1 for d in sig]
@@ -136,7 +139,7 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
             else:
                 visits.append([s])
         rws = np.asarray(rws, np.int32)
-        npieces = -(-len(rws) // MAX_LIST)
+        npieces = -(-len(rws) // max_list)
         pieces = np.array_split(rws, npieces)
         for v in visits:
             for pc in pieces:
