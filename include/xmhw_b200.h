@@ -138,6 +138,10 @@ int xmhw_event_stats_f32(const float* ts, int64_t T, int64_t ngrid, const int32_
                          const double* thresh, const double* seas, int64_t nev, int64_t cap,
                          int32_t* ev_i32, double* ev_f64, void* stream);
 
+/* Pre-step of both public functions (xmhw.py:159-160, :409-410, maxPadLength): in-place linear
+ * interpolation along time of interior NaN runs of at most max_pad steps, per cell.        */
+int xmhw_interp_gaps_f32(float* ts, int64_t T, int64_t ngrid, int32_t max_pad, void* stream);
+
 /* Strided 2-D copy (cudaMemcpy2DAsync) used to move a column block of the (time, cell) host
  * array to / from the device: kind 0 = host->device, 1 = device->host, 2 = device->device. */
 int xmhw_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,

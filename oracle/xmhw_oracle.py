@@ -63,6 +63,27 @@ def land_mask(ts, anynans=False):
     return ~nan.any(axis=0) if anynans else ~nan.all(axis=0)
 
 
+def interp_gaps(ts, max_pad):
+    """xmhw.py:159-160, :409-410 `interpolate_na(dim=tdim, max_gap=maxPadLength)`: linear
+    interpolation along time (axis 0) of interior NaN runs of at most max_pad steps
+    (Oliver's `pad` semantics: run length in samples; np.interp arithmetic in float64)."""
+    out = np.array(ts, np.float32, copy=True)
+    T = out.shape[0]
+    flat = out.reshape(T, -1)
+    idx = np.arange(T)
+    for c in range(flat.shape[1]):
+        col = flat[:, c]
+        nan = np.isnan(col)
+        if not nan.any() or nan.all():
+            continue
+        filled = np.interp(idx, idx[~nan], col[~nan]).astype(np.float32)
+        edges = np.diff(np.concatenate(([0], nan.view(np.int8), [0])))
+        for s, e in zip(np.nonzero(edges == 1)[0], np.nonzero(edges == -1)[0]):
+            if s > 0 and e < T and (e - s) <= max_pad:
+                col[s:e] = filled[s:e]
+    return out
+
+
 # ---------------------------------------------------------------------------
 # climatology
 # ---------------------------------------------------------------------------

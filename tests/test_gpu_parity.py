@@ -256,3 +256,18 @@ def test_host_buffer_entry_point(core):
     assert res["n_events"] == ev.n
     assert np.array_equal(res["ev_i32"].numpy(), ev.i32[:, :ev.n].cpu().numpy())
     assert np.array_equal(res["ev_f64"].numpy(), ev.f64[:, :ev.n].cpu().numpy(), equal_nan=True)
+
+
+def test_interp_gaps_pre_step(core):
+    """maxPadLength pre-step (xmhw.py:159-160, :409-410): bit-equal to the np.interp oracle."""
+    from xmhw_b200 import synth
+    O = _oracle()
+    ts_h = synth.synth_sst(500, 70, synth.season_table(500), nan_ppm=60000)
+    ts_h[:3, 4] = np.nan           # leading gap: never filled
+    ts_h[-2:, 5] = np.nan          # trailing gap: never filled
+    ts_h[100:140, 6] = np.nan      # long gap: left as NaN
+    ts_h[:, 7] = np.nan
+    for max_pad in (1, 3, 10):
+        got = core.interp_gaps_(torch.from_numpy(ts_h.copy()).cuda(), max_pad).cpu().numpy()
+        exp = O.interp_gaps(ts_h, max_pad)
+        assert np.array_equal(got.view(np.int32), exp.view(np.int32)), max_pad

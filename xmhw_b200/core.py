@@ -162,6 +162,16 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
     return (out_t, out_s, raw_t, raw_s) if return_raw else (out_t, out_s)
 
 
+def interp_gaps_(ts, max_pad):
+    """In-place pre-step `maxPadLength` (xmhw.py:159-160, :409-410): NaN runs of at most
+    `max_pad` steps between two valid samples are filled by linear interpolation along time."""
+    _require_cuda(ts, "ts", torch.float32)
+    T, ngrid = ts.shape
+    with torch.cuda.device(ts.device):
+        _call("xmhw_interp_gaps_f32", _ptr(ts), T, ngrid, int(max_pad), _stream())
+    return ts
+
+
 class EventTable:
     """Compact event table on the device (struct of arrays).
 

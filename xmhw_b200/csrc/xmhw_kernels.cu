@@ -442,6 +442,32 @@ __global__ void synth_kernel(float* __restrict__ ts, int64_t T, int64_t ngrid, i
   }
 }
 
+// ---------------------------------------------------------------------------
+// pre-step: linear interpolation along time of NaN runs no longer than max_pad
+// (xmhw.py:159-160, :409-410 `interpolate_na(dim=tdim, max_gap=maxPadLength)`), in place.
+// One thread = one cell (coalesced rows); np.interp arithmetic: slope * (x - x0) + y0 in f64.
+// ---------------------------------------------------------------------------
+__global__ void interp_gaps_kernel(float* __restrict__ ts, int64_t T, int64_t ngrid, int max_pad) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ngrid) return;
+  float* col = ts + cell;
+  int64_t last_t = -1;
+  float last_v = 0.0f;
+  for (int64_t t = 0; t < T; ++t) {
+    const float v = col[t * ngrid];
+    if (v == v) {
+      const int64_t gap = t - last_t - 1;
+      if (last_t >= 0 && gap >= 1 && gap <= max_pad) {
+        const double slope = ((double)v - (double)last_v) / (double)(gap + 1);
+        for (int64_t k = 1; k <= gap; ++k)
+          col[(last_t + k) * ngrid] = (float)(slope * (double)k + (double)last_v);
+      }
+      last_t = t;
+      last_v = v;
+    }
+  }
+}
+
 inline int cuda_status() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
@@ -582,6 +608,14 @@ int xmhw_event_stats_f32(const float* ts, int64_t T, int64_t ngrid, const int32_
   const int nt = 128;
   event_stats_kernel<<<(unsigned)((nev + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
       ts, T, ngrid, doy, thresh, seas, nev, cap, ev_i32, ev_f64);
+  return cuda_status();
+}
+
+int xmhw_interp_gaps_f32(float* ts, int64_t T, int64_t ngrid, int32_t max_pad, void* stream) {
+  if (!ts || T <= 0 || ngrid <= 0 || max_pad < 0) return XMHW_E_ARG;
+  if (max_pad == 0) return 0;
+  const int nt = 128;
+  interp_gaps_kernel<<<(unsigned)((ngrid + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(ts, T, ngrid, max_pad);
   return cuda_status();
 }
 

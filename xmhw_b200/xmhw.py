@@ -56,29 +56,6 @@ def _unpack(temp, tdim):
     return np.ascontiguousarray(data), time, other, coords, dict(getattr(temp, "attrs", {})), enc, tattrs
 
 
-def _interp_gaps(ts, max_pad):
-    """Pre-step `interpolate_na(dim=tdim, max_gap=maxPadLength)` (xmhw.py:159-160, :409-410):
-    linear interpolation along time of NaN runs no longer than max_pad steps (host-side
-    pre-step; not part of the timed hot path)."""
-    T = ts.shape[0]
-    flat = ts.reshape(T, -1)
-    idx = np.arange(T)
-    for c in range(flat.shape[1]):
-        col = flat[:, c]
-        nan = np.isnan(col)
-        if not nan.any() or nan.all():
-            continue
-        good = ~nan
-        filled = np.interp(idx, idx[good], col[good]).astype(np.float32)
-        # only interior gaps of length <= max_pad
-        edges = np.diff(np.concatenate(([0], nan.view(np.int8), [0])))
-        starts, ends = np.nonzero(edges == 1)[0], np.nonzero(edges == -1)[0]
-        for s, e in zip(starts, ends):
-            if s > 0 and e < T and (e - s) <= max_pad:
-                col[s:e] = filled[s:e]
-    return ts
-
-
 def _wrap(ds, like):
     if labeled.is_xarray(like):
         try:
@@ -127,8 +104,6 @@ def threshold(temp, tdim="time", climatologyPeriod=[None, None], pctile=90, wind
     grid_shape = data.shape[1:]
     T = data.shape[0]
     flat = data.reshape(T, -1)
-    if maxPadLength:                                           # xmhw.py:159-160
-        flat = _interp_gaps(flat.copy(), maxPadLength)
     nan = np.isnan(flat)
     ocean = ~nan.any(axis=0) if anynans else ~nan.all(axis=0)  # identify.py:522-525
     if not point and not ocean.any():
@@ -138,6 +113,8 @@ def threshold(temp, tdim="time", climatologyPeriod=[None, None], pctile=90, wind
     ts = torch.from_numpy(np.ascontiguousarray(flat)).cuda()
     if coldSpells:                                             # xmhw.py:153-154
         ts = -ts
+    if maxPadLength:                                           # xmhw.py:159-160
+        core.interp_gaps_(ts, maxPadLength)
     if anynans:                                                # dropped cells produce no output
         ts[:, torch.from_numpy(~ocean).cuda()] = float("nan")
     th, se = core.threshold_arrays(ts, doy, ndoy, pctile, windowHalfWidth, smoothPercentile,
@@ -246,8 +223,6 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
     grid_shape = data.shape[1:]
     T = data.shape[0]
     flat = data.reshape(T, -1)
-    if maxPadLength:                                           # xmhw.py:409-410
-        flat = _interp_gaps(flat.copy(), maxPadLength)
     nan = np.isnan(flat)
     ocean = ~nan.any(axis=0) if anynans else ~nan.all(axis=0)
     if not point and not ocean.any():
@@ -257,6 +232,8 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
     if not torch.cuda.is_available():
         raise RuntimeError("xmhw_b200 needs a CUDA device (there is no CPU path)")
     ts = torch.from_numpy(np.ascontiguousarray(flat)).cuda()
+    if maxPadLength:                                           # xmhw.py:409-410
+        core.interp_gaps_(ts, maxPadLength)
     if coldSpells:                                             # xmhw.py:412-413
         ts = -ts
     if anynans:
