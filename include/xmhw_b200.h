@@ -138,6 +138,19 @@ int xmhw_event_stats_f32(const float* ts, int64_t T, int64_t ngrid, const int32_
                          const double* thresh, const double* seas, int64_t nev, int64_t cap,
                          int32_t* ev_i32, double* ev_f64, void* stream);
 
+/* intermediate=True (identify.py:404-411): dense per-timestep fields of mhw_df
+ * (features.py:22-69), every array [T][ngrid]; `events` must be pre-filled with NaN by the
+ * caller (it receives the event label = start index on event days).  T <= 65535.           */
+typedef struct xmhw_intermediate {
+  double* events; double* seas; double* thresh; double* relSeas; double* relThresh;
+  double* relThreshNorm; double* severity; double* cats; float* mabs;
+  uint8_t* bthresh; uint8_t* duration_moderate; uint8_t* duration_strong;
+  uint8_t* duration_severe; uint8_t* duration_extreme;
+} xmhw_intermediate;
+int xmhw_intermediate_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy,
+                          const double* thresh, const double* seas, const int32_t* ev_i32,
+                          int64_t nev, int64_t cap, const xmhw_intermediate* out, void* stream);
+
 /* Pre-step of both public functions (xmhw.py:159-160, :409-410, maxPadLength): in-place linear
  * interpolation along time of interior NaN runs of at most max_pad steps, per cell.        */
 int xmhw_interp_gaps_f32(float* ts, int64_t T, int64_t ngrid, int32_t max_pad, void* stream);

@@ -368,6 +368,44 @@ def event_stats(ts, thresh_t, seas_t, start, end):
     return out
 
 
+INTER_FIELDS = ("events", "seas", "thresh", "relSeas", "relThresh", "relThreshNorm", "severity", "cats",
+                "mabs", "bthresh", "duration_moderate", "duration_strong", "duration_severe",
+                "duration_extreme")
+
+
+def intermediate(ts, doy, thresh, seas, minDuration=5, joinGaps=True, maxGap=2):
+    """identify.py:404-411 + features.py:22-69 (mhw_df): per-timestep dataset returned with
+    `intermediate=True`, for every column of ts[T, ncell].  Event days carry the event label
+    (start index); seas/thresh/relSeas/... are NaN off events, flags False."""
+    ts = np.asarray(ts, np.float32)
+    if ts.ndim == 1:
+        ts = ts[:, None]
+        thresh = np.asarray(thresh)[:, None] if np.ndim(thresh) == 1 else thresh
+        seas = np.asarray(seas)[:, None] if np.ndim(seas) == 1 else seas
+    doy = np.asarray(doy)
+    T, n = ts.shape
+    th_t = np.asarray(thresh, np.float64)[doy - 1]
+    se_t = np.asarray(seas, np.float64)[doy - 1]
+    x = ts.astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        b = x > th_t                                            # identify.py:372
+        events = np.full((T, n), np.nan)
+        for c in range(n):
+            s, e = find_events(b[:, c], minDuration, joinGaps, maxGap)
+            for si, ei in zip(s, e):
+                events[si:ei + 1, c] = si                       # identify.py:466-470, :534-535
+        m = ~np.isnan(events)                                   # features.py:38
+        relS, relT, ths = x - se_t, x - th_t, th_t - se_t       # :52-54
+        norm, sev = relT / ths, relS / -(ths)                   # :57-61
+        cats = np.floor(1.0 + norm)                             # :62
+    nanw = lambda a: np.where(m, a, np.nan)
+    return {"events": events, "seas": nanw(se_t), "thresh": nanw(th_t), "relSeas": nanw(relS),
+            "relThresh": nanw(relT), "relThreshNorm": nanw(norm), "severity": nanw(sev), "cats": nanw(cats),
+            "mabs": np.where(m, ts, np.float32(np.nan)).astype(np.float32), "bthresh": b,
+            "duration_moderate": m & (cats == 1.0), "duration_strong": m & (cats == 2.0),
+            "duration_severe": m & (cats == 3.0), "duration_extreme": m & (cats >= 4.0)}
+
+
 def detect(ts, doy, thresh, seas, minDuration=5, joinGaps=True, maxGap=2):
     """xmhw.py:440-454 + identify.py:328-412 for every column of ts[T, ncell].
 

@@ -87,3 +87,29 @@ def test_climatology_period_and_anynans(api, oisst):
     got = clim["thresh"].values
     assert got.shape[0] == 365                     # doy 60 has no sample in 2003: dropped like the groupby does
     assert int(np.sum(~np.isnan(got[0]))) == int(keep.sum())
+
+
+def test_intermediate_and_maxpad_api(api, oisst):
+    """detect(..., intermediate=True) returns (mhw, mhw_inter) like xmhw.py:516-518; maxPadLength
+    fills short gaps before detection (xmhw.py:409-410)."""
+    xmhw, labeled = api
+    from oracle import xmhw_oracle as O
+    ts = oisst["sst"][:, 1, 2].copy()
+    da = labeled.DataArray(ts, ("time",), {"time": oisst["time"]})
+    clim = xmhw.threshold(da)
+    mhw, inter = xmhw.detect(da, clim["thresh"], clim["seas"], intermediate=True)
+    doy = O.add_doy(oisst["time"])
+    exp = O.intermediate(ts, doy, clim["thresh"].values, clim["seas"].values)
+    assert inter["events"].dims == ("time",)
+    assert np.array_equal(inter["events"].values, exp["events"][:, 0], equal_nan=True)
+    assert np.allclose(inter["relSeas"].values, exp["relSeas"][:, 0], equal_nan=True)
+    assert np.array_equal(inter["duration_moderate"].values, exp["duration_moderate"][:, 0])
+    sst = oisst["sst"].copy()
+    sst[100:103, 1, 2] = np.nan                        # 3-day gap inside the first-year series
+    dg = labeled.DataArray(sst, ("time", "lat", "lon"), {"time": oisst["time"], "lat": oisst["lat"], "lon": oisst["lon"]})
+    c1 = xmhw.threshold(dg, maxPadLength=5)
+    filled = O.interp_gaps(sst.reshape(len(doy), -1), 5)
+    oth, _ = O.threshold(filled, doy, 366)
+    ocean = ~np.isnan(oisst["sst"]).all(0)
+    assert np.array_equal(c1["thresh"].values.reshape(366, -1),
+                          oth.reshape(366, 8, 4)[:, ocean.any(1)][:, :, ocean.any(0)].reshape(366, -1), equal_nan=True)

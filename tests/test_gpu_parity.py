@@ -271,3 +271,26 @@ def test_interp_gaps_pre_step(core):
         got = core.interp_gaps_(torch.from_numpy(ts_h.copy()).cuda(), max_pad).cpu().numpy()
         exp = O.interp_gaps(ts_h, max_pad)
         assert np.array_equal(got.view(np.int32), exp.view(np.int32)), max_pad
+
+
+def test_intermediate_dataset(core):
+    """intermediate=True per-timestep fields (identify.py:404-411, features.py:22-69) vs oracle."""
+    from xmhw_b200 import synth
+    O = _oracle()
+    time = synth.daily_time(1996, 2003)
+    doy = synth.doy366(time)
+    land = np.zeros(50, np.uint8)
+    land[7] = 1
+    ts_h = synth.synth_sst(len(time), 50, synth.season_table(time), land=land, nan_ppm=4000)
+    ts = torch.from_numpy(ts_h).cuda()
+    th, se = core.threshold_arrays(ts, doy, 366)
+    ev = core.detect_arrays(ts, doy, 366, th, se)
+    got = core.intermediate_arrays(ts, doy, 366, th, se, ev)
+    exp = O.intermediate(ts_h, doy, th.cpu().numpy(), se.cpu().numpy())
+    for k in O.INTER_FIELDS:
+        g = got[k].cpu().numpy()
+        if g.dtype == bool:
+            assert np.array_equal(g, exp[k]), k
+        else:
+            assert np.array_equal(np.isnan(g), np.isnan(exp[k])), k
+            assert np.allclose(g, exp[k], rtol=0, atol=1e-12, equal_nan=True), k

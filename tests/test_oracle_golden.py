@@ -147,3 +147,25 @@ def test_reference_event_tables(ref_cases):
             np.testing.assert_allclose(ev[f], c[f], rtol=tol, atol=tol, equal_nan=True, err_msg=f)
         nev += len(ev["cell"])
     assert nev > 500
+
+
+def test_intermediate_golden():
+    # test_identify.py:158-190 with intermediate=True + fixture inter_data (xmhw_fixtures.py:267-332)
+    ts = np.array([15.6, 17.3, 18.2, 19.5, 19.4, 19.6, 18.1, 17.0, 15.2], np.float32)
+    se = np.array([15.8, 16.0, 16.2, 16.5, 16.6, 16.4, 16.6, 16.7, 16.4])
+    th = np.array([16.0, 16.7, 17.6, 17.9, 18.1, 18.2, 17.3, 17.2, 17.0])
+    r = O.intermediate(ts, np.arange(1, 10), th, se)
+    nan = np.nan
+    exp = {"seas": [nan, 16.0, 16.2, 16.5, 16.6, 16.4, 16.6, nan, nan],
+           "thresh": [nan, 16.7, 17.6, 17.9, 18.1, 18.2, 17.3, nan, nan],
+           "bthresh": [0, 1, 1, 1, 1, 1, 1, 0, 0], "events": [nan, 1, 1, 1, 1, 1, 1, nan, nan],
+           "relSeas": [nan, 1.3, 2.0, 3.0, 2.79999, 3.2, 1.5, nan, nan],
+           "relThresh": [nan, 0.6, 0.6, 1.6, 1.3, 1.4, 0.8, nan, nan],
+           "relThreshNorm": [nan, 0.85714, 0.4285714, 1.142857, 0.866667, 0.77778, 1.142857, nan, nan],
+           "severity": [nan, -1.857143, -1.42857, -2.142857, -1.8666667, -1.77778, -2.142857, nan, nan],
+           "cats": [nan, 1, 1, 2, 1, 1, 2, nan, nan], "duration_moderate": [0, 1, 1, 0, 1, 1, 0, 0, 0],
+           "duration_strong": [0, 0, 0, 1, 0, 0, 1, 0, 0], "duration_severe": [0] * 9, "duration_extreme": [0] * 9,
+           "mabs": [nan, 17.3, 18.2, 19.5, 19.4, 19.6, 18.1, nan, nan]}
+    for k, v in exp.items():
+        np.testing.assert_allclose(np.asarray(r[k][:, 0], float), np.asarray(v, float), rtol=1e-5, atol=1e-5,
+                                   equal_nan=True, err_msg=k)

@@ -41,6 +41,17 @@ class ClimPlanStruct(C.Structure):
                 ("step_rec", C.c_void_p), ("q", C.c_double)]
 
 
+INTERMEDIATE_FIELDS = (("events", "f8"), ("seas", "f8"), ("thresh", "f8"), ("relSeas", "f8"),
+                       ("relThresh", "f8"), ("relThreshNorm", "f8"), ("severity", "f8"), ("cats", "f8"),
+                       ("mabs", "f4"), ("bthresh", "u1"), ("duration_moderate", "u1"),
+                       ("duration_strong", "u1"), ("duration_severe", "u1"), ("duration_extreme", "u1"))
+
+
+class IntermediateStruct(C.Structure):
+    """Mirror of `xmhw_intermediate` (include/xmhw_b200.h)."""
+    _fields_ = [(name, C.c_void_p) for name, _ in INTERMEDIATE_FIELDS]
+
+
 PLAN_ARRAYS = ("inst_base", "inst_size", "inst_keep", "inst_sbase", "inst_row_off", "rows", "leave_off", "leave",
                "enter_off", "enter", "use_off", "use", "step_rec")
 
@@ -63,6 +74,9 @@ _SIGNATURES = {
     "xmhw_event_stats_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    "xmhw_intermediate_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int64, C.c_int64, C.POINTER(IntermediateStruct),
+                                        C.c_void_p]),
     "xmhw_interp_gaps_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
     "xmhw_copy2d_async": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                     C.c_int32, C.c_void_p]),

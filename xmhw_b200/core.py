@@ -26,7 +26,7 @@ _plan_cache = {}
 # bracketed by CUDA events on the launch stream and (name, start, end) is appended.
 TRACE = None
 LAUNCHES = {"n": 0}
-_KERNELS_PER_CALL = {"xmhw_exclusive_scan_i32": 3}      # finish2: 1 (width 31) or 2 launches
+_KERNELS_PER_CALL = {"xmhw_exclusive_scan_i32": 3, "xmhw_intermediate_f32": 2}      # finish2: 1 (width 31) or 2 launches
 
 
 def _call(name, *args):
@@ -260,6 +260,27 @@ def synth_sst_device(T, ngrid, season, land=None, cell0=0, seed=None, nan_ppm=0,
                                      synth.NOISE_SCALE, int(nan_ppm), _stream())
         torch.cuda.current_stream().synchronize()   # keep `sea`/`ld` alive until the kernel is done
     return ts
+
+
+def intermediate_arrays(ts, doy, ndoy, thresh, seas, events):
+    """Dense per-timestep fields of the reference's `intermediate=True` dataset
+    (identify.py:404-411; mhw_df, features.py:22-69) for an EventTable from detect_arrays.
+    Returns {name: CUDA tensor [T, ngrid]} (float64, `mabs` float32, flags/bthresh bool)."""
+    _require_cuda(ts, "ts", torch.float32)
+    T, ngrid = ts.shape
+    dev = ts.device
+    dt = {"f8": torch.float64, "f4": torch.float32, "u1": torch.uint8}
+    with torch.cuda.device(dev):
+        out = {n: torch.empty((T, ngrid), dtype=dt[k], device=dev) for n, k in _cabi.INTERMEDIATE_FIELDS}
+        out["events"].fill_(float("nan"))
+        st = _cabi.IntermediateStruct(**{n: _ptr(out[n]) for n, _ in _cabi.INTERMEDIATE_FIELDS})
+        _, _, doy32 = _doy_tables(doy, ndoy, dev)
+        _call("xmhw_intermediate_f32", _ptr(ts), T, ngrid, _ptr(doy32), _ptr(thresh), _ptr(seas),
+              _ptr(events.i32), events.n, events.i32.shape[1], st, _stream())
+    for n, k in _cabi.INTERMEDIATE_FIELDS:
+        if k == "u1":
+            out[n] = out[n].bool()
+    return out
 
 
 def threshold_detect_host(ts_host, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercentile=True,

@@ -468,6 +468,48 @@ __global__ void interp_gaps_kernel(float* __restrict__ ts, int64_t T, int64_t ng
   }
 }
 
+// ---------------------------------------------------------------------------
+// intermediate=True (identify.py:404-411): per-timestep fields of mhw_df (features.py:22-69)
+// ---------------------------------------------------------------------------
+__global__ void event_labels_kernel(const int32_t* __restrict__ ei, int64_t nev, int64_t cap, int64_t ngrid,
+                                    double* __restrict__ events) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nev) return;
+  const int64_t cell = ei[EI_CELL * cap + i];
+  const int s = ei[EI_START * cap + i], e = ei[EI_END * cap + i];
+  for (int t = s; t <= e; ++t) events[(int64_t)t * ngrid + cell] = (double)s;      // label = start index
+}
+
+__global__ void intermediate_kernel(const float* __restrict__ ts, int64_t T, int64_t ngrid,
+                                    const int32_t* __restrict__ doy, const double* __restrict__ thresh,
+                                    const double* __restrict__ seas, const double* __restrict__ events,
+                                    xmhw_intermediate out) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t t = blockIdx.y;
+  if (cell >= ngrid) return;
+  const int64_t i = t * ngrid + cell;
+  const int d = doy[t] - 1;
+  const float xf = ts[i];
+  const double x = (double)xf, th = thresh[(int64_t)d * ngrid + cell], se = seas[(int64_t)d * ngrid + cell];
+  out.bthresh[i] = (uint8_t)(x > th);                       // identify.py:372
+  const bool in_ev = events[i] == events[i];                // features.py:38
+  const double nan = qnan();
+  const double relS = x - se, relT = x - th, ths = th - se; // features.py:52-54
+  const double norm = relT / ths, sev = relS / -(ths), cat = floor(1.0 + norm);     // :57-62
+  out.seas[i] = in_ev ? se : nan;
+  out.thresh[i] = in_ev ? th : nan;
+  out.relSeas[i] = in_ev ? relS : nan;
+  out.relThresh[i] = in_ev ? relT : nan;
+  out.relThreshNorm[i] = in_ev ? norm : nan;
+  out.severity[i] = in_ev ? sev : nan;
+  out.cats[i] = in_ev ? cat : nan;
+  out.mabs[i] = in_ev ? xf : __uint_as_float(0x7fc00000u);  // float32, features.py:68
+  out.duration_moderate[i] = (uint8_t)(in_ev && cat == 1.0);                        // :63-66
+  out.duration_strong[i] = (uint8_t)(in_ev && cat == 2.0);
+  out.duration_severe[i] = (uint8_t)(in_ev && cat == 3.0);
+  out.duration_extreme[i] = (uint8_t)(in_ev && cat >= 4.0);
+}
+
 inline int cuda_status() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
@@ -608,6 +650,20 @@ int xmhw_event_stats_f32(const float* ts, int64_t T, int64_t ngrid, const int32_
   const int nt = 128;
   event_stats_kernel<<<(unsigned)((nev + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
       ts, T, ngrid, doy, thresh, seas, nev, cap, ev_i32, ev_f64);
+  return cuda_status();
+}
+
+int xmhw_intermediate_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy, const double* thresh,
+                          const double* seas, const int32_t* ev_i32, int64_t nev, int64_t cap,
+                          const xmhw_intermediate* out, void* stream) {
+  if (!ts || !doy || !thresh || !seas || !out || !out->events || T <= 0 || ngrid <= 0 || nev < 0 ||
+      (nev > 0 && !ev_i32) || T > 65535)
+    return XMHW_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  // events is pre-filled with NaN by the caller; labels first, then the elementwise fields
+  if (nev) event_labels_kernel<<<(unsigned)((nev + 127) / 128), 128, 0, st>>>(ev_i32, nev, cap, ngrid, out->events);
+  dim3 grid((unsigned)((ngrid + 127) / 128), (unsigned)T);
+  intermediate_kernel<<<grid, 128, 0, st>>>(ts, T, ngrid, doy, thresh, seas, out->events, *out);
   return cuda_status();
 }
 

@@ -213,8 +213,6 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
     if maxGap >= minDuration:                                  # xmhw.py:373-377
         raise XmhwException("Maximum gap between mhw events should"
                             + " be smaller than event minimum duration")
-    if intermediate:
-        raise NotImplementedError("intermediate=True (per-timestep dataset, identify.py:404-411) is not built yet")
     data, time, other, coords, attrs, enc, tattrs = _unpack(temp, tdim)
     point = data.ndim == 1
     if not point:
@@ -240,6 +238,15 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
         ts[:, torch.from_numpy(~ocean).cuda()] = float("nan")
     ev = core.detect_arrays(ts, doy, ndoy, torch.from_numpy(th_full).cuda(), torch.from_numpy(se_full).cuda(),
                             minDuration, joinGaps, maxGap)
+    inter = None
+    if intermediate:                                           # identify.py:404-411
+        nbytes = T * flat.shape[1] * 80
+        if nbytes > DENSE_LIMIT_BYTES:
+            raise XmhwException("the per-timestep (intermediate) dataset would need %.1f GB; "
+                                "split the grid (reference docs/dask.rst)" % (nbytes / 1e9))
+        thd, sed = torch.from_numpy(th_full).cuda(), torch.from_numpy(se_full).cuda()
+        inter = {k: v.cpu().numpy() for k, v in core.intermediate_arrays(ts, doy, ndoy, thd, sed, ev).items()}
+        inter["ts"] = ts.cpu().numpy()
     tab = ev.to_numpy()
     n = len(tab["cell"])
     cols = {"event": tab["index_start"].astype(np.float64)}
@@ -313,4 +320,25 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
             ds[v] = labeled.DataArray(dense, dims)
     annotate_ds(ds.attrs, {"ts": attrs}, "mhw")
     ds.attrs["xmhw_parameters"] = params                       # xmhw.py:487-515
+    if intermediate:                                           # xmhw.py:461-463, :471-478
+        if point:
+            di = labeled.Dataset(coords={tdim: time})
+            for k, v in inter.items():
+                di[k] = labeled.DataArray(v[:, 0], (tdim,))
+        else:
+            keep = _present(ocean.reshape(grid_shape))
+            out_coords = {tdim: time}
+            order = []
+            for d, k in zip(other, keep):
+                c = coords[d][k]
+                srt = np.argsort(c, kind="stable")
+                order.append(k[srt])
+                out_coords[d] = c[srt]
+            di = labeled.Dataset(coords=out_coords)
+            for name, v in inter.items():
+                a = v.reshape((T,) + tuple(grid_shape))
+                for ax, ix in enumerate(order):
+                    a = np.take(a, ix, axis=ax + 1)
+                di[name] = labeled.DataArray(a, (tdim,) + tuple(other))
+        return _wrap(ds, temp), _wrap(di, temp)
     return _wrap(ds, temp)
