@@ -213,7 +213,16 @@ def run_ours(args):
 
     # end-to-end through the host-buffer entry point (rank-local, inputs in pinned host memory)
     e2e = None
-    if not args.no_e2e:
+    need_host = T * ngrid * 4 + 2 * 366 * ngrid * 8 + int(nev * 1.05) * (core.EI_COUNT * 4 + core.EF_COUNT * 8)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available / max(1, world)
+    except Exception:
+        avail = float("inf")
+    if not args.no_e2e and avail < need_host * 1.15:
+        e2e = {"value": None, "unit": "cell-years/s", "skipped": "host memory: %.0f GB available per rank, "
+               "%.0f GB of pinned buffers needed" % (avail / 1e9, need_host / 1e9)}
+    elif not args.no_e2e:
         host = torch.empty((T, ngrid), dtype=torch.float32, pin_memory=True)
         host.copy_(ts)
         torch.cuda.synchronize()
