@@ -261,6 +261,24 @@ struct Sweeper {
   // keys of the prefetched instance -> sorted block in the pool
   template <int N>
   XMHW_HD void consume(int base, int sbase, int size, int keep, int& len, int& ptr) {
+    // all-land shortcut: a warp whose 32 cells have no valid sample in this list skips the key
+    // conversion, sums and sort (ocean warps pay one compare + vote for the test)
+    bool some = env.any(ok && pv[0] == pv[0]);
+    if (!some) {
+      bool anyv = false;
+#pragma unroll
+      for (int i = 1; i < N; ++i) anyv = anyv || (i < size && pv[i] == pv[i]);
+      some = env.any(ok && anyv);
+    }
+    if (!some) {
+      len = 0; ptr = 0;
+      scratch[(size_t)(sbase + SCR_SUM) * 32 + lane] = 0u;
+      scratch[(size_t)(sbase + SCR_SUM + 1) * 32 + lane] = 0u;
+      at(base + POOL_META) = ((uint32_t)keep << 12) | ((uint32_t)sbase << 18);
+      at(base + POOL_CINC) = 0xffffffffu;
+      at(base + POOL_CEXC) = 0u;
+      return;
+    }
     uint32_t k[N];
     len = 0;
     double sum = 0.0;
