@@ -50,7 +50,7 @@ static_assert((int)XMHW_EI_COUNT == (int)EI_COUNT && (int)XMHW_EF_COUNT == (int)
 // MAXN = keys per sorted list: 32 (series of <= 32 years: one list per calendar day, ~96
 // registers, 20 warps/SM) or 48 (longer series; larger register sorting networks, fewer warps).
 template <int MAXN>
-__global__ void __launch_bounds__(32, MAXN == 32 ? 20 : 10) clim_sweep_kernel(
+__global__ void __launch_bounds__(32, MAXN == 32 ? 16 : 10) clim_sweep_kernel(
     ClimPlan p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr, double* __restrict__ seas,
     uint32_t* __restrict__ scratch) {
   extern __shared__ uint32_t pool[];
