@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128) clim_finish_reg_kernel(const double* __re
 // exactly as ts > round_down_f32(thresh).
 // ---------------------------------------------------------------------------
 constexpr int EXC_WARPS = 8;
-constexpr int EXC_BATCH = 8;
+constexpr int EXC_BATCH = 16;   // rows in flight per lane (memory-level parallelism)
 
 __global__ void __launch_bounds__(EXC_WARPS * 32) exceed_kernel(
     const float* __restrict__ ts, int64_t T, int64_t ngrid, const int32_t* __restrict__ doy_ptr,
