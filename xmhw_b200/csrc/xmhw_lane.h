@@ -431,92 +431,78 @@ struct Sweeper {
       if (v >= nm1) { fl = nm1; gamma = 0.0; }
       target = n - (int)fl;       // rank (1-based, from the top) of s[floor v]
     }
-    // Walk: every iteration scans the lists in use once, tracking the two smallest keys
-    // above the cut (i1 <= i2, from lists bi1 != bi2) and the two largest keys below it
-    // (e1 >= e2).  A lane that is off target then makes up to TWO moves in its direction
-    // (the second-best candidate is either the other list's or the same list's next key),
-    // lanes on target do nothing; the scan of the last iteration (no lane off target)
-    // delivers a = i1 and the runner-up for b.
-    uint32_t i1 = 0xffffffffu, i2 = 0xffffffffu, e1 = 0u, e2 = 0u;
-    int bi1 = 0, bi2 = 0, be1 = 0, be2 = 0;
+    // Walk.  A lane is off target by d = C - target: it must DROP the d smallest keys above the
+    // cut (d > 0) or ADD the -d largest keys below it (d < 0), in order.  With transformed
+    // candidates (cinc for drops, ~cexc for adds) both are "pop the smallest head of the lists".
+    // One scan certifies the FRONT smallest heads (all other heads are >= bound = the largest of
+    // them); a pop replaces that list's head by its next key, which re-enters the front iff it
+    // is <= bound, otherwise the certified front just shrinks.  A rescan happens only when some
+    // lane exhausts its front -- typically one directional scan + the final scan per doy
+    // instead of one scan per two moves.
     int d = live ? C - target : 0;
-    while (true) {
-      // only the directions some lane still needs are scanned; the last scan (no lane off
-      // target) is a "drop"-side scan because a and b are the two smallest keys above the cut
-      const bool any_dn = env.any(d > 0), any_up = env.any(d < 0);
-      if (any_up && any_dn) scan<true, true>(ub, m4, i1, i2, bi1, bi2, e1, e2, be1, be2);
-      else if (any_up) scan<false, true>(ub, m4, i1, i2, bi1, bi2, e1, e2, be1, be2);
-      else scan<true, false>(ub, m4, i1, i2, bi1, bi2, e1, e2, be1, be2);
-      if (!any_up && !any_dn) break;
-      // ---- drop the smallest keys above the cut (d > 0)
-      if (any_dn) {
-        const bool mv = d > 0;
-        const uint32_t meta = at(bi1 + POOL_META);
-        const int pa = meta_ptr(meta);                          // >= 1 when mv
-        const uint32_t nxt = key_at(bi1, meta, pa - 2, mv && pa >= 2);      // next key up in the same list
-        const uint32_t nx = pa >= 2 ? nxt : 0xffffffffu;
-        const bool two = mv && d >= 2;
-        const bool same = two && nx <= i2;                      // second smallest is in the same list
-        const bool other = two && !same;
-        const uint32_t nn = key_at(bi1, meta, pa - 3, same && pa >= 3);
-        const uint32_t metab = at(bi2 + POOL_META);
-        const int pb = meta_ptr(metab);
-        const uint32_t nb = key_at(bi2, metab, pb - 2, other && pb >= 2);
+    while (env.any(d != 0)) {
+      const bool drop = d >= 0;
+      uint32_t f0 = 0xffffffffu, f1 = 0xffffffffu, f2 = 0xffffffffu, f3 = 0xffffffffu;
+      int g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+      const int crow = drop ? POOL_CINC : POOL_CEXC;
+#pragma unroll 4
+      for (int j = 0; j < m4; ++j) {
+        const int x = (int)ub[j];
+        const uint32_t raw = at(x + crow);
+        const uint32_t tk = drop ? raw : ~raw;
+        if (tk < f3) {
+          f3 = tk; g3 = x;
+          if (f3 < f2) { uint32_t t = f2; f2 = f3; f3 = t; int u = g2; g2 = g3; g3 = u; }
+          if (f2 < f1) { uint32_t t = f1; f1 = f2; f2 = t; int u = g1; g1 = g2; g2 = u; }
+          if (f1 < f0) { uint32_t t = f0; f0 = f1; f1 = t; int u = g0; g0 = g1; g1 = u; }
+        }
+      }
+      const uint32_t bound = f3;
+      int nf = 4;
+      // pop until every lane is on target or some lane has used up its certified front
+      while (true) {
+        const bool mv = d != 0 && nf > 0;
+        if (!env.any(mv)) break;
+        // ---- apply the move of key f0 in list g0
+        const uint32_t meta = at(g0 + POOL_META);
+        const int pa = meta_ptr(meta), la = meta_len(meta);
+        const int np = drop ? pa - 1 : pa + 1;                       // new ptr
+        const int nr = drop ? np - 1 : np;                           // rank of the list's next head
+        const bool has = drop ? np > 0 : np < la;
+        const uint32_t nk = key_at(g0, meta, nr, mv && has);
+        uint32_t ntk = 0xffffffffu;                                  // transformed next head
         if (mv) {
-          if (same) {
-            at(bi1 + POOL_META) = meta - 2u * XMHW_META_PTR1;
-            at(bi1 + POOL_CEXC) = nx;
-            at(bi1 + POOL_CINC) = pa >= 3 ? nn : 0xffffffffu;
-            C -= 2;
+          const uint32_t moved = drop ? f0 : ~f0;                    // the key that crossed the cut
+          at(g0 + POOL_META) = drop ? meta - XMHW_META_PTR1 : meta + XMHW_META_PTR1;
+          if (drop) {
+            at(g0 + POOL_CEXC) = moved;
+            at(g0 + POOL_CINC) = has ? nk : 0xffffffffu;
+            ntk = has ? nk : 0xffffffffu;
+            --C; --d;
           } else {
-            at(bi1 + POOL_META) = meta - XMHW_META_PTR1;
-            at(bi1 + POOL_CEXC) = i1;
-            at(bi1 + POOL_CINC) = nx;
-            C -= 1;
-            if (other) {
-              at(bi2 + POOL_META) = metab - XMHW_META_PTR1;
-              at(bi2 + POOL_CEXC) = i2;
-              at(bi2 + POOL_CINC) = pb >= 2 ? nb : 0xffffffffu;
-              C -= 1;
-            }
+            at(g0 + POOL_CINC) = moved;
+            at(g0 + POOL_CEXC) = has ? nk : 0u;
+            ntk = has ? ~nk : 0xffffffffu;
+            ++C; ++d;
+          }
+          // front: remove f0, insert the list's next head if it is certified (<= bound)
+          const int gm = g0;
+          f0 = f1; g0 = g1; f1 = f2; g1 = g2; f2 = f3; g2 = g3; f3 = 0xffffffffu; g3 = 0;
+          --nf;
+          if (ntk <= bound && ntk != 0xffffffffu) {
+            f3 = ntk; g3 = gm;
+            if (f3 < f2) { uint32_t t = f2; f2 = f3; f3 = t; int u = g2; g2 = g3; g3 = u; }
+            if (f2 < f1) { uint32_t t = f1; f1 = f2; f2 = t; int u = g1; g1 = g2; g2 = u; }
+            if (f1 < f0) { uint32_t t = f0; f0 = f1; f1 = t; int u = g0; g0 = g1; g1 = u; }
+            ++nf;
           }
         }
       }
-      // ---- add the largest keys below the cut (d < 0)
-      if (any_up) {
-        const bool mv = d < 0;
-        const uint32_t meta = at(be1 + POOL_META);
-        const int pa = meta_ptr(meta), la = meta_len(meta);     // pa < la when mv
-        const uint32_t nxt = key_at(be1, meta, pa + 1, mv && pa + 1 < la);  // next key down in the same list
-        const bool two = mv && d <= -2;
-        const bool same = two && nxt >= e2 && pa + 1 < la;      // second largest is in the same list
-        const bool other = two && !same && e2 > 0u;
-        const uint32_t nn = key_at(be1, meta, pa + 2, same && pa + 2 < la);
-        const uint32_t metab = at(be2 + POOL_META);
-        const int pb = meta_ptr(metab), lb = meta_len(metab);
-        const uint32_t nb = key_at(be2, metab, pb + 1, other && pb + 1 < lb);
-        if (mv) {
-          if (same) {
-            at(be1 + POOL_META) = meta + 2u * XMHW_META_PTR1;
-            at(be1 + POOL_CINC) = nxt;
-            at(be1 + POOL_CEXC) = nn;
-            C += 2;
-          } else {
-            at(be1 + POOL_META) = meta + XMHW_META_PTR1;
-            at(be1 + POOL_CINC) = e1;
-            at(be1 + POOL_CEXC) = nxt;
-            C += 1;
-            if (other) {
-              at(be2 + POOL_META) = metab + XMHW_META_PTR1;
-              at(be2 + POOL_CINC) = e2;
-              at(be2 + POOL_CEXC) = nb;
-              C += 1;
-            }
-          }
-        }
-      }
-      d = live ? C - target : 0;
     }
+    // final scan: the two smallest keys above the cut
+    uint32_t i1, i2, e1 = 0u, e2 = 0u;
+    int bi1, bi2, be1 = 0, be2 = 0;
+    scan<true, false>(ub, m4, i1, i2, bi1, bi2, e1, e2, be1, be2);
     // f64 sum of the window; a = i1 (smallest key above the cut), b = next one up
     double sum = 0.0;
     for (int j = 0; j < m4; ++j) {
