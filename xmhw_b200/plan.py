@@ -163,7 +163,7 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
         alive = np.zeros(ndoy, np.int64)
         for i, it in enumerate(insts):
             alive[it["steps"][0]:it["steps"][-1] + 1] += keeps[i] + META_ROWS
-        regular = int(np.percentile(alive, 90)) + NULL_ROWS + 4
+        regular = int(np.median(alive)) + NULL_ROWS
         budget = next((b for b in POOL_ROW_STEPS if b >= regular), POOL_ROW_STEPS[-1])
 
     def allocate(keeps):
@@ -240,7 +240,7 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
         live = sorted({i for s in range(lo_s, hi_s + 1) for i in in_use[s]}, key=lambda i: -keeps[i])
         shrunk = False
         for i in live[:max(1, len(live) // 2)]:
-            if keeps[i] > 2:
+            if keeps[i] > 1:
                 keeps[i] -= 1
                 shrunk = True
         if not shrunk:
