@@ -31,6 +31,7 @@ WORKLOADS = {
     # name: (nlat, nlon, first year, last year, land fraction)
     "global025_30yr": (720, 1440, 1982, 2011, 0.33),     # BASELINE configs[2], the config the metric names
     "regional_40yr": (160, 240, 1982, 2021, 0.0),        # BASELINE configs[1]
+    "global025_quarter": (180, 1440, 1982, 2011, 0.33),  # a quarter of the global grid (development timing)
     "small": (32, 64, 2001, 2010, 0.2),
 }
 METRIC = "cell-years/s, threshold+detect, global 0.25deg 30-yr SST"

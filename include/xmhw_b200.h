@@ -138,6 +138,18 @@ int xmhw_event_stats_f32(const float* ts, int64_t T, int64_t ngrid, const int32_
                          const double* thresh, const double* seas, int64_t nev, int64_t cap,
                          int32_t* ev_i32, double* ev_f64, void* stream);
 
+/* Same statistics from a cell-major interleaved copy of the climatologies,
+ * clim_cm[(cell * ndoy + d) * 2 + {0, 1}] = {thresh, seas}[d][cell] (16-byte aligned,
+ * 2 * ndoy * ngrid doubles, built by xmhw_clim_cellmajor_f64): the consecutive days of an
+ * event then read one contiguous run instead of two scattered 32-byte sectors per day.
+ * Replaces the same reference lines as xmhw_event_stats_f32 (features.py:22-295; the
+ * per-timestep label lookup th.sel(doy=ts.doy), identify.py:367-368). */
+int xmhw_clim_cellmajor_f64(const double* thresh, const double* seas, int32_t ndoy, int64_t ngrid,
+                            double* clim_cm, void* stream);
+int xmhw_event_stats_cm_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy, int32_t ndoy,
+                            const double* clim_cm, int64_t nev, int64_t cap,
+                            int32_t* ev_i32, double* ev_f64, void* stream);
+
 /* intermediate=True (identify.py:404-411): dense per-timestep fields of mhw_df
  * (features.py:22-69), every array [T][ngrid]; `events` must be pre-filled with NaN by the
  * caller (it receives the event label = start index on event days).  T <= 65535.           */

@@ -74,6 +74,9 @@ _SIGNATURES = {
     "xmhw_event_stats_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    "xmhw_clim_cellmajor_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "xmhw_event_stats_cm_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_intermediate_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int64, C.c_int64, C.POINTER(IntermediateStruct),
                                         C.c_void_p]),

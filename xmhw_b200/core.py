@@ -240,8 +240,11 @@ def detect_arrays(ts, doy, ndoy, thresh, seas, minDuration=5, joinGaps=True, max
         if nev:
             _call("xmhw_events_fill", _ptr(mask), T, ngrid, int(minDuration), int(bool(joinGaps)), int(maxGap),
                                        _ptr(offsets), cap, _ptr(ev_i32), st)
-            _call("xmhw_event_stats_f32", _ptr(ts), T, ngrid, _ptr(doy32), _ptr(thresh), _ptr(seas), nev, cap,
-                                           _ptr(ev_i32), _ptr(ev_f64), st)
+            # cell-major {thresh, seas} pairs: an event's consecutive days become one contiguous run
+            clim_cm = torch.empty((ngrid, ndoy, 2), dtype=torch.float64, device=dev)
+            _call("xmhw_clim_cellmajor_f64", _ptr(thresh), _ptr(seas), ndoy, ngrid, _ptr(clim_cm), st)
+            _call("xmhw_event_stats_cm_f32", _ptr(ts), T, ngrid, _ptr(doy32), ndoy, _ptr(clim_cm), nev, cap,
+                                              _ptr(ev_i32), _ptr(ev_f64), st)
     return EventTable(ev_i32, ev_f64, nev, offsets, nvalid, T, ngrid)
 
 

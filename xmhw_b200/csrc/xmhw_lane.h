@@ -582,29 +582,56 @@ enum EvF64 { EF_INT_MAX = 0, EF_INT_MEAN, EF_INT_CUM, EF_INT_VAR,
              EF_ABS_MAX, EF_ABS_MEAN, EF_ABS_CUM, EF_ABS_VAR,
              EF_RATE_ONSET, EF_RATE_DECLINE, EF_COUNT };
 
-enum { EV_BATCH = 4 };
+enum { EV_BATCH_DEFAULT = 4 };
 
-// NaN-skipping running moments (pandas groupby mean/sum/var(ddof=1) skip NaN;
-// Welford update like pandas' group_var).
+// NaN-skipping running sums (pandas groupby mean/sum/var(ddof=1) skip NaN).  Plain f64
+// sum and sum of squares: for this data (|x| < 1e3, an event is < 1e4 days) the cancellation
+// error of (sq - sum^2/n) is < 1e-9 relative, far inside the 1e-5 / 1 f32 ulp contract, and
+// it costs 3 FP64 operations per day instead of the division of a Welford update.
 struct Moments {
-  int n; double sum, mean, m2;
-  XMHW_HD Moments() : n(0), sum(0.0), mean(0.0), m2(0.0) {}
+  int n; double sum, sq;
+  XMHW_HD Moments() : n(0), sum(0.0), sq(0.0) {}
   XMHW_HD void add(double x) {
     if (x != x) return;
-    ++n; sum = sum + x;
-    double d = x - mean;
-    mean = mean + d / (double)n;
-    m2 = m2 + d * (x - mean);
+    ++n; sum = sum + x; sq = sq + x * x;
   }
   XMHW_HD double avg() const { return n ? sum / (double)n : qnan(); }
-  XMHW_HD double sd() const { return n >= 2 ? sqrt(m2 / (double)(n - 1)) : qnan(); }
+  XMHW_HD double sd() const {
+    if (n < 2) return qnan();
+    const double v = (sq - sum * sum / (double)n) / (double)(n - 1);
+    return v > 0.0 ? sqrt(v) : (v == v ? 0.0 : v);
+  }
 };
 
 XMHW_HD double round_f32(double x) { return (double)(float)x; }
 
 // One event [s, e] of the cell whose series starts at `col` (stride ngrid),
 // thresholds/seasonal at th/se (doy-major, stride ngrid), doy[t] 1-based.
+// Climatology access of one cell: get(d, thresh, seas) for the 0-based day-of-year d.
+// Doy-major = the reference layout (doy, cell); the CUDA path also has a cell-major
+// interleaved copy (xmhw_kernels.cu) so that the ~12 consecutive days of an event are one
+// contiguous 200-byte run instead of 2 x 12 scattered 32-byte sectors.
+struct ClimDoyMajor {
+  const double* th; const double* se; int64_t ngrid;
+  XMHW_HD void get(int d, double& t, double& s) const {
+    t = XMHW_LDG(th + (int64_t)d * ngrid);
+    s = XMHW_LDG(se + (int64_t)d * ngrid);
+  }
+};
+
+template <int EV_BATCH, class Clim>
+XMHW_HD void event_stats(const float* col, const Clim& clim, const int32_t* doy,
+                         int64_t ngrid, int T, int s, int e, int32_t* oi, double* of, int64_t stride);
+
+template <int EV_BATCH = EV_BATCH_DEFAULT>
 XMHW_HD void event_stats(const float* col, const double* th, const double* se, const int32_t* doy,
+                         int64_t ngrid, int T, int s, int e, int32_t* oi, double* of, int64_t stride) {
+  ClimDoyMajor clim{th, se, ngrid};
+  event_stats<EV_BATCH, ClimDoyMajor>(col, clim, doy, ngrid, T, s, e, oi, of, stride);
+}
+
+template <int EV_BATCH, class Clim>
+XMHW_HD void event_stats(const float* col, const Clim& clim, const int32_t* doy,
                          int64_t ngrid, int T, int s, int e, int32_t* oi, double* of, int64_t stride) {
   Moments mS, mV, mT, mA;
   double smax = -INFINITY, vmax = -INFINITY, catmax = -INFINITY;
@@ -617,8 +644,9 @@ XMHW_HD void event_stats(const float* col, const double* th, const double* se, c
   // anom[t-1], anom_minus anom[t+1] (features.py:45-46)
   double prev_anom = qnan();
   if (s >= 1) {
-    int d = XMHW_LDG(doy + s - 1) - 1;
-    prev_anom = (double)XMHW_LDG(col + (int64_t)(s - 1) * ngrid) - XMHW_LDG(se + (int64_t)d * ngrid);
+    double t_, s_;
+    clim.get(XMHW_LDG(doy + s - 1) - 1, t_, s_);
+    prev_anom = (double)XMHW_LDG(col + (int64_t)(s - 1) * ngrid) - s_;
   }
   // days are processed in batches of EV_BATCH with all loads of a batch issued first
   // (memory-level parallelism; the per-day arithmetic is a serial f64 chain)
@@ -630,8 +658,7 @@ XMHW_HD void event_stats(const float* col, const double* th, const double* se, c
       const int tt = t0 + i <= e ? t0 + i : e;           // clamped: loads stay unconditional
       const int dd = XMHW_LDG(doy + tt) - 1;
       xs[i] = XMHW_LDG(col + (int64_t)tt * ngrid);
-      thb[i] = XMHW_LDG(th + (int64_t)dd * ngrid);
-      seb[i] = XMHW_LDG(se + (int64_t)dd * ngrid);
+      clim.get(dd, thb[i], seb[i]);
     }
 #pragma unroll
     for (int i = 0; i < EV_BATCH; ++i) {
@@ -642,8 +669,11 @@ XMHW_HD void event_stats(const float* col, const double* th, const double* se, c
       double relT = x - thr;                 // :53
       double ths = thr - sea;                // :54
       double norm = relT / ths;              // :57
-      double sev = relS / -(ths);            // :59-61
-      double cat = floor(1.0 + norm);        // :62
+      double one_norm = 1.0 + norm;
+      // :59-61 severity = relS / -(ths); relS = relT + ths up to an ulp, so it is -(1 + norm)
+      // to ~2 f64 ulp (inf / NaN cases agree) -- one division per day instead of two
+      double sev = -one_norm;
+      double cat = floor(one_norm);          // :62
       if (anom_first != anom_first && prev_anom == prev_anom) anom_first = prev_anom;   // first non-null anom_plus
       if (t > s && relS == relS) anom_last = relS;     // anom_minus of day t-1 is anom[t]
       if (relS == relS) {
@@ -662,8 +692,9 @@ XMHW_HD void event_stats(const float* col, const double* th, const double* se, c
     }
   }
   if (e + 1 <= T - 1) {       // anom_minus of the last event day
-    int d = XMHW_LDG(doy + e + 1) - 1;
-    double a = (double)XMHW_LDG(col + (int64_t)(e + 1) * ngrid) - XMHW_LDG(se + (int64_t)d * ngrid);
+    double t_, s_;
+    clim.get(XMHW_LDG(doy + e + 1) - 1, t_, s_);
+    double a = (double)XMHW_LDG(col + (int64_t)(e + 1) * ngrid) - s_;
     if (a == a) anom_last = a;
   }
   oi[EI_START * stride] = s;
