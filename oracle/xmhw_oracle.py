@@ -187,17 +187,39 @@ def feb29(x):
 
 def runavg(x, w):
     """identify.py:154-181: circular centred moving mean of odd width w over the
-    doy axis (axis 0); any NaN in a window gives NaN (rolling min_periods=w)."""
+    doy axis (axis 0); any NaN in a window gives NaN (rolling min_periods=w).
+
+    The reference's rounding depends on the installed rolling backend (bottleneck
+    running sum or numpy window mean), so the summation ORDER is defined here and the
+    CUDA kernel follows it bit for bit: wrap the series, e[j] = x[(j - h) mod nd] for
+    j = 0 .. nd + w - 2, cut e into blocks of w, and write window d = b w + p as the
+    right-to-left suffix sum of block b from p plus the left-to-right prefix sum of
+    block b + 1 up to p - 1 (p == 0: the suffix alone).  Any order is within ~1e-15
+    relative of any other; this one costs 3 additions per output."""
     if w % 2 == 0:
         raise ValueError("Running average window should be odd")
+    x = np.asarray(x, np.float64)
     nd = x.shape[0]
     h = (w - 1) // 2
+    L = nd + w - 1
+    e = x[(np.arange(L) - h) % nd]
+    pre = np.empty_like(e)
+    suf = np.empty_like(e)
+    for lo in range(0, L, w):
+        hi = min(L, lo + w)
+        acc = e[lo].copy()
+        pre[lo] = acc
+        for j in range(lo + 1, hi):
+            acc = acc + e[j]
+            pre[j] = acc
+        acc = e[hi - 1].copy()
+        suf[hi - 1] = acc
+        for j in range(hi - 2, lo - 1, -1):
+            acc = e[j] + acc
+            suf[j] = acc
     out = np.empty_like(x, dtype=np.float64)
     for d in range(nd):
-        acc = np.zeros(x.shape[1:], np.float64)
-        for k in range(-h, h + 1):
-            acc = acc + x[(d + k) % nd]
-        out[d] = acc / w
+        out[d] = (suf[d] if d % w == 0 else suf[d] + pre[d + w - 1]) / w
     return out
 
 

@@ -9,6 +9,7 @@
 // exactly like numpy/pandas (no FMA contraction).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/xmhw_b200.h"
 #include "xmhw_lane.h"
@@ -49,8 +50,8 @@ static_assert((int)XMHW_EI_COUNT == (int)EI_COUNT && (int)XMHW_EF_COUNT == (int)
 // ---------------------------------------------------------------------------
 // MAXN = keys per sorted list: 32 (series of <= 32 years: one list per calendar day, ~96
 // registers, 20 warps/SM) or 48 (longer series; larger register sorting networks, fewer warps).
-template <int MAXN>
-__global__ void __launch_bounds__(32, MAXN == 32 ? 16 : 10) clim_sweep_kernel(
+template <int MAXN, int MINB>
+__global__ void __launch_bounds__(32, MINB) clim_sweep_kernel(
     ClimPlan p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr, double* __restrict__ seas,
     uint32_t* __restrict__ scratch) {
   extern __shared__ uint32_t pool[];
@@ -72,94 +73,150 @@ __global__ void __launch_bounds__(32, MAXN == 32 ? 16 : 10) clim_sweep_kernel(
 }
 
 // ---------------------------------------------------------------------------
-// K1b  Feb-29 rule + circular running mean over doy.  One thread = one cell,
-// a ring of `W` raw values per thread in shared memory (column = thread, so
-// bank-conflict free); fresh left-to-right f64 sum per output (bit-equal to the
-// oracle's order).
+// K1b  Feb-29 rule + circular running mean over doy.  One thread = one cell.
+//
+// Summation order (shared with the oracle, oracle/xmhw_oracle.py:runavg, so results are
+// bit-equal): with the wrapped sequence e[j] = x[(j - h) mod ndoy], j = 0 .. ndoy + W - 2,
+// cut into blocks of W, output d = b W + p is
+//     suf_b[p]                      (p == 0: the whole block, summed right to left)
+//     suf_b[p] + pre_{b+1}[p - 1]   (p >= 1)
+// where suf_b[p] = e[bW+p] + (e[bW+p+1] + (... + e[bW+W-1])) and pre_b[i] = ((e[bW] + e[bW+1]) + ...) + e[bW+i].
+// Every window is one suffix of a block plus one prefix of the next, so an output costs
+// 3 FP64 additions instead of W - 1 (the FP64 pipe, not HBM, bounded the direct sum).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double finish_value(const double* __restrict__ raw, int64_t ngrid, int64_t cell,
-                                               int ndoy, int feb29, int idx) {
-  if (feb29 && idx == 59 && ndoy >= 61) {
-    double acc = 0.0; int n = 0;
+struct FinishSrc {
+  const double* __restrict__ raw;     // this cell's column (stride ngrid)
+  int64_t ngrid;
+  int ndoy;
+  bool feb;                           // substitute doy 60 (index 59)
+  double v59;                         // mean of the non-NaN values at doy 59, 60, 61 (identify.py:137-151)
+  __device__ __forceinline__ void init(const double* r, int64_t ng, int nd, int feb29) {
+    raw = r; ngrid = ng; ndoy = nd; feb = feb29 && nd >= 61; v59 = 0.0;
+    if (feb) {
+      double acc = 0.0; int n = 0;
 #pragma unroll
-    for (int d = 58; d <= 60; ++d) {
-      double v = raw[(int64_t)d * ngrid + cell];
-      if (v == v) { acc = acc + v; ++n; }
+      for (int d = 58; d <= 60; ++d) {
+        const double v = raw[(int64_t)d * ngrid];
+        if (v == v) { acc = acc + v; ++n; }
+      }
+      v59 = n ? acc / (double)n : qnan();
     }
-    return n ? acc / (double)n : qnan();
   }
-  return raw[(int64_t)idx * ngrid + cell];
+  __device__ __forceinline__ double at(int idx) const {          // idx in [0, ndoy)
+    const double v = raw[(int64_t)idx * ngrid];
+    return (feb && idx == 59) ? v59 : v;
+  }
+};
+
+// x / W, correctly rounded, for a small odd constant W: q = x * RN(1/W) refined by one
+// exact-residual step (Markstein); non-finite or tiny values take the true division.
+template <int W>
+__device__ __forceinline__ double div_const(double x) {
+  const double w = (double)W, rc = 1.0 / (double)W;
+  const double q = x * rc;
+  const double rem = __fma_rn(-q, w, x);
+  const double q2 = __fma_rn(rem, rc, q);
+  const double ax = fabs(x);
+  return (ax > 1e-280 && ax < 1e300) ? q2 : x / w;
 }
 
+// generic odd width: W slots per thread in shared memory (column = thread: conflict free)
 __global__ void clim_finish_kernel(const double* __restrict__ raw, double* __restrict__ out, int ndoy,
                                    int64_t ngrid, int feb29, int W) {
-  extern __shared__ double ring[];
+  extern __shared__ double slots[];
   const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= ngrid) return;
+  FinishSrc src;
+  src.init(raw + cell, ngrid, ndoy, feb29);
+  double* __restrict__ o = out + cell;
   if (W <= 1) {
-    for (int d = 0; d < ndoy; ++d) out[(int64_t)d * ngrid + cell] = finish_value(raw, ngrid, cell, ndoy, feb29, d);
+    for (int d = 0; d < ndoy; ++d) o[(int64_t)d * ngrid] = src.at(d);
     return;
   }
   const int h = (W - 1) / 2;
   const int nt = blockDim.x, tid = threadIdx.x;
-  // unwrapped index u = d + k, k in [-h, h]; ring slot = (u + h) mod W
-  for (int u = -h; u < h; ++u) {
-    int idx = ((u % ndoy) + ndoy) % ndoy;
-    ring[((u + h) % W) * nt + tid] = finish_value(raw, ngrid, cell, ndoy, feb29, idx);
-  }
-  for (int d = 0; d < ndoy; ++d) {
-    int u = d + h;
-    ring[((u + h) % W) * nt + tid] = finish_value(raw, ngrid, cell, ndoy, feb29, u % ndoy);
-    int slot = d % W;     // slot of u = d - h
-    double acc = 0.0;
-    for (int k = 0; k < W; ++k) {
-      acc = acc + ring[slot * nt + tid];
-      slot = slot + 1 == W ? 0 : slot + 1;
+  int idx = ((-h) % ndoy + ndoy) % ndoy;                        // index of e[j], advanced with wrap
+  for (int i = 0; i < W; ++i) { slots[i * nt + tid] = src.at(idx); idx = idx + 1 == ndoy ? 0 : idx + 1; }
+  for (int i = W - 2; i >= 0; --i) slots[i * nt + tid] = slots[i * nt + tid] + slots[(i + 1) * nt + tid];
+  const double w = (double)W;
+  for (int d0 = 0; d0 < ndoy; d0 += W) {
+    double pre = 0.0;
+    for (int p = 0; p < W && d0 + p < ndoy; ++p) {
+      double S = slots[p * nt + tid];
+      if (p >= 1) {
+        const double en = src.at(idx); idx = idx + 1 == ndoy ? 0 : idx + 1;
+        pre = p == 1 ? en : pre + en;
+        S = S + pre;
+        slots[(p - 1) * nt + tid] = en;
+      }
+      o[(int64_t)(d0 + p) * ngrid] = S / w;
     }
-    out[(int64_t)d * ngrid + cell] = acc / (double)W;
+    if (d0 + W < ndoy) {
+      slots[(W - 1) * nt + tid] = src.at(idx); idx = idx + 1 == ndoy ? 0 : idx + 1;
+      for (int i = W - 2; i >= 0; --i) slots[i * nt + tid] = slots[i * nt + tid] + slots[(i + 1) * nt + tid];
+    }
   }
 }
 
-// Register-ring variant for a compile-time width (the default 31): the doy loop is
-// unrolled by W so every ring slot is a statically indexed register; same left-to-right
-// f64 summation order as the generic kernel, ~5x fewer instructions per output.
+// compile-time width (the default 31): the W slots are statically indexed registers
 template <int W>
 __global__ void __launch_bounds__(128) clim_finish_reg_kernel(const double* __restrict__ raw0, double* __restrict__ out0,
                                                               const double* __restrict__ raw1, double* __restrict__ out1,
                                                               int ndoy, int64_t ngrid, int feb29) {
   const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= ngrid) return;
-  const double* __restrict__ raw = blockIdx.y ? raw1 : raw0;
-  double* __restrict__ out = blockIdx.y ? out1 : out0;
+  FinishSrc src;
+  src.init((blockIdx.y ? raw1 : raw0) + cell, ngrid, ndoy, feb29);
+  double* __restrict__ o = (blockIdx.y ? out1 : out0) + cell;
   constexpr int h = (W - 1) / 2;
-  double ring[W];
+  double slot[W];
+  int idx = ((-h) % ndoy + ndoy) % ndoy;
 #pragma unroll
-  for (int i = 0; i < W - 1; ++i)
-    ring[i] = finish_value(raw, ngrid, cell, ndoy, feb29, (((i - h) % ndoy) + ndoy) % ndoy);
-  // Two consecutive outputs per inner step: their left-to-right sums are independent
-  // dependency chains (each ~W x FP64-add latency), interleaving them doubles the ILP.
+  for (int i = 0; i < W; ++i) { slot[i] = src.at(idx); idx = idx + 1 == ndoy ? 0 : idx + 1; }
+#pragma unroll
+  for (int i = W - 2; i >= 0; --i) slot[i] = slot[i] + slot[i + 1];
   for (int d0 = 0; d0 < ndoy; d0 += W) {
+    double pre = 0.0;
+    if (d0 + W < ndoy) {                        // full block of outputs, another block follows
+      constexpr int G = 8;                      // loads in flight per thread
 #pragma unroll
-    for (int r = 0; r < W; r += 2) {
-      const int d = d0 + r;
-      if (d < ndoy) {
-        const bool two = r + 1 < W && d + 1 < ndoy;
-        ring[(r + W - 1) % W] = finish_value(raw, ngrid, cell, ndoy, feb29, (d + h) % ndoy);
-        double nxt = 0.0;                       // value entering the window of d + 1 (slot r)
-        if (two) nxt = finish_value(raw, ngrid, cell, ndoy, feb29, (d + 1 + h) % ndoy);
-        double acc0 = 0.0, acc1 = 0.0;
+      for (int p0 = 0; p0 < W; p0 += G) {
+        double en[G];
 #pragma unroll
-        for (int k = 0; k < W; ++k) {
-          acc0 = acc0 + ring[(r + k) % W];
-          if (k >= 1) acc1 = acc1 + ring[(r + k) % W];
-        }
-        acc1 = acc1 + nxt;
-        out[(int64_t)d * ngrid + cell] = acc0 / (double)W;
-        if (two) {
-          out[(int64_t)(d + 1) * ngrid + cell] = acc1 / (double)W;
-          ring[r % W] = nxt;
+        for (int i = 0; i < G; ++i)
+          if (p0 + i < W) { en[i] = src.at(idx); idx = idx + 1 == ndoy ? 0 : idx + 1; }
+        // en[i] = e[(b+1)W + p0 + i]: feeds output p0 + i + 1 and becomes slot[p0 + i] of the next block
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          const int p = p0 + i;                 // output p (needs en of p - 1, loaded in the previous group)
+          if (p < W) {
+            if (p == 0) o[(int64_t)d0 * ngrid] = div_const<W>(slot[0]);
+            if (p + 1 < W) {
+              pre = p == 0 ? en[i] : pre + en[i];
+              o[(int64_t)(d0 + p + 1) * ngrid] = div_const<W>(slot[p + 1] + pre);
+            }
+            slot[p] = en[i];
+          }
         }
       }
+    } else {
+#pragma unroll
+      for (int p = 0; p < W; ++p) {
+        if (d0 + p < ndoy) {
+          double S = slot[p];
+          if (p >= 1) {
+            const double e1 = src.at(idx); idx = idx + 1 == ndoy ? 0 : idx + 1;
+            pre = p == 1 ? e1 : pre + e1;
+            S = S + pre;
+            slot[p - 1] = e1;
+          }
+          o[(int64_t)(d0 + p) * ngrid] = div_const<W>(S);
+        }
+      }
+    }
+    if (d0 + W < ndoy) {
+#pragma unroll
+      for (int i = W - 2; i >= 0; --i) slot[i] = slot[i] + slot[i + 1];
     }
   }
 }
@@ -590,15 +647,20 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
   memcpy(&p, plan, sizeof(p));
   const int64_t ncg = (ngrid + 31) / 32;
   cudaError_t e;
-  if (plan->max_size <= 32) {
-    e = cudaFuncSetAttribute(clim_sweep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    clim_sweep_kernel<32><<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw, scratch);
-  } else {
-    e = cudaFuncSetAttribute(clim_sweep_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    clim_sweep_kernel<48><<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw, scratch);
+  static const int minb = getenv("XMHW_B200_SWEEP_MINB") ? atoi(getenv("XMHW_B200_SWEEP_MINB")) : 16;   // development knob
+#define XMHW_SWEEP(N, B)                                                                                            \
+  {                                                                                                                 \
+    e = cudaFuncSetAttribute(clim_sweep_kernel<N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e != cudaSuccess) return (int)e;                                                                            \
+    clim_sweep_kernel<N, B><<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw,  \
+                                                                               scratch);                           \
   }
+  if (plan->max_size <= 32) {
+    if (minb >= 24) XMHW_SWEEP(32, 24) else if (minb >= 20) XMHW_SWEEP(32, 20) else XMHW_SWEEP(32, 16)
+  } else {
+    XMHW_SWEEP(48, 10)
+  }
+#undef XMHW_SWEEP
   return cuda_status();
 }
 

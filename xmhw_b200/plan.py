@@ -90,9 +90,9 @@ def default_keep():
     return int(os.environ.get("XMHW_B200_KEEP", "6"))
 
 
-# pool rows that let N = 20, 19, ... 1 single-warp blocks share one SM's 227 KB of shared
+# pool rows that let N = 32, 31, ... 1 single-warp blocks share one SM's 227 KB of shared
 # memory (1 KB per block is reserved by the system, 2 rows per pool are staging rows)
-POOL_ROW_STEPS = tuple((227 * 1024 // nw - 1024) // 128 - STAGE_ROWS for nw in range(20, 0, -1))
+POOL_ROW_STEPS = tuple((227 * 1024 // nw - 1024) // 128 - STAGE_ROWS for nw in range(32, 0, -1))
 
 
 def default_pool_rows():
