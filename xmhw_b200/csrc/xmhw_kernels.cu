@@ -234,11 +234,12 @@ __global__ void __launch_bounds__(EXC_WARPS * 32) exceed_kernel(
     const float* __restrict__ ts, int64_t T, int64_t ngrid, const int32_t* __restrict__ doy_ptr,
     const int32_t* __restrict__ doy_tidx, int ndoy, int nchunk, const double* __restrict__ thresh,
     uint32_t* __restrict__ mask, int32_t* __restrict__ nvalid) {
+  // the warps of a block take ADJACENT cell groups of the same doy chunk, so a block reads
+  // EXC_WARPS x 128 contiguous bytes of every row (DRAM page locality)
   const int lane = threadIdx.x & 31;
-  const int64_t w = (int64_t)blockIdx.x * EXC_WARPS + (threadIdx.x >> 5);
   const int64_t ncg = (ngrid + 31) / 32;
-  const int64_t cg = w / nchunk;
-  const int chunk = (int)(w % nchunk);
+  const int64_t cg = (int64_t)(blockIdx.x / nchunk) * EXC_WARPS + (threadIdx.x >> 5);
+  const int chunk = (int)(blockIdx.x % nchunk);
   if (cg >= ncg) return;
   const int64_t cell = cg * 32 + lane;
   const bool ok = cell < ngrid;
@@ -281,10 +282,10 @@ __global__ void __launch_bounds__(EXC_WARPS * 32) exceed4_kernel(
     const int32_t* __restrict__ doy_tidx, int ndoy, int nchunk, const double* __restrict__ thresh,
     uint32_t* __restrict__ mask, int32_t* __restrict__ nvalid) {
   const int lane = threadIdx.x & 31;
-  const int64_t w = (int64_t)blockIdx.x * EXC_WARPS + (threadIdx.x >> 5);
   const int64_t nsg = (ngrid + 127) / 128;                  // super-groups of 128 cells
-  const int64_t sg = w / nchunk;
-  const int chunk = (int)(w % nchunk);
+  // adjacent super-groups per block, same doy chunk: EXC_WARPS x 512 contiguous bytes per row
+  const int64_t sg = (int64_t)(blockIdx.x / nchunk) * EXC_WARPS + (threadIdx.x >> 5);
+  const int chunk = (int)(blockIdx.x % nchunk);
   if (sg >= nsg) return;
   const int64_t cell = sg * 128 + 4 * lane;                 // first of this lane's 4 cells
   const bool ok = cell < ngrid;                             // ngrid % 4 == 0: all 4 or none
@@ -710,13 +711,13 @@ int xmhw_exceed_mask_f32(const float* ts, int64_t T, int64_t ngrid, const int32_
     const int64_t nsg = (ngrid + 127) / 128;
     int nc4 = (int)((148 * 64 * 2 + nsg - 1) / nsg);
     nc4 = nc4 < 1 ? 1 : (nc4 > ndoy ? ndoy : nc4);
-    const int64_t nw4 = nsg * nc4;
-    exceed4_kernel<<<(unsigned)((nw4 + EXC_WARPS - 1) / EXC_WARPS), EXC_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    const int64_t nb4 = ((nsg + EXC_WARPS - 1) / EXC_WARPS) * nc4;
+    exceed4_kernel<<<(unsigned)nb4, EXC_WARPS * 32, 0, (cudaStream_t)stream>>>(
         ts, T, ngrid, doy_ptr, doy_tidx, ndoy, nc4, thresh, mask, nvalid);
     return cuda_status();
   }
-  const int64_t nwarp = ncg * nchunk;
-  exceed_kernel<<<(unsigned)((nwarp + EXC_WARPS - 1) / EXC_WARPS), EXC_WARPS * 32, 0, (cudaStream_t)stream>>>(
+  const int64_t nblk = ((ncg + EXC_WARPS - 1) / EXC_WARPS) * nchunk;
+  exceed_kernel<<<(unsigned)nblk, EXC_WARPS * 32, 0, (cudaStream_t)stream>>>(
       ts, T, ngrid, doy_ptr, doy_tidx, ndoy, nchunk, thresh, mask, nvalid);
   return cuda_status();
 }

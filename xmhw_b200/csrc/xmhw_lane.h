@@ -29,6 +29,20 @@
 
 #include "sortnet_gen.h"
 
+// development statistics hooks (tools/sweep_stats.cpp defines them; no-ops in the product)
+#ifndef XMHW_STAT_SCAN
+#define XMHW_STAT_SCAN()
+#define XMHW_STAT_POP(in_scratch)
+#define XMHW_STAT_STEP(d0)
+#endif
+#ifndef XMHW_STAT_RANK
+#define XMHW_STAT_RANK(r)
+#endif
+#ifndef XMHW_STAT_PTR0
+#define XMHW_STAT_PTR0(base, ptr)
+#define XMHW_STAT_OFF(base, r)
+#endif
+
 namespace xmhw {
 
 // ---------------------------------------------------------------------------
@@ -440,7 +454,10 @@ struct Sweeper {
     // lane exhausts its front -- typically one directional scan + the final scan per doy
     // instead of one scan per two moves.
     int d = live ? C - target : 0;
+    XMHW_STAT_STEP(d);
+    for (int j = 0; j < m; ++j) { XMHW_STAT_PTR0((int)ub[j], meta_ptr(at((int)ub[j] + POOL_META))); }
     while (env.any(d != 0)) {
+      XMHW_STAT_SCAN();
       const bool drop = d >= 0;
       uint32_t f0 = 0xffffffffu, f1 = 0xffffffffu, f2 = 0xffffffffu, f3 = 0xffffffffu;
       int g0 = 0, g1 = 0, g2 = 0, g3 = 0;
@@ -470,6 +487,7 @@ struct Sweeper {
         const int nr = drop ? np - 1 : np;                           // rank of the list's next head
         const bool has = drop ? np > 0 : np < la;
         const uint32_t nk = key_at(g0, meta, nr, mv && has);
+        if (mv) { XMHW_STAT_POP(has && nr >= meta_keep(meta)); if (has) { XMHW_STAT_RANK(nr); XMHW_STAT_OFF(g0, nr); } }
         uint32_t ntk = 0xffffffffu;                                  // transformed next head
         if (mv) {
           const uint32_t moved = drop ? f0 : ~f0;                    // the key that crossed the cut
