@@ -130,6 +130,17 @@ int xmhw_exclusive_scan_i32(const int32_t* counts, int64_t n, int64_t* offsets, 
 int xmhw_events_fill(const uint32_t* mask, int64_t T, int64_t ngrid, int32_t min_duration,
                      int32_t join_gaps, int32_t max_gap, const int64_t* offsets, int64_t cap,
                      int32_t* ev_i32, void* stream);
+/* One-pass variant of count + fill (same reference lines, identify.py:415-479, :273-325):
+ * the count pass also parks the first cap_per_cell (start, end) pairs of every cell in
+ * stage [ceil(ngrid/32)][2][cap_per_cell][32] i32 and ORs 1 into *overflow when a cell has
+ * more; after the scan, xmhw_events_gather copies the staged pairs to ev_i32 at the
+ * offsets.  If *overflow is set the caller runs xmhw_events_fill instead (exact path).   */
+int xmhw_events_count_stage(const uint32_t* mask, int64_t T, int64_t ngrid, int32_t min_duration,
+                            int32_t join_gaps, int32_t max_gap, int32_t* counts, int32_t* stage,
+                            int32_t cap_per_cell, int32_t* overflow, void* stream);
+int xmhw_events_gather(const int32_t* stage, int32_t cap_per_cell, const int32_t* counts,
+                       const int64_t* offsets, int64_t ngrid, int64_t cap, int32_t* ev_i32,
+                       void* stream);
 
 /* features.py:22-295 mhw_df + agg_df + properties + onset_decline for nev events.
  * doy [T] i32 (1-based labels); thresh, seas [ndoy][ngrid] f64;

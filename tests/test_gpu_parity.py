@@ -139,6 +139,26 @@ def test_detect_options(core):
         core.detect_arrays(ts, doy, 366, th, se, minDuration=3, maxGap=3)
 
 
+def test_event_staging_overflow_falls_back_to_exact_fill(core, monkeypatch):
+    """The one-pass event finder parks a bounded number of events per cell; a cell with more
+    must take the exact two-pass path and give the same table."""
+    from xmhw_b200 import synth
+    time = synth.daily_time(1982, 2011)
+    doy = synth.doy366(time)
+    ts = torch.from_numpy(synth.synth_sst(len(time), 96, synth.season_table(time))).cuda()
+    th, se = core.threshold_arrays(ts, doy, 366)
+    a = core.detect_arrays(ts, doy, 366, th, se).to_numpy()
+    assert np.bincount(a["cell"]).max() > 8
+    monkeypatch.setattr(core, "STAGE_EVENTS_PER_YEAR", 0)        # staging capacity 8 events per cell
+    core.TRACE = []
+    b = core.detect_arrays(ts, doy, 366, th, se).to_numpy()
+    names = [n for n, _, _ in core.TRACE]
+    core.TRACE = None
+    assert "xmhw_events_fill" in names and "xmhw_events_gather" not in names
+    for f in a:
+        assert np.array_equal(a[f], b[f], equal_nan=True), f
+
+
 def test_reference_event_tables(core, ref_cases):
     """Event tables from the UNMODIFIED reference pandas code (tests/golden/ref_detect_cases.npz)."""
     from tests.util import F32_FIELDS

@@ -172,6 +172,11 @@ def interp_gaps_(ts, max_pad):
     return ts
 
 
+# staging capacity of the one-pass event finder (events per cell and year; overflow falls back
+# to the exact two-pass path)
+STAGE_EVENTS_PER_YEAR = 4
+
+
 class EventTable:
     """Compact event table on the device (struct of arrays).
 
@@ -228,18 +233,33 @@ def detect_arrays(ts, doy, ndoy, thresh, seas, minDuration=5, joinGaps=True, max
         _call("xmhw_exceed_mask_f32", _ptr(ts), T, ngrid, _ptr(ptr), _ptr(tidx), ndoy, _ptr(thresh),
                                        _ptr(mask), _ptr(nvalid), st)
         counts = torch.empty(ngrid, dtype=torch.int32, device=dev)
-        _call("xmhw_events_count", _ptr(mask), T, ngrid, int(minDuration), int(bool(joinGaps)), int(maxGap),
-                                    _ptr(counts), st)
-        offsets = torch.empty(ngrid + 1, dtype=torch.int64, device=dev)
+        # the count pass parks each cell's (start, end) pairs in a staging table sized for
+        # STAGE_EVENTS_PER_YEAR events per year, so the mask is scanned once; a cell with more
+        # events sets the overflow flag and the exact second pass over the mask runs instead
+        years = max(1, -(-T // max(ndoy, 1)))
+        stage_cap = int(min(max(8, STAGE_EVENTS_PER_YEAR * years), max(8, T // max(1, minDuration + 1) + 1)))
+        stage = torch.empty((ncg, 2, stage_cap, 32), dtype=torch.int32, device=dev)
+        offsets = torch.empty(ngrid + 2, dtype=torch.int64, device=dev)     # [ngrid + 1] = overflow flag
+        overflow = offsets[ngrid + 1:].view(torch.int32)
+        overflow.zero_()
+        _call("xmhw_events_count_stage", _ptr(mask), T, ngrid, int(minDuration), int(bool(joinGaps)), int(maxGap),
+                                          _ptr(counts), _ptr(stage), stage_cap, _ptr(overflow), st)
         scratch = torch.empty(ngrid // 1024 + 2, dtype=torch.int64, device=dev)
         _call("xmhw_exclusive_scan_i32", _ptr(counts), ngrid, _ptr(offsets), _ptr(scratch), st)
-        nev = int(offsets[-1].item())          # the one host sync: sizes the event table
+        tail = offsets[ngrid:].cpu()           # the one host sync: event total (sizes the table) + overflow flag
+        nev, overflowed = int(tail[0]), bool(int(tail[1]) & 0xffffffff)
+        offsets = offsets[:ngrid + 1]
         cap = max(nev, 1)
         ev_i32 = torch.empty((EI_COUNT, cap), dtype=torch.int32, device=dev)
         ev_f64 = torch.empty((EF_COUNT, cap), dtype=torch.float64, device=dev)
         if nev:
-            _call("xmhw_events_fill", _ptr(mask), T, ngrid, int(minDuration), int(bool(joinGaps)), int(maxGap),
-                                       _ptr(offsets), cap, _ptr(ev_i32), st)
+            if overflowed:
+                _call("xmhw_events_fill", _ptr(mask), T, ngrid, int(minDuration), int(bool(joinGaps)), int(maxGap),
+                                           _ptr(offsets), cap, _ptr(ev_i32), st)
+            else:
+                _call("xmhw_events_gather", _ptr(stage), stage_cap, _ptr(counts), _ptr(offsets), ngrid, cap,
+                                             _ptr(ev_i32), st)
+            del stage
             # cell-major {thresh, seas} pairs: an event's consecutive days become one contiguous run
             clim_cm = torch.empty((ngrid, ndoy, 2), dtype=torch.float64, device=dev)
             _call("xmhw_clim_cellmajor_f64", _ptr(thresh), _ptr(seas), ndoy, ngrid, _ptr(clim_cm), st)

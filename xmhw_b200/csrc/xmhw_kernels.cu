@@ -360,6 +360,16 @@ struct CountEmit {
   int n;
   __device__ __forceinline__ void operator()(int, int) { ++n; }
 };
+// counts and also parks the first `cap` events of the cell in a staging table
+// (slot-major: [cell group][slot][lane]) so that no second pass over the mask is needed
+struct StageEmit {
+  int n, cap;
+  int32_t* s_row; int32_t* e_row;      // this lane's column of the group's staging block
+  __device__ __forceinline__ void operator()(int s, int e) {
+    if (n < cap) { s_row[(size_t)n * 32] = s; e_row[(size_t)n * 32] = e; }
+    ++n;
+  }
+};
 struct FillEmit {
   int32_t* ev; int64_t cap, pos; int32_t cell;
   __device__ __forceinline__ void operator()(int s, int e) {
@@ -390,6 +400,53 @@ __global__ void __launch_bounds__(EVT_WARPS * 32) events_kernel(
   }
   if (FILL) { if (ok) rf.finish((int)T, fe); }
   else { rf.finish((int)T, ce); if (ok) counts[cell] = ce.n; }
+}
+
+// count pass that also stages the events: stage [ncg][2][cap][32] int32 (starts, ends)
+__global__ void __launch_bounds__(EVT_WARPS * 32) events_stage_kernel(
+    const uint32_t* __restrict__ mask, int64_t T, int64_t ngrid, int min_dur, int join, int max_gap,
+    int32_t* __restrict__ counts, int32_t* __restrict__ stage, int cap, int32_t* __restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const int64_t cg = (int64_t)blockIdx.x * EVT_WARPS + (threadIdx.x >> 5);
+  if (cg >= (ngrid + 31) / 32) return;
+  const int64_t cell = cg * 32 + lane;
+  const bool ok = cell < ngrid;
+  const uint32_t* mrow = mask + cg * T;
+  RunFinder rf(min_dur, join, max_gap);
+  StageEmit se;
+  se.n = 0; se.cap = ok ? cap : 0;
+  se.s_row = stage + (size_t)cg * 2 * cap * 32 + lane;
+  se.e_row = se.s_row + (size_t)cap * 32;
+  for (int64_t t0 = 0; t0 < T; t0 += 32) {
+    uint32_t x = (t0 + lane < T) ? __ldg(mrow + t0 + lane) : 0u;
+    uint32_t bits = transpose32(x, lane);
+    rf.feed(bits, (int)t0, se);
+  }
+  rf.finish((int)T, se);
+  if (ok) {
+    counts[cell] = se.n;
+    if (se.n > cap) atomicOr(overflow, 1);
+  }
+}
+
+// staged events -> event table columns (cell, start, end) at the scanned offsets
+__global__ void __launch_bounds__(EVT_WARPS * 32) events_gather_kernel(
+    const int32_t* __restrict__ stage, int cap_per_cell, const int32_t* __restrict__ counts,
+    const int64_t* __restrict__ offsets, int64_t ngrid, int64_t cap, int32_t* __restrict__ ev) {
+  const int lane = threadIdx.x & 31;
+  const int64_t cg = (int64_t)blockIdx.x * EVT_WARPS + (threadIdx.x >> 5);
+  if (cg >= (ngrid + 31) / 32) return;
+  const int64_t cell = cg * 32 + lane;
+  const bool ok = cell < ngrid;
+  const int n = ok ? counts[cell] : 0;
+  const int64_t pos = ok ? offsets[cell] : 0;
+  const int32_t* s_row = stage + (size_t)cg * 2 * cap_per_cell * 32 + lane;
+  const int32_t* e_row = s_row + (size_t)cap_per_cell * 32;
+  for (int k = 0; k < n; ++k) {
+    ev[EI_CELL * cap + pos + k] = (int32_t)cell;
+    ev[EI_START * cap + pos + k] = s_row[(size_t)k * 32];
+    ev[EI_END * cap + pos + k] = e_row[(size_t)k * 32];
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -728,6 +785,27 @@ int xmhw_events_count(const uint32_t* mask, int64_t T, int64_t ngrid, int32_t mi
   const int64_t ncg = (ngrid + 31) / 32;
   events_kernel<false><<<(unsigned)((ncg + EVT_WARPS - 1) / EVT_WARPS), EVT_WARPS * 32, 0, (cudaStream_t)stream>>>(
       mask, T, ngrid, min_duration, join_gaps, max_gap, counts, nullptr, 0, nullptr);
+  return cuda_status();
+}
+
+int xmhw_events_count_stage(const uint32_t* mask, int64_t T, int64_t ngrid, int32_t min_duration,
+                            int32_t join_gaps, int32_t max_gap, int32_t* counts, int32_t* stage,
+                            int32_t cap_per_cell, int32_t* overflow, void* stream) {
+  if (!mask || !counts || !stage || !overflow || T <= 0 || ngrid <= 0 || min_duration < 1 || max_gap < 0 ||
+      cap_per_cell < 1)
+    return XMHW_E_ARG;
+  const int64_t ncg = (ngrid + 31) / 32;
+  events_stage_kernel<<<(unsigned)((ncg + EVT_WARPS - 1) / EVT_WARPS), EVT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      mask, T, ngrid, min_duration, join_gaps, max_gap, counts, stage, cap_per_cell, overflow);
+  return cuda_status();
+}
+
+int xmhw_events_gather(const int32_t* stage, int32_t cap_per_cell, const int32_t* counts, const int64_t* offsets,
+                       int64_t ngrid, int64_t cap, int32_t* ev_i32, void* stream) {
+  if (!stage || !counts || !offsets || !ev_i32 || ngrid <= 0 || cap <= 0 || cap_per_cell < 1) return XMHW_E_ARG;
+  const int64_t ncg = (ngrid + 31) / 32;
+  events_gather_kernel<<<(unsigned)((ncg + EVT_WARPS - 1) / EVT_WARPS), EVT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      stage, cap_per_cell, counts, offsets, ngrid, cap, ev_i32);
   return cuda_status();
 }
 
