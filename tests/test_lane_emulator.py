@@ -70,6 +70,24 @@ def test_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct, keep):
     assert hp.rows_loaded < len(doy) * 1.1 and hp.max_size <= 48
 
 
+def test_sweep_infinite_samples(em):
+    """+-inf samples poison the running window sum only while they are inside the window."""
+    tm = S.daily_time(2001, 2012)
+    doy = S.doy366(tm)
+    ts = S.synth_sst(len(tm), 6, S.season_table(tm))
+    ts[500, 1] = np.inf
+    ts[900, 2] = -np.inf
+    ts[1300, 3] = np.inf
+    ts[1302, 3] = -np.inf
+    hp, thr, se = sweep(em, ts, doy, 366, 5, 0.9)
+    with np.errstate(invalid="ignore"):
+        oth, ose = O.threshold(ts, doy, 366, smoothPercentile=False, tstep=True)
+    assert bit_equal(thr, oth)
+    assert np.array_equal(np.isnan(se), np.isnan(ose)) and np.array_equal(np.isinf(se), np.isinf(ose))
+    fin = np.isfinite(ose)
+    assert np.abs(se[fin] - ose[fin]).max() <= 1e-12 and (~fin).sum() >= 30
+
+
 def test_sweep_pentad_and_reference_cube(em, oisst):
     doy = np.tile(np.arange(1, 74), 30)
     ts = S.synth_sst(len(doy), 16, S.season_table(len(doy)))

@@ -221,13 +221,14 @@ struct Sweeper {
   const int64_t ngrid;
   const bool ok;
   int C, n;              // keys above the cut / valid samples, over the lists in use
+  double wsum;           // running f64 sum of the samples of the lists in use (+ entering, - leaving list sums)
   uint32_t pivot;        // cut value (key of the smallest sample above the cut)
   float pv[MAXN];        // prefetched rows of the next instance to load (MAXN = 32 or 48 keys per list)
   int total_enter;
   Vec rec_next, use_next;   // step record / list bases of the next step (prefetched)
 
   XMHW_HD Sweeper(const Env& e, const ClimPlan& pl, uint32_t* po, uint32_t* sc, int ln, const float* c, int64_t ng, bool k)
-      : env(e), p(pl), pool(po), scratch(sc), lane(ln), col(c), ngrid(ng), ok(k), C(0), n(0), pivot(0xffffffffu) {}
+      : env(e), p(pl), pool(po), scratch(sc), lane(ln), col(c), ngrid(ng), ok(k), C(0), n(0), wsum(0.0), pivot(0xffffffffu) {}
 
   XMHW_HD uint32_t& at(int row) { return pool[row * 32 + lane]; }
 
@@ -321,15 +322,21 @@ struct Sweeper {
     }
     scratch[(size_t)(sbase + SCR_SUM) * 32 + lane] = f64_lo(sum);
     scratch[(size_t)(sbase + SCR_SUM + 1) * 32 + lane] = f64_hi(sum);
+    wsum = wsum + sum;
     at(base + POOL_META) = (uint32_t)len | ((uint32_t)ptr << 6) | ((uint32_t)keep << 12) | ((uint32_t)sbase << 18);
     at(base + POOL_CINC) = cinc;
     at(base + POOL_CEXC) = cexc;
   }
 
-  XMHW_HD void leave_list(int base) {
+  // the leaving list's f64 sum comes back as two words so that the caller can defer the
+  // subtraction until after the walk (the scratch load latency then hides behind it)
+  XMHW_HD void leave_list(int base, uint32_t& slo, uint32_t& shi) {
     const uint32_t meta = at(base + POOL_META);
     C -= meta_ptr(meta);
     n -= meta_len(meta);
+    const size_t sb = (size_t)meta_sbase(meta) * 32 + lane;
+    slo = scratch[sb + SCR_SUM * 32];
+    shi = scratch[sb + (SCR_SUM + 1) * 32];
   }
 
   XMHW_HD void enter_list(int e, int base, int size, int keep, int sbase, int entry_index) {
@@ -350,6 +357,8 @@ struct Sweeper {
       const uint32_t ce = key_at(base, meta, ptr, ptr < len);
       at(base + POOL_CINC) = ptr > 0 ? ci : 0xffffffffu;
       at(base + POOL_CEXC) = ce;
+      const size_t sb = (size_t)meta_sbase(meta) * 32 + lane;
+      wsum = wsum + f64_from(scratch[sb + SCR_SUM * 32], scratch[sb + (SCR_SUM + 1) * 32]);
     }
     C += ptr;
     n += len;
@@ -409,8 +418,13 @@ struct Sweeper {
     const int n_leave = ovf ? XMHW_LDG(p.leave_off + s + 1) - l0 : (int)(w0 & 0xffu);
     const int eoff = ovf ? XMHW_LDG(p.enter_off + s) : env.vget(rec, STEP_ENTER_OFF);
     const int n_enter = ovf ? XMHW_LDG(p.enter_off + s + 1) - eoff : (int)((w0 >> 8) & 0xffu);
-    for (int j = 0; j < n_leave; ++j)
-      leave_list(ovf ? XMHW_LDG(p.leave + l0 + j) : env.vget(rec, (STEP_LEAVE + j) & 31));
+    uint32_t plo = 0u, phi = 0u;          // sum of the first leaving list, subtracted after the walk
+    for (int j = 0; j < n_leave; ++j) {
+      uint32_t slo, shi;
+      leave_list(ovf ? XMHW_LDG(p.leave + l0 + j) : env.vget(rec, (STEP_LEAVE + j) & 31), slo, shi);
+      if (j == 0) { plo = slo; phi = shi; }
+      else wsum = wsum - f64_from(slo, shi);
+    }
 #pragma unroll 1
     for (int j = 0; j < n_enter; ++j) {
       int e, base, size, keep, sbase;
@@ -433,7 +447,11 @@ struct Sweeper {
     env.vstage(ub, usev, m, m4, lane);
 
     const bool live = n > 0;
-    if (!env.any(live)) { thresh = qnan(); seas = qnan(); return; }   // all-land warp
+    if (!env.any(live)) {                                             // all-land warp
+      wsum = wsum - f64_from(plo, phi);
+      thresh = qnan(); seas = qnan();
+      return;
+    }
     // numpy 'linear' quantile: v = (n-1) q, a = s[floor v], b = s[floor v + 1]; v >= n-1 -> max
     int target = 0;
     double gamma = 0.0;
@@ -521,12 +539,18 @@ struct Sweeper {
     uint32_t i1, i2, e1 = 0u, e2 = 0u;
     int bi1, bi2, be1 = 0, be2 = 0;
     scan<true, false>(ub, m4, i1, i2, bi1, bi2, e1, e2, be1, be2);
-    // f64 sum of the window; a = i1 (smallest key above the cut), b = next one up
-    double sum = 0.0;
-    for (int j = 0; j < m4; ++j) {
-      const size_t sb = (size_t)meta_sbase(at((int)ub[j] + POOL_META)) * 32 + lane;
-      sum = sum + f64_from(scratch[sb + SCR_SUM * 32], scratch[sb + (SCR_SUM + 1) * 32]);
+    // f64 sum of the window = running sum of the list sums (exact whenever the list sums are:
+    // f32 samples of similar exponent); a non-finite value (inf samples) is rebuilt from the lists
+    wsum = wsum - f64_from(plo, phi);
+    if (env.any(!(wsum - wsum == 0.0))) {
+      double fresh = 0.0;
+      for (int j = 0; j < m4; ++j) {
+        const size_t sb = (size_t)meta_sbase(at((int)ub[j] + POOL_META)) * 32 + lane;
+        fresh = fresh + f64_from(scratch[sb + SCR_SUM * 32], scratch[sb + (SCR_SUM + 1) * 32]);
+      }
+      if (!(wsum - wsum == 0.0)) wsum = fresh;
     }
+    const double sum = wsum;
     const uint32_t m1 = i1, m2 = i2;
     const uint32_t meta1 = at(bi1 + POOL_META);
     const int ptr1 = meta_ptr(meta1);
