@@ -187,6 +187,23 @@ template <> XMHW_HD void sort_desc<32>(uint32_t* k) { XMHW_SORTNET_32 }
 template <> XMHW_HD void sort_desc<40>(uint32_t* k) { XMHW_SORTNET_40 }
 template <> XMHW_HD void sort_desc<48>(uint32_t* k) { XMHW_SORTNET_48 }
 
+XMHW_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+XMHW_HD uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+// Branch-free insertion of (key t, tag x) into the ascending 4-entry front (f0 <= f1 <= f2 <= f3)
+// that keeps the 4 smallest; ties keep the earlier entry first.  All 4 compares and the 7
+// min/max are independent of each other (depth 2), unlike a chain of conditional swaps.
+XMHW_HD void front_insert(uint32_t t, int x, uint32_t& f0, uint32_t& f1, uint32_t& f2, uint32_t& f3,
+                          int& g0, int& g1, int& g2, int& g3) {
+  const bool c0 = t < f0, c1 = t < f1, c2 = t < f2, c3 = t < f3;
+  const uint32_t n3 = umin32(f3, umax32(f2, t)), n2 = umin32(f2, umax32(f1, t)), n1 = umin32(f1, umax32(f0, t));
+  g3 = c2 ? g2 : (c3 ? x : g3);
+  g2 = c1 ? g1 : (c2 ? x : g2);
+  g1 = c0 ? g0 : (c1 ? x : g1);
+  g0 = c0 ? x : g0;
+  f0 = umin32(f0, t); f1 = n1; f2 = n2; f3 = n3;
+}
+
 // numpy _lerp (lib/_function_base_impl.py): d = b - a in float32, result in
 // float64 with two roundings, no FMA (the .cu is compiled with --fmad=false).
 XMHW_HD double lerp_q(float a, float b, double g) {
@@ -258,9 +275,11 @@ struct Sweeper {
   // key at rank r of the list at `base` (0 when !need)
   XMHW_HD uint32_t key_at(int base, uint32_t meta, int r, bool need) {
     const int keep = meta_keep(meta);
-    uint32_t k = 0u;
-    if (need) k = r < keep ? at(base + POOL_KEYS + r) : scratch[(size_t)(meta_sbase(meta) + SCR_KEYS + r - keep) * 32 + lane];
-    return k;
+    const bool in_pool = r < keep;
+    // shared-memory read is unconditional (row clamped into the block); the scratch read is the rare path
+    uint32_t k = at(base + POOL_KEYS + ((in_pool && need) ? r : 0));
+    if (need && !in_pool) k = scratch[(size_t)(meta_sbase(meta) + SCR_KEYS + r - keep) * 32 + lane];
+    return need ? k : 0u;
   }
 
   // number of keys of the list strictly above `piv` (keys descending)
@@ -386,19 +405,15 @@ struct Sweeper {
       const int x = (int)ub[j];
       if (INC) {
         const uint32_t ki = at(x + POOL_CINC);
-        if (ki < i2) {
-          const bool first = ki < i1;
-          i2 = first ? i1 : ki; bi2 = first ? bi1 : x;
-          if (first) { i1 = ki; bi1 = x; }
-        }
+        const bool c1 = ki < i1, c2 = ki < i2;            // branch-free 2-entry front (ties keep the earlier list)
+        i2 = umin32(i2, umax32(i1, ki)); bi2 = c1 ? bi1 : (c2 ? x : bi2);
+        i1 = umin32(i1, ki); bi1 = c1 ? x : bi1;
       }
       if (EXC) {
         const uint32_t ke = at(x + POOL_CEXC);
-        if (ke > e2) {
-          const bool first = ke > e1;
-          e2 = first ? e1 : ke; be2 = first ? be1 : x;
-          if (first) { e1 = ke; be1 = x; }
-        }
+        const bool c1 = ke > e1, c2 = ke > e2;
+        e2 = umax32(e2, umin32(e1, ke)); be2 = c1 ? be1 : (c2 ? x : be2);
+        e1 = umax32(e1, ke); be1 = c1 ? x : be1;
       }
     }
   }
@@ -485,15 +500,14 @@ struct Sweeper {
         const int x = (int)ub[j];
         const uint32_t raw = at(x + crow);
         const uint32_t tk = drop ? raw : ~raw;
-        if (tk < f3) {
-          f3 = tk; g3 = x;
-          if (f3 < f2) { uint32_t t = f2; f2 = f3; f3 = t; int u = g2; g2 = g3; g3 = u; }
-          if (f2 < f1) { uint32_t t = f1; f1 = f2; f2 = t; int u = g1; g1 = g2; g2 = u; }
-          if (f1 < f0) { uint32_t t = f0; f0 = f1; f1 = t; int u = g0; g0 = g1; g1 = u; }
-        }
+        front_insert(tk, x, f0, f1, f2, f3, g0, g1, g2, g3);
       }
       const uint32_t bound = f3;
       int nf = 4;
+      // direction constants of this lane (a walk never changes direction)
+      const uint32_t flip = drop ? 0u : 0xffffffffu;
+      const int sgn = drop ? -1 : 1, nroff = drop ? -2 : 1;
+      const int rowA = drop ? POOL_CEXC : POOL_CINC, rowB = drop ? POOL_CINC : POOL_CEXC;
       // pop until every lane is on target or some lane has used up its certified front
       while (true) {
         const bool mv = d != 0 && nf > 0;
@@ -501,37 +515,23 @@ struct Sweeper {
         // ---- apply the move of key f0 in list g0
         const uint32_t meta = at(g0 + POOL_META);
         const int pa = meta_ptr(meta), la = meta_len(meta);
-        const int np = drop ? pa - 1 : pa + 1;                       // new ptr
-        const int nr = drop ? np - 1 : np;                           // rank of the list's next head
-        const bool has = drop ? np > 0 : np < la;
+        const int nr = pa + nroff;                                   // rank of the list's next head
+        const bool has = (unsigned)nr < (unsigned)la;                // drop: ptr >= 2, add: ptr + 1 < len
         const uint32_t nk = key_at(g0, meta, nr, mv && has);
         if (mv) { XMHW_STAT_POP(has && nr >= meta_keep(meta)); if (has) { XMHW_STAT_RANK(nr); XMHW_STAT_OFF(g0, nr); } }
-        uint32_t ntk = 0xffffffffu;                                  // transformed next head
         if (mv) {
-          const uint32_t moved = drop ? f0 : ~f0;                    // the key that crossed the cut
-          at(g0 + POOL_META) = drop ? meta - XMHW_META_PTR1 : meta + XMHW_META_PTR1;
-          if (drop) {
-            at(g0 + POOL_CEXC) = moved;
-            at(g0 + POOL_CINC) = has ? nk : 0xffffffffu;
-            ntk = has ? nk : 0xffffffffu;
-            --C; --d;
-          } else {
-            at(g0 + POOL_CINC) = moved;
-            at(g0 + POOL_CEXC) = has ? nk : 0u;
-            ntk = has ? ~nk : 0xffffffffu;
-            ++C; ++d;
-          }
+          const uint32_t ntk = has ? (nk ^ flip) : 0xffffffffu;      // transformed next head
+          at(g0 + POOL_META) = meta + (uint32_t)(sgn * (int)XMHW_META_PTR1);
+          at(g0 + rowA) = f0 ^ flip;                                 // the key that crossed the cut
+          at(g0 + rowB) = ntk ^ flip;                                // next head, or the empty sentinel of that side
+          C += sgn; d += sgn;
           // front: remove f0, insert the list's next head if it is certified (<= bound)
           const int gm = g0;
           f0 = f1; g0 = g1; f1 = f2; g1 = g2; f2 = f3; g2 = g3; f3 = 0xffffffffu; g3 = 0;
           --nf;
-          if (ntk <= bound && ntk != 0xffffffffu) {
-            f3 = ntk; g3 = gm;
-            if (f3 < f2) { uint32_t t = f2; f2 = f3; f3 = t; int u = g2; g2 = g3; g3 = u; }
-            if (f2 < f1) { uint32_t t = f1; f1 = f2; f2 = t; int u = g1; g1 = g2; g2 = u; }
-            if (f1 < f0) { uint32_t t = f0; f0 = f1; f1 = t; int u = g0; g0 = g1; g1 = u; }
-            ++nf;
-          }
+          const bool cert = ntk <= bound && ntk != 0xffffffffu;
+          front_insert(cert ? ntk : 0xffffffffu, gm, f0, f1, f2, f3, g0, g1, g2, g3);   // ~0 never enters
+          nf += cert;
         }
       }
     }
