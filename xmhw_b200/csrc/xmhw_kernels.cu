@@ -857,19 +857,9 @@ int xmhw_event_stats_cm_f32(const float* ts, int64_t T, int64_t ngrid, const int
     return XMHW_E_ARG;
   if (nev == 0) return 0;
   const int nt = 128;
-  const unsigned nb = (unsigned)((nev + nt - 1) / nt);
-  cudaStream_t st = (cudaStream_t)stream;
-  static const int variant = getenv("XMHW_B200_EVK") ? atoi(getenv("XMHW_B200_EVK")) : 0;   // development knob
-#define XMHW_EVK(B, M) event_stats_cm_kernel<B, M><<<nb, nt, 0, st>>>(ts, T, ngrid, doy, ndoy, (const double2*)clim_cm, nev, cap, ev_i32, ev_f64)
-  switch (variant) {
-    case 1: XMHW_EVK(8, 5); break;
-    case 2: XMHW_EVK(6, 5); break;
-    case 3: XMHW_EVK(4, 5); break;
-    case 4: XMHW_EVK(12, 3); break;
-    case 5: XMHW_EVK(6, 4); break;
-    default: XMHW_EVK(8, 4); break;   // 8 days of loads in flight per thread (memory-level parallelism beats occupancy)
-  }
-#undef XMHW_EVK
+  // 8 days of loads in flight per thread, 4 blocks/SM: measured best of {4,6,8,12} x {3..6 blocks}
+  event_stats_cm_kernel<8, 4><<<(unsigned)((nev + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
+      ts, T, ngrid, doy, ndoy, (const double2*)clim_cm, nev, cap, ev_i32, ev_f64);
   return cuda_status();
 }
 

@@ -146,6 +146,7 @@ enum { STEP_COUNTS = 0,      // n_leave | n_enter << 8 | n_use << 16 | overflow 
        STEP_ENTER = 6,       // 4 x 3 words: (instance id | load flag << 30), (base | size << 16 | keep << 24), scratch base
        STEP_NEXT_USE_OFF = 18, STEP_NEXT_NUSE = 19,   // the same two numbers of the next step
        STEP_ENTER_OFF = 20,  // index of this step's first entry in plan.enter
+       STEP_NEXT_LOAD = 21,  // 4 x 2 words: (offset into plan.rows, size) of the list to prefetch after entry j (size 0: none)
        STEP_WORDS = 32, STEP_MAX_INLINE = 4 };
 
 // Instance block layout in the pool (row = 32 words, word index = lane):
@@ -255,8 +256,15 @@ struct Sweeper {
     while (j < total_enter && !(XMHW_LDG(p.enter + j) >> 30)) ++j;
     if (j >= total_enter) return;
     const int id = XMHW_LDG(p.enter + j) & 0x3fffffff;
-    const int size = XMHW_LDG(p.inst_size + id);
-    const Vec rv = env.vload(p.rows + XMHW_LDG(p.inst_row_off + id), size, lane);   // up to 64 entries
+    prefetch_rows(XMHW_LDG(p.inst_row_off + id), XMHW_LDG(p.inst_size + id));
+  }
+
+  // issue the loads of the list whose time rows are plan.rows[row_off .. row_off + size)
+  XMHW_HD void prefetch_rows(int row_off, int size) {
+    if (size <= 0) return;
+    prefetch_rows(env.vload(p.rows + row_off, size, lane), size);   // up to 64 entries
+  }
+  XMHW_HD void prefetch_rows(const Vec& rv, int size) {
     // unconditional loads (entries past `size` read row 0 and are masked in consume), so the
     // compiler keeps all of them in flight instead of waiting on each predicated result
     const uint32_t ng32 = (uint32_t)ngrid;      // row offset as one 32x32->64 multiply (ngrid < 2^32)
@@ -358,14 +366,16 @@ struct Sweeper {
     shi = scratch[sb + (SCR_SUM + 1) * 32];
   }
 
-  XMHW_HD void enter_list(int e, int base, int size, int keep, int sbase, int entry_index) {
+  // next_off / next_size: the list to prefetch afterwards when known from the step record
+  // (next_size < 0: look it up in the plan arrays -- a chain of dependent loads)
+  XMHW_HD void enter_list(int e, int base, int size, int keep, int sbase, int entry_index, int next_off, int next_size) {
     int len, ptr;
     if (e >> 30) {
       if (size <= 8) consume<8>(base, sbase, size, keep, len, ptr);
       else if (MAXN == 32 || size <= 32) consume<32>(base, sbase, size, keep, len, ptr);
       else if (size <= 40) consume<(MAXN > 32 ? 40 : 32)>(base, sbase, size, keep, len, ptr);
       else consume<(MAXN > 32 ? 48 : 32)>(base, sbase, size, keep, len, ptr);
-      prefetch(entry_index + 1);
+      if (next_size >= 0) prefetch_rows(next_off, next_size); else prefetch(entry_index + 1);
     } else {          // list re-enters after a hole (Feb 29): pointer against the current cut
       uint32_t meta = at(base + POOL_META);
       len = meta_len(meta);
@@ -434,15 +444,24 @@ struct Sweeper {
     const int eoff = ovf ? XMHW_LDG(p.enter_off + s) : env.vget(rec, STEP_ENTER_OFF);
     const int n_enter = ovf ? XMHW_LDG(p.enter_off + s + 1) - eoff : (int)((w0 >> 8) & 0xffu);
     uint32_t plo = 0u, phi = 0u;          // sum of the first leaving list, subtracted after the walk
-    for (int j = 0; j < n_leave; ++j) {
+    if (n_leave > 0)                      // no use of the loaded words here: the load stays in flight
+      leave_list(ovf ? XMHW_LDG(p.leave + l0) : env.vget(rec, STEP_LEAVE), plo, phi);
+    for (int j = 1; j < n_leave; ++j) {
       uint32_t slo, shi;
       leave_list(ovf ? XMHW_LDG(p.leave + l0 + j) : env.vget(rec, (STEP_LEAVE + j) & 31), slo, shi);
-      if (j == 0) { plo = slo; phi = shi; }
-      else wsum = wsum - f64_from(slo, shi);
+      wsum = wsum - f64_from(slo, shi);
+    }
+    // row indices of the list that will be prefetched after this step's first entering load:
+    // requested now so that they are here when the prefetch is issued (no dependent-load wait)
+    int early_size = -1;
+    Vec early_rows = rec;
+    if (!ovf && n_enter > 0) {
+      early_size = env.vget(rec, STEP_NEXT_LOAD + 1);
+      if (early_size > 0) early_rows = env.vload(p.rows + env.vget(rec, STEP_NEXT_LOAD), early_size, lane);
     }
 #pragma unroll 1
     for (int j = 0; j < n_enter; ++j) {
-      int e, base, size, keep, sbase;
+      int e, base, size, keep, sbase, next_off = 0, next_size = -1;
       if (ovf) {
         e = XMHW_LDG(p.enter + eoff + j);
         const int id = e & 0x3fffffff;
@@ -453,8 +472,15 @@ struct Sweeper {
         const uint32_t pk = (uint32_t)env.vget(rec, (STEP_ENTER + 3 * j + 1) & 31);
         sbase = env.vget(rec, (STEP_ENTER + 3 * j + 2) & 31);
         base = (int)(pk & 0xffffu); size = (int)((pk >> 16) & 0xffu); keep = (int)(pk >> 24);
+        next_off = env.vget(rec, (STEP_NEXT_LOAD + 2 * j) & 31);
+        next_size = env.vget(rec, (STEP_NEXT_LOAD + 2 * j + 1) & 31);
       }
-      enter_list(e, base, size, keep, sbase, eoff + j);
+      if (j == 0 && early_size >= 0 && (e >> 30)) {        // row indices already on their way
+        enter_list(e, base, size, keep, sbase, eoff + j, 0, 0);     // (0, 0): no prefetch inside
+        if (early_size > 0) prefetch_rows(early_rows, early_size);
+      } else {
+        enter_list(e, base, size, keep, sbase, eoff + j, next_off, next_size);
+      }
     }
     // stage the base rows of the lists in use (padded to a multiple of 4 with the null list)
     const int m4 = (m + 3) & ~3;

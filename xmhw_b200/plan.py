@@ -305,6 +305,16 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
             rec[s, 18] = use_off[s + 1]
             rec[s, 19] = use_off[s + 2] - use_off[s + 1]
         rec[s, 20] = enter_off[s]
+        if not ovf:
+            # the list to prefetch after each entering load: (row offset, size) of the next load entry
+            for j in range(ne):
+                g = enter_off[s] + j + 1
+                while g < len(enter) and not enter[g] & LOAD_FLAG:
+                    g += 1
+                if g < len(enter):
+                    i = enter[g] & (LOAD_FLAG - 1)
+                    rec[s, 21 + 2 * j] = int(row_off[i])
+                    rec[s, 22 + 2 * j] = int(sizes[i])
     step_rec = rec.astype(np.uint32).view(np.int32).reshape(-1)
 
     def arr(x):
