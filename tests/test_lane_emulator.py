@@ -116,8 +116,8 @@ def test_plan_rejects_unsupported():
 def test_run_finder_fuzz(em):
     lib, _ = em
     rng = np.random.default_rng(5)
-    for trial in range(1500):
-        T = int(rng.integers(1, 200))
+    for trial in range(2500):
+        T = int(rng.integers(1, 200)) if trial < 1500 else int(rng.integers(60, 700))
         b = (rng.random(T) < rng.uniform(0.05, 0.95)).astype(np.uint8)
         if trial % 2:
             b = np.repeat(b, rng.integers(1, 6))[:T].copy()

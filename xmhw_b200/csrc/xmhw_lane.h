@@ -96,6 +96,13 @@ XMHW_HD uint32_t f32_key(float f) {
 XMHW_HD float key_f32(uint32_t k) {
   return bits_f32((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
 }
+XMHW_HD int clz32(uint32_t x) {      // x != 0
+#ifdef __CUDA_ARCH__
+  return __clz((int)x);
+#else
+  return __builtin_clz(x);
+#endif
+}
 XMHW_HD int ctz32(uint32_t x) {
 #ifdef __CUDA_ARCH__
   return __ffs((int)x) - 1;
@@ -612,9 +619,35 @@ struct RunFinder {
     if (ps >= 0) emit(ps, pe);
     ps = s; pe = e;
   }
+  // Runs shorter than min_dur never qualify and never bridge a gap (the duration filter comes
+  // before the join), so those lying strictly inside the word can be erased with a few
+  // word-parallel operations before the sequential scan: most exceedance runs are short, and
+  // the scan cost is per transition of the slowest lane of the warp.  Runs touching bit 0 or
+  // bit 31 may continue in the neighbouring word and are kept as they are.
+  XMHW_HD uint32_t erase_short_runs(uint32_t b) const {
+    if (min_dur <= 1 || min_dur > 32) return b;
+    uint32_t open = b;                                   // bit i: b[i .. i + min_dur - 1] all ones
+    for (int rem = min_dur - 1, s = 1; rem > 0; s <<= 1) {
+      const int step = s < rem ? s : rem;
+      open &= open >> step;
+      rem -= step;
+    }
+    uint32_t lng = open;                                 // dilate back: all bits of runs >= min_dur
+    for (int rem = min_dur - 1, s = 1; rem > 0; s <<= 1) {
+      const int step = s < rem ? s : rem;
+      lng |= lng << step;
+      rem -= step;
+    }
+    const uint32_t low_run = b & ~(b + 1u);              // trailing ones (run through bit 0)
+    const uint32_t nb = ~b;
+    const uint32_t high_run = nb ? ~(0xffffffffu >> clz32(nb)) : 0xffffffffu;   // leading ones (run through bit 31)
+    return lng | low_run | (b & high_run);
+  }
+
   // bits: bit i = exceedance at time t0 + i (bits past the series end are 0)
   template <class Emit> XMHW_HD void feed(uint32_t bits, int t0, Emit& emit) {
     if (t0 == 0) bits &= ~1u;
+    bits = erase_short_runs(bits);
     int pos = 0;
     while (pos < 32) {
       uint32_t rem = bits >> pos;
