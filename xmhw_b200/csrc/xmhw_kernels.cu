@@ -714,7 +714,8 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
                                                                                scratch);                           \
   }
   if (plan->max_size <= 32) {
-    if (minb >= 24) XMHW_SWEEP(32, 24) else if (minb >= 20) XMHW_SWEEP(32, 20) else XMHW_SWEEP(32, 16)
+    if (minb >= 24) XMHW_SWEEP(32, 24) else if (minb >= 20) XMHW_SWEEP(32, 20) else if (minb >= 16) XMHW_SWEEP(32, 16)
+    else if (minb >= 14) XMHW_SWEEP(32, 14) else XMHW_SWEEP(32, 12)
   } else {
     XMHW_SWEEP(48, 10)
   }
