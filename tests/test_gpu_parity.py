@@ -159,6 +159,39 @@ def test_event_staging_overflow_falls_back_to_exact_fill(core, monkeypatch):
         assert np.array_equal(a[f], b[f], equal_nan=True), f
 
 
+def test_event_stats_layouts_and_two_pass_fill_agree(core):
+    """The exported doy-major statistics entry point and the two-pass count/fill give exactly
+    the table of the path core.detect_arrays uses (cell-major climatology copy, staged events)."""
+    from xmhw_b200 import synth, _cabi
+    from xmhw_b200.core import _call, _ptr, _stream, _doy_tables
+    time = synth.daily_time(1995, 2006)
+    doy = synth.doy366(time)
+    T, ngrid = len(time), 200
+    ts = torch.from_numpy(synth.synth_sst(T, ngrid, synth.season_table(time), nan_ppm=3000)).cuda()
+    th, se = core.threshold_arrays(ts, doy, 366)
+    ref = core.detect_arrays(ts, doy, 366, th, se)
+    st = _stream()
+    ptr, tidx, doy32 = _doy_tables(doy, 366, ts.device)
+    mask = torch.empty(((ngrid + 31) // 32, T), dtype=torch.int32, device="cuda")
+    nvalid = torch.zeros(ngrid, dtype=torch.int32, device="cuda")
+    _call("xmhw_exceed_mask_f32", _ptr(ts), T, ngrid, _ptr(ptr), _ptr(tidx), 366, _ptr(th), _ptr(mask), _ptr(nvalid), st)
+    counts = torch.empty(ngrid, dtype=torch.int32, device="cuda")
+    _call("xmhw_events_count", _ptr(mask), T, ngrid, 5, 1, 2, _ptr(counts), st)
+    offsets = torch.empty(ngrid + 1, dtype=torch.int64, device="cuda")
+    scratch = torch.empty(ngrid // 1024 + 2, dtype=torch.int64, device="cuda")
+    _call("xmhw_exclusive_scan_i32", _ptr(counts), ngrid, _ptr(offsets), _ptr(scratch), st)
+    nev = int(offsets[-1].item())
+    assert nev == ref.n and torch.equal(offsets, ref.offsets)
+    ei = torch.empty((_cabi.EI_COUNT, nev), dtype=torch.int32, device="cuda")
+    ef = torch.empty((_cabi.EF_COUNT, nev), dtype=torch.float64, device="cuda")
+    _call("xmhw_events_fill", _ptr(mask), T, ngrid, 5, 1, 2, _ptr(offsets), nev, _ptr(ei), st)
+    _call("xmhw_event_stats_f32", _ptr(ts), T, ngrid, _ptr(doy32), _ptr(th), _ptr(se), nev, nev, _ptr(ei), _ptr(ef), st)
+    torch.cuda.synchronize()
+    assert torch.equal(ei, ref.i32[:, :nev])
+    a, b = ef.cpu().numpy(), ref.f64[:, :nev].cpu().numpy()
+    assert np.array_equal(a.view(np.int64), b.view(np.int64))
+
+
 def test_reference_event_tables(core, ref_cases):
     """Event tables from the UNMODIFIED reference pandas code (tests/golden/ref_detect_cases.npz)."""
     from tests.util import F32_FIELDS
