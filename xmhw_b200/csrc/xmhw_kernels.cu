@@ -761,14 +761,19 @@ int xmhw_exceed_mask_f32(const float* ts, int64_t T, int64_t ngrid, const int32_
       ngrid > 0xffffffffll || T > 0x7fffffffll)
     return XMHW_E_ARG;
   const int64_t ncg = (ngrid + 31) / 32;
-  // enough warps to fill the machine: 148 SMs x 64 warps; split the doy axis on small grids
+  // doy chunks: enough warps to fill the machine (148 SMs x 64 warps x 2) on small grids, and never
+  // more than ~5 doys per warp -- measured on B200: 9.1 ms at 5 doys/chunk vs 10.6 ms at 120 (1440x720x30yr);
+  // consecutive blocks are the chunks of the same cell groups, so the resident blocks read the whole
+  // time extent of a narrow column band
+  const int by_doy = (ndoy + 4) / 5;
   int nchunk = (int)((148 * 64 * 2 + ncg - 1) / ncg);
-  if (nchunk < 1) nchunk = 1;
+  if (nchunk < by_doy) nchunk = by_doy;
   if (nchunk > ndoy) nchunk = ndoy;
   if (ngrid % 4 == 0 && ((uintptr_t)ts & 15) == 0) {
     const int64_t nsg = (ngrid + 127) / 128;
     int nc4 = (int)((148 * 64 * 2 + nsg - 1) / nsg);
-    nc4 = nc4 < 1 ? 1 : (nc4 > ndoy ? ndoy : nc4);
+    nc4 = nc4 < by_doy ? by_doy : nc4;
+    nc4 = nc4 > ndoy ? ndoy : nc4;
     const int64_t nb4 = ((nsg + EXC_WARPS - 1) / EXC_WARPS) * nc4;
     exceed4_kernel<<<(unsigned)nb4, EXC_WARPS * 32, 0, (cudaStream_t)stream>>>(
         ts, T, ngrid, doy_ptr, doy_tidx, ndoy, nc4, thresh, mask, nvalid);
