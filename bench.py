@@ -32,6 +32,9 @@ WORKLOADS = {
     "global025_30yr": (720, 1440, 1982, 2011, 0.33),     # BASELINE configs[2], the config the metric names
     "regional_40yr": (160, 240, 1982, 2021, 0.0),        # BASELINE configs[1]
     "global025_quarter": (180, 1440, 1982, 2011, 0.33),  # a quarter of the global grid (development timing)
+    # diagnostic: blocks of 64 cells share mean/amplitude/phase (spatially coherent climatology, as in
+    # real SST); NOT the headline -- it shows how much of the sweep is SIMT loss on independent cells
+    "global025_30yr_coherent": (720, 1440, 1982, 2011, 0.33),
     "small": (32, 64, 2001, 2010, 0.2),
 }
 METRIC = "cell-years/s, threshold+detect, global 0.25deg 30-yr SST"
@@ -158,7 +161,8 @@ def run_ours(args):
     nocean = ngrid - (int(land.sum()) if land is not None else 0)
     season = synth.season_table(tm)
     # every rank generates its own realisation of the grid (weak scaling), seeded by global cell id
-    ts = core.synth_sst_device(T, ngrid, season, land=land, cell0=rank * ngrid, device=dev)
+    ts = core.synth_sst_device(T, ngrid, season, land=land, cell0=rank * ngrid, device=dev,
+                               coherent=64 if args.workload.endswith("_coherent") else 1)
 
     def barrier():
         if world > 1:

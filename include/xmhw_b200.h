@@ -185,10 +185,12 @@ int xmhw_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src
 
 /* Deterministic synthetic SST: seasonal cycle + AR(1) noise rounded to
  * 0.01 degC, NaN on land; bit-identical to xmhw_b200/synth.py on the host.
- * season [T + 366] f64 host-computed sine table, land [ngrid] u8 (1 = land).    */
+ * season [T + 366] f64 host-computed sine table, land [ngrid] u8 (1 = land).
+ * coherent >= 1: blocks of that many consecutive cells share mean/amplitude/phase
+ * (1 = independent cells, the benchmark default; the noise is always per cell).   */
 int xmhw_synth_sst_f32(float* ts, int64_t T, int64_t ngrid, int64_t cell0, const uint8_t* land,
                        const double* season, uint64_t seed, double rho, double sigma,
-                       double noise_scale, uint32_t nan_per_million, void* stream);
+                       double noise_scale, uint32_t nan_per_million, uint32_t coherent, void* stream);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,9 @@ def test_synth_device_matches_host(core):
     host = synth.synth_sst(len(time), 96, sea, land=land, cell0=1000, nan_ppm=3000)
     dev = core.synth_sst_device(len(time), 96, sea, land=land, cell0=1000, nan_ppm=3000).cpu().numpy()
     assert np.array_equal(host.view(np.int32), dev.view(np.int32))
+    host = synth.synth_sst(len(time), 96, sea, cell0=1000, coherent=32)
+    dev = core.synth_sst_device(len(time), 96, sea, cell0=1000, coherent=32).cpu().numpy()
+    assert np.array_equal(host.view(np.int32), dev.view(np.int32))
 
 
 def test_oisst_cube_threshold_and_detect(core, oisst, clim_gold):

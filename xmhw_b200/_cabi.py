@@ -89,7 +89,7 @@ _SIGNATURES = {
                                     C.c_int32, C.c_void_p]),
     "xmhw_synth_sst_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_double,
-                                     C.c_uint32, C.c_void_p]),
+                                     C.c_uint32, C.c_uint32, C.c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

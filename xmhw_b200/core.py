@@ -268,7 +268,8 @@ def detect_arrays(ts, doy, ndoy, thresh, seas, minDuration=5, joinGaps=True, max
     return EventTable(ev_i32, ev_f64, nev, offsets, nvalid, T, ngrid)
 
 
-def synth_sst_device(T, ngrid, season, land=None, cell0=0, seed=None, nan_ppm=0, device="cuda", out=None):
+def synth_sst_device(T, ngrid, season, land=None, cell0=0, seed=None, nan_ppm=0, device="cuda", out=None,
+                     coherent=1):
     """Device twin of synth.synth_sst (bit-identical): float32 [T, ngrid] on `device`."""
     from . import synth
     dev = torch.device(device)
@@ -280,7 +281,7 @@ def synth_sst_device(T, ngrid, season, land=None, cell0=0, seed=None, nan_ppm=0,
         ld = None if land is None else torch.from_numpy(np.ascontiguousarray(land, np.uint8).ravel()).to(dev)
         _call("xmhw_synth_sst_f32", _ptr(ts), T, ngrid, int(cell0), 0 if ld is None else _ptr(ld), _ptr(sea),
                                      synth.SEED if seed is None else int(seed), synth.RHO, synth.SIGMA,
-                                     synth.NOISE_SCALE, int(nan_ppm), _stream())
+                                     synth.NOISE_SCALE, int(nan_ppm), int(coherent), _stream())
         torch.cuda.current_stream().synchronize()   # keep `sea`/`ld` alive until the kernel is done
     return ts
 

@@ -578,15 +578,19 @@ __device__ __forceinline__ double u01(uint64_t h) { return (double)(h >> 11) * (
 __global__ void synth_kernel(float* __restrict__ ts, int64_t T, int64_t ngrid, int64_t cell0,
                              const uint8_t* __restrict__ land, const double* __restrict__ season,
                              uint64_t seed, double rho, double sigma, double noise_scale,
-                             uint32_t nan_ppm) {
+                             uint32_t nan_ppm, uint32_t coherent) {
   const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= ngrid) return;
   const uint64_t gid = (uint64_t)(cell0 + cell);
   const bool is_land = land && land[cell];
   const uint64_t h0 = splitmix64(seed ^ (gid * 0xD1B54A32D192ED03ull));
-  const double m = 28.0 * u01(splitmix64(h0 + 1));
-  const double A = 1.0 + 5.0 * u01(splitmix64(h0 + 2));
-  const int phi = (int)(365.0 * u01(splitmix64(h0 + 3)));
+  // climatology parameters (mean, amplitude, phase) are shared by blocks of `coherent` consecutive
+  // cells (1 = every cell its own, the benchmark default); the AR(1) noise is always per cell
+  const uint64_t pgid = (gid / coherent) * coherent;
+  const uint64_t hp = splitmix64(seed ^ (pgid * 0xD1B54A32D192ED03ull));
+  const double m = 28.0 * u01(splitmix64(hp + 1));
+  const double A = 1.0 + 5.0 * u01(splitmix64(hp + 2));
+  const int phi = (int)(365.0 * u01(splitmix64(hp + 3)));
   double x = 0.0;
   for (int64_t t = 0; t < T; ++t) {
     const uint64_t r = splitmix64(h0 ^ ((uint64_t)t * 0x9E3779B97F4A7C15ull + 0x1234567ull));
@@ -904,11 +908,11 @@ int xmhw_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src
 
 int xmhw_synth_sst_f32(float* ts, int64_t T, int64_t ngrid, int64_t cell0, const uint8_t* land,
                        const double* season, uint64_t seed, double rho, double sigma, double noise_scale,
-                       uint32_t nan_per_million, void* stream) {
-  if (!ts || !season || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
+                       uint32_t nan_per_million, uint32_t coherent, void* stream) {
+  if (!ts || !season || T <= 0 || ngrid <= 0 || coherent < 1) return XMHW_E_ARG;
   const int nt = 128;
   synth_kernel<<<(unsigned)((ngrid + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
-      ts, T, ngrid, cell0, land, season, seed, rho, sigma, noise_scale, nan_per_million);
+      ts, T, ngrid, cell0, land, season, seed, rho, sigma, noise_scale, nan_per_million, coherent);
   return cuda_status();
 }
 

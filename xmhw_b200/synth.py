@@ -72,14 +72,17 @@ def land_mask(nlat, nlon, frac=0.33):
     return m
 
 
-def synth_sst(T, ngrid, season, land=None, cell0=0, seed=SEED, rho=RHO, sigma=SIGMA, nan_ppm=0):
-    """numpy twin of the CUDA generator: float32 [T, ngrid]."""
+def synth_sst(T, ngrid, season, land=None, cell0=0, seed=SEED, rho=RHO, sigma=SIGMA, nan_ppm=0, coherent=1):
+    """numpy twin of the CUDA generator: float32 [T, ngrid].  `coherent` consecutive cells share
+    mean / amplitude / phase (1 = independent cells, the benchmark default); noise is per cell."""
     gid = (np.arange(ngrid, dtype=np.uint64) + np.uint64(cell0))
     with np.errstate(over="ignore"):
         h0 = splitmix64(np.uint64(seed) ^ (gid * np.uint64(0xD1B54A32D192ED03)))
-        m = 28.0 * _u01(splitmix64(h0 + np.uint64(1)))
-        A = 1.0 + 5.0 * _u01(splitmix64(h0 + np.uint64(2)))
-        phi = (365.0 * _u01(splitmix64(h0 + np.uint64(3)))).astype(np.int64)
+        pgid = (gid // np.uint64(coherent)) * np.uint64(coherent)
+        hp = splitmix64(np.uint64(seed) ^ (pgid * np.uint64(0xD1B54A32D192ED03)))
+        m = 28.0 * _u01(splitmix64(hp + np.uint64(1)))
+        A = 1.0 + 5.0 * _u01(splitmix64(hp + np.uint64(2)))
+        phi = (365.0 * _u01(splitmix64(hp + np.uint64(3)))).astype(np.int64)
     out = np.empty((T, ngrid), np.float32)
     x = np.zeros(ngrid, np.float64)
     season = np.asarray(season, np.float64)
