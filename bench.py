@@ -241,11 +241,11 @@ def run_ours(args):
                "nvalid": torch.empty(ngrid, dtype=torch.int32, pin_memory=True),
                "ev_i32": torch.empty((core.EI_COUNT, cap), dtype=torch.int32, pin_memory=True),
                "ev_f64": torch.empty((core.EF_COUNT, cap), dtype=torch.float64, pin_memory=True)}
-        core.threshold_detect_host(host, doy, 366, device=dev, out=out)      # warm-up
+        core.threshold_detect_host(host, doy, 366, device=dev, out=out, slabs=args.slabs)      # warm-up
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            res = core.threshold_detect_host(host, doy, 366, device=dev, out=out)
+            res = core.threshold_detect_host(host, doy, 366, device=dev, out=out, slabs=args.slabs)
         barrier()
         dt = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
         if world > 1:
@@ -300,6 +300,7 @@ def main():
     ap.add_argument("--workload", default="global025_30yr", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-cells", type=int, default=400, help="cells per host process in the CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--slabs", type=int, default=8, help="column blocks of the host-buffer (e2e) pipeline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

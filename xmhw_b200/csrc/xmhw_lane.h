@@ -257,28 +257,25 @@ struct Sweeper {
 
   XMHW_HD uint32_t& at(int row) { return pool[row * 32 + lane]; }
 
-  // issue the loads of the next instance that has to be loaded, entry index >= from
-  XMHW_HD void prefetch(int from) {
+  // (offset into plan.rows, size) of the next instance that has to be loaded, entry index >= from;
+  // size 0 when there is none.  A chain of dependent plan loads: only used where the step record
+  // does not carry the answer (start of the sweep, steps with more than 4 entering lists).
+  XMHW_HD void next_load(int from, int& row_off, int& size) {
     int j = from;
+    row_off = 0; size = 0;
     while (j < total_enter && !(XMHW_LDG(p.enter + j) >> 30)) ++j;
     if (j >= total_enter) return;
     const int id = XMHW_LDG(p.enter + j) & 0x3fffffff;
-    prefetch_rows(XMHW_LDG(p.inst_row_off + id), XMHW_LDG(p.inst_size + id));
+    row_off = XMHW_LDG(p.inst_row_off + id);
+    size = XMHW_LDG(p.inst_size + id);
   }
 
-  // issue the loads of the list whose time rows are plan.rows[row_off .. row_off + size)
-  XMHW_HD void prefetch_rows(int row_off, int size) {
-    if (size <= 0) return;
-    prefetch_rows(env.vload(p.rows + row_off, size, lane), size);   // up to 64 entries
-  }
+  // issue the loads of the list whose time rows are the first `size` entries of rv
   XMHW_HD void prefetch_rows(const Vec& rv, int size) {
     // unconditional loads (entries past `size` read row 0 and are masked in consume), so the
     // compiler keeps all of them in flight instead of waiting on each predicated result
     const uint32_t ng32 = (uint32_t)ngrid;      // row offset as one 32x32->64 multiply (ngrid < 2^32)
-    if (size <= 8) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(uint32_t)env.vget(rv, i) * ng32);
-    } else if (MAXN == 32 || size <= 32) {
+    if (MAXN == 32 || size <= 32) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(uint32_t)env.vget(rv, i) * ng32);
     } else {
@@ -373,16 +370,16 @@ struct Sweeper {
     shi = scratch[sb + (SCR_SUM + 1) * 32];
   }
 
-  // next_off / next_size: the list to prefetch afterwards when known from the step record
-  // (next_size < 0: look it up in the plan arrays -- a chain of dependent loads)
-  XMHW_HD void enter_list(int e, int base, int size, int keep, int sbase, int entry_index, int next_off, int next_size) {
+  // returns true when the list was loaded (the prefetched rows are consumed: the caller issues the
+  // next prefetch -- at ONE site, the unrolled loads are the bulkiest code of the step after the sort)
+  XMHW_HD bool enter_list(int e, int base, int size, int keep, int sbase) {
     int len, ptr;
-    if (e >> 30) {
+    const bool loaded = (e >> 30) != 0;
+    if (loaded) {
       if (size <= 8) consume<8>(base, sbase, size, keep, len, ptr);
       else if (MAXN == 32 || size <= 32) consume<32>(base, sbase, size, keep, len, ptr);
       else if (size <= 40) consume<(MAXN > 32 ? 40 : 32)>(base, sbase, size, keep, len, ptr);
       else consume<(MAXN > 32 ? 48 : 32)>(base, sbase, size, keep, len, ptr);
-      if (next_size >= 0) prefetch_rows(next_off, next_size); else prefetch(entry_index + 1);
     } else {          // list re-enters after a hole (Feb 29): pointer against the current cut
       uint32_t meta = at(base + POOL_META);
       len = meta_len(meta);
@@ -398,6 +395,7 @@ struct Sweeper {
     }
     C += ptr;
     n += len;
+    return loaded;
   }
 
   XMHW_HD void init() {
@@ -407,7 +405,9 @@ struct Sweeper {
     rec_next = env.vload(p.step_rec, STEP_WORDS, lane);
     use_next = env.vload(p.use + XMHW_LDG(p.step_rec + STEP_USE_OFF),
                          (XMHW_LDG(p.step_rec + STEP_COUNTS) >> 16) & 0x7f, lane);
-    prefetch(0);
+    int off0, size0;
+    next_load(0, off0, size0);
+    if (size0 > 0) prefetch_rows(env.vload(p.rows + off0, size0, lane), size0);
   }
 
   // One pass over the lists in use: the two smallest keys above the cut (i1 <= i2, lists
@@ -482,11 +482,15 @@ struct Sweeper {
         next_off = env.vget(rec, (STEP_NEXT_LOAD + 2 * j) & 31);
         next_size = env.vget(rec, (STEP_NEXT_LOAD + 2 * j + 1) & 31);
       }
-      if (j == 0 && early_size >= 0 && (e >> 30)) {        // row indices already on their way
-        enter_list(e, base, size, keep, sbase, eoff + j, 0, 0);     // (0, 0): no prefetch inside
-        if (early_size > 0) prefetch_rows(early_rows, early_size);
-      } else {
-        enter_list(e, base, size, keep, sbase, eoff + j, next_off, next_size);
+      if (enter_list(e, base, size, keep, sbase)) {       // loaded: prefetch the next list to load
+        Vec rv = early_rows;
+        int rsize = early_size;
+        if (j != 0 || early_size < 0) {                   // not the one requested at the top of the step
+          if (next_size < 0) next_load(eoff + j + 1, next_off, next_size);
+          rsize = next_size;
+          if (rsize > 0) rv = env.vload(p.rows + next_off, rsize, lane);
+        }
+        if (rsize > 0) prefetch_rows(rv, rsize);
       }
     }
     // stage the base rows of the lists in use (padded to a multiple of 4 with the null list)
