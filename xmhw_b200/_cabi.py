@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_xmhw_b200.so")
+LIB_PATH = os.environ.get("XMHW_B200_LIB") or os.path.join(_HERE, "_xmhw_b200.so")   # env override: development builds
 
 EI_FIELDS = ("cell", "index_start", "index_end", "index_peak", "duration", "category",
              "duration_moderate", "duration_strong", "duration_severe", "duration_extreme")

@@ -198,18 +198,31 @@ template <> XMHW_HD void sort_desc<48>(uint32_t* k) { XMHW_SORTNET_48 }
 XMHW_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 XMHW_HD uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
-// Branch-free insertion of (key t, tag x) into the ascending 4-entry front (f0 <= f1 <= f2 <= f3)
-// that keeps the 4 smallest; ties keep the earlier entry first.  All 4 compares and the 7
+// Branch-free insertion of (key t, tag x) into the ascending F-entry front (f[0] <= ... <= f[F-1])
+// that keeps the F smallest; ties keep the earlier entry first.  All F compares and the 2F-1
 // min/max are independent of each other (depth 2), unlike a chain of conditional swaps.
-XMHW_HD void front_insert(uint32_t t, int x, uint32_t& f0, uint32_t& f1, uint32_t& f2, uint32_t& f3,
-                          int& g0, int& g1, int& g2, int& g3) {
-  const bool c0 = t < f0, c1 = t < f1, c2 = t < f2, c3 = t < f3;
-  const uint32_t n3 = umin32(f3, umax32(f2, t)), n2 = umin32(f2, umax32(f1, t)), n1 = umin32(f1, umax32(f0, t));
-  g3 = c2 ? g2 : (c3 ? x : g3);
-  g2 = c1 ? g1 : (c2 ? x : g2);
-  g1 = c0 ? g0 : (c1 ? x : g1);
-  g0 = c0 ? x : g0;
-  f0 = umin32(f0, t); f1 = n1; f2 = n2; f3 = n3;
+#ifndef XMHW_FRONT
+#define XMHW_FRONT 4
+#endif
+template <int F>
+XMHW_HD void front_insert(uint32_t t, int x, uint32_t (&f)[F], int (&g)[F]) {
+  bool c[F];
+#pragma unroll
+  for (int i = 0; i < F; ++i) c[i] = t < f[i];
+#pragma unroll
+  for (int i = F - 1; i >= 1; --i) {
+    g[i] = c[i - 1] ? g[i - 1] : (c[i] ? x : g[i]);
+    f[i] = umin32(f[i], umax32(f[i - 1], t));
+  }
+  g[0] = c[0] ? x : g[0];
+  f[0] = umin32(f[0], t);
+}
+// drop the head of the front
+template <int F>
+XMHW_HD void front_pop(uint32_t (&f)[F], int (&g)[F]) {
+#pragma unroll
+  for (int i = 0; i + 1 < F; ++i) { f[i] = f[i + 1]; g[i] = g[i + 1]; }
+  f[F - 1] = 0xffffffffu; g[F - 1] = 0;
 }
 
 // numpy _lerp (lib/_function_base_impl.py): d = b - a in float32, result in
@@ -529,18 +542,20 @@ struct Sweeper {
     while (env.any(d != 0)) {
       XMHW_STAT_SCAN();
       const bool drop = d >= 0;
-      uint32_t f0 = 0xffffffffu, f1 = 0xffffffffu, f2 = 0xffffffffu, f3 = 0xffffffffu;
-      int g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+      uint32_t f[XMHW_FRONT];
+      int g[XMHW_FRONT];
+#pragma unroll
+      for (int i = 0; i < XMHW_FRONT; ++i) { f[i] = 0xffffffffu; g[i] = 0; }
       const int crow = drop ? POOL_CINC : POOL_CEXC;
 #pragma unroll 4
       for (int j = 0; j < m4; ++j) {
         const int x = (int)ub[j];
         const uint32_t raw = at(x + crow);
         const uint32_t tk = drop ? raw : ~raw;
-        front_insert(tk, x, f0, f1, f2, f3, g0, g1, g2, g3);
+        front_insert<XMHW_FRONT>(tk, x, f, g);
       }
-      const uint32_t bound = f3;
-      int nf = 4;
+      const uint32_t bound = f[XMHW_FRONT - 1];
+      int nf = XMHW_FRONT;
       // direction constants of this lane (a walk never changes direction)
       const uint32_t flip = drop ? 0u : 0xffffffffu;
       const int sgn = drop ? -1 : 1, nroff = drop ? -2 : 1;
@@ -549,7 +564,9 @@ struct Sweeper {
       while (true) {
         const bool mv = d != 0 && nf > 0;
         if (!env.any(mv)) break;
-        // ---- apply the move of key f0 in list g0
+        // ---- apply the move of key f[0] in list g[0]
+        const int g0 = g[0];
+        const uint32_t f0 = f[0];
         const uint32_t meta = at(g0 + POOL_META);
         const int pa = meta_ptr(meta), la = meta_len(meta);
         const int nr = pa + nroff;                                   // rank of the list's next head
@@ -563,11 +580,10 @@ struct Sweeper {
           at(g0 + rowB) = ntk ^ flip;                                // next head, or the empty sentinel of that side
           C += sgn; d += sgn;
           // front: remove f0, insert the list's next head if it is certified (<= bound)
-          const int gm = g0;
-          f0 = f1; g0 = g1; f1 = f2; g1 = g2; f2 = f3; g2 = g3; f3 = 0xffffffffu; g3 = 0;
+          front_pop<XMHW_FRONT>(f, g);
           --nf;
           const bool cert = ntk <= bound && ntk != 0xffffffffu;
-          front_insert(cert ? ntk : 0xffffffffu, gm, f0, f1, f2, f3, g0, g1, g2, g3);   // ~0 never enters
+          front_insert<XMHW_FRONT>(cert ? ntk : 0xffffffffu, g0, f, g);   // ~0 never enters
           nf += cert;
         }
       }
