@@ -703,7 +703,9 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
   if (plan->scratch_rows < 0 || (plan->scratch_rows > 0 && !scratch)) return XMHW_E_ARG;
   if (ngrid > 0xffffffffll || T > 0x7fffffffll) return XMHW_E_ARG;
   if (plan->nsteps <= 0 || plan->pool_rows <= 0 || plan->max_size > 48 || plan->nmax <= 0) return XMHW_E_PLAN;
-  const size_t smem = (size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 128;
+  size_t smem = (size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 128;
+  static const int smem_pad = getenv("XMHW_B200_SWEEP_SMEM_PAD") ? atoi(getenv("XMHW_B200_SWEEP_SMEM_PAD")) : 0;
+  smem += (size_t)smem_pad;       // development knob: lowers the resident warps per SM without touching the code
   if (smem > 227 * 1024) return XMHW_E_SMEM;
   ClimPlan p;
   memcpy(&p, plan, sizeof(p));
