@@ -225,6 +225,41 @@ XMHW_HD void front_pop(uint32_t (&f)[F], int (&g)[F]) {
   f[F - 1] = 0xffffffffu; g[F - 1] = 0;
 }
 
+// Position of `pivot` in a descending sorted register array: ptr = #{k[i] > pivot},
+// cinc = k[ptr-1] (0xffffffff when ptr == 0), cexc = k[ptr] (0 when ptr == N).  For a power-of-two
+// N a branch-free halving search that carries the window e[base-1 .. base+L] through selects
+// (log2 N compares + ~N+10 selects) replaces N compares, N counts and 2N selects.
+template <int N>
+XMHW_HD void partition_sorted(const uint32_t (&k)[N], uint32_t pivot, int& ptr, uint32_t& cinc, uint32_t& cexc) {
+  if ((N & (N - 1)) == 0) {
+    uint32_t V[N + 2];
+    V[0] = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < N; ++i) V[i + 1] = k[i];
+    V[N + 1] = 0u;
+    int base = 0;
+#pragma unroll
+    for (int h = N / 2; h >= 1; h >>= 1) {        // window V[0 .. 2h+1] = e[base-1 .. base+2h]
+      const bool t = V[h] > pivot;                // k[base + h - 1] > pivot: at least h more keys above
+      base += t ? h : 0;
+#pragma unroll
+      for (int i = 0; i <= h + 1; ++i) V[i] = t ? V[h + i] : V[i];
+    }
+    const bool t = V[1] > pivot;                  // V = {k[base-1], k[base], k[base+1]}
+    ptr = base + (t ? 1 : 0);
+    cinc = t ? V[1] : V[0];
+    cexc = t ? V[2] : V[1];
+  } else {
+    ptr = 0; cinc = 0xffffffffu; cexc = 0u;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const bool ab = k[i] > pivot;
+      ptr += ab;
+      if (ab) cinc = k[i]; else cexc = cexc > k[i] ? cexc : k[i];
+    }
+  }
+}
+
 // numpy _lerp (lib/_function_base_impl.py): d = b - a in float32, result in
 // float64 with two roundings, no FMA (the .cu is compiled with --fmad=false).
 XMHW_HD double lerp_q(float a, float b, double g) {
@@ -359,10 +394,8 @@ struct Sweeper {
       for (int i = 0; i < N; ++i) {
         if (i < keep) srow[i * 32] = k[i];                  // top `keep` keys: shared memory
         if (i >= keep && i < size) grow[i * 32] = k[i];     // sorted remainder: global scratch
-        const bool ab = k[i] > pivot;
-        ptr += ab;
-        if (ab) cinc = k[i]; else cexc = cexc > k[i] ? cexc : k[i];
       }
+      partition_sorted<N>(k, pivot, ptr, cinc, cexc);
     }
     scratch[(size_t)(sbase + SCR_SUM) * 32 + lane] = f64_lo(sum);
     scratch[(size_t)(sbase + SCR_SUM + 1) * 32 + lane] = f64_hi(sum);
