@@ -217,12 +217,26 @@ XMHW_HD void front_insert(uint32_t t, int x, uint32_t (&f)[F], int (&g)[F]) {
   g[0] = c[0] ? x : g[0];
   f[0] = umin32(f[0], t);
 }
-// drop the head of the front
+// Drop the head of the front and insert (t, x) in one step (t = 0xffffffff: nothing enters, the
+// last slot becomes empty): F-1 compares, 2F-2 min/max, 2F-1 selects instead of a shift + insert.
 template <int F>
-XMHW_HD void front_pop(uint32_t (&f)[F], int (&g)[F]) {
+XMHW_HD void front_replace_head(uint32_t t, int x, uint32_t (&f)[F], int (&g)[F]) {
+  bool c[F];
 #pragma unroll
-  for (int i = 0; i + 1 < F; ++i) { f[i] = f[i + 1]; g[i] = g[i + 1]; }
-  f[F - 1] = 0xffffffffu; g[F - 1] = 0;
+  for (int i = 1; i < F; ++i) c[i] = t < f[i];
+  uint32_t nf[F];
+  int ng[F];
+  nf[0] = umin32(f[1], t);
+  ng[0] = c[1] ? x : g[1];
+#pragma unroll
+  for (int i = 1; i + 1 < F; ++i) {
+    nf[i] = umin32(f[i + 1], umax32(f[i], t));
+    ng[i] = c[i] ? g[i] : (c[i + 1] ? x : g[i + 1]);
+  }
+  nf[F - 1] = umax32(f[F - 1], t);
+  ng[F - 1] = c[F - 1] ? g[F - 1] : x;
+#pragma unroll
+  for (int i = 0; i < F; ++i) { f[i] = nf[i]; g[i] = ng[i]; }
 }
 
 // Position of `pivot` in a descending sorted register array: ptr = #{k[i] > pivot},
@@ -575,24 +589,22 @@ struct Sweeper {
     while (env.any(d != 0)) {
       XMHW_STAT_SCAN();
       const bool drop = d >= 0;
+      // direction constants of this lane (a walk never changes direction): transformed key = key ^ flip,
+      // rowB = the cached head on the side being consumed (scanned here), rowA = the other side
+      const uint32_t flip = drop ? 0u : 0xffffffffu;
+      const int sgn = drop ? -1 : 1, nroff = drop ? -2 : 1;
+      const int rowA = drop ? POOL_CEXC : POOL_CINC, rowB = drop ? POOL_CINC : POOL_CEXC;
       uint32_t f[XMHW_FRONT];
       int g[XMHW_FRONT];
 #pragma unroll
       for (int i = 0; i < XMHW_FRONT; ++i) { f[i] = 0xffffffffu; g[i] = 0; }
-      const int crow = drop ? POOL_CINC : POOL_CEXC;
 #pragma unroll 4
       for (int j = 0; j < m4; ++j) {
         const int x = (int)ub[j];
-        const uint32_t raw = at(x + crow);
-        const uint32_t tk = drop ? raw : ~raw;
-        front_insert<XMHW_FRONT>(tk, x, f, g);
+        front_insert<XMHW_FRONT>(at(x + rowB) ^ flip, x, f, g);
       }
       const uint32_t bound = f[XMHW_FRONT - 1];
       int nf = XMHW_FRONT;
-      // direction constants of this lane (a walk never changes direction)
-      const uint32_t flip = drop ? 0u : 0xffffffffu;
-      const int sgn = drop ? -1 : 1, nroff = drop ? -2 : 1;
-      const int rowA = drop ? POOL_CEXC : POOL_CINC, rowB = drop ? POOL_CINC : POOL_CEXC;
       // pop until every lane is on target or some lane has used up its certified front
       while (true) {
         const bool mv = d != 0 && nf > 0;
@@ -613,11 +625,9 @@ struct Sweeper {
           at(g0 + rowB) = ntk ^ flip;                                // next head, or the empty sentinel of that side
           C += sgn; d += sgn;
           // front: remove f0, insert the list's next head if it is certified (<= bound)
-          front_pop<XMHW_FRONT>(f, g);
-          --nf;
           const bool cert = ntk <= bound && ntk != 0xffffffffu;
-          front_insert<XMHW_FRONT>(cert ? ntk : 0xffffffffu, g0, f, g);   // ~0 never enters
-          nf += cert;
+          front_replace_head<XMHW_FRONT>(cert ? ntk : 0xffffffffu, g0, f, g);   // ~0 never enters
+          nf += cert ? 0 : -1;
         }
       }
     }
