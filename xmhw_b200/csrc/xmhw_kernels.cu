@@ -417,10 +417,15 @@ __global__ void __launch_bounds__(EVT_WARPS * 32) events_stage_kernel(
   se.n = 0; se.cap = ok ? cap : 0;
   se.s_row = stage + (size_t)cg * 2 * cap * 32 + lane;
   se.e_row = se.s_row + (size_t)cap * 32;
-  for (int64_t t0 = 0; t0 < T; t0 += 32) {
-    uint32_t x = (t0 + lane < T) ? __ldg(mrow + t0 + lane) : 0u;
-    uint32_t bits = transpose32(x, lane);
-    rf.feed(bits, (int)t0, se);
+  // 4 mask words in flight: the run scan of one word is a data-dependent loop the compiler cannot
+  // hoist the next load across, and a warp's words are consumed strictly in order
+  for (int64_t t0 = 0; t0 < T; t0 += 128) {
+    uint32_t x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = (t0 + 32 * u + lane < T) ? __ldg(mrow + t0 + 32 * u + lane) : 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (t0 + 32 * u < T) rf.feed(transpose32(x[u], lane), (int)(t0 + 32 * u), se);
   }
   rf.finish((int)T, se);
   if (ok) {
