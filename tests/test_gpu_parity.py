@@ -279,6 +279,67 @@ def test_regional_properties(core):
     assert_events_match(sub, exp, _float_fields())
 
 
+def test_global_config3_properties(core):
+    """BASELINE config 3 at FULL size (1440x720 grid, 1982-2011, T=10957, 45.4 GB, 33 % land: the
+    bench workload): size-independent properties on the device + oracle spot check on sampled cells."""
+    from xmhw_b200 import synth
+    if torch.cuda.get_device_properties(0).total_memory < 120e9:
+        pytest.skip("needs ~90 GB of device memory")
+    O = _oracle()
+    time = synth.daily_time(1982, 2011)
+    doy = synth.doy366(time)
+    nlat, nlon = 720, 1440
+    T, ngrid = len(time), nlat * nlon
+    land = synth.land_mask(nlat, nlon, 0.33).ravel()
+    ts = core.synth_sst_device(T, ngrid, synth.season_table(time), land=land)
+    th, se = core.threshold_arrays(ts, doy, 366)
+    ev = core.detect_arrays(ts, doy, 366, th, se)
+    torch.cuda.synchronize()
+    land_d = torch.from_numpy(land.astype(bool)).cuda()
+    # land cells: NaN climatology, no valid sample, no event; ocean cells: finite, thresh above the mean
+    assert bool(torch.isnan(th[:, land_d]).all()) and bool(torch.isnan(se[:, land_d]).all())
+    assert not bool(torch.isnan(th[:, ~land_d]).any()) and bool((th[:, ~land_d] > se[:, ~land_d]).all())
+    assert bool((ev.nvalid[land_d] == 0).all()) and bool((ev.nvalid[~land_d] == T).all())
+    n = ev.n
+    nocean = int((~land_d).sum())
+    assert 1.5 < n / (nocean * 30) < 3.5                # ~2.2 events per ocean cell-year
+    col = {f: ev.column(f) for f in ("cell", "index_start", "index_end", "index_peak", "duration", "category",
+                                     "duration_moderate", "duration_strong", "duration_severe", "duration_extreme")}
+    assert bool((col["duration"] == col["index_end"] - col["index_start"] + 1).all())
+    assert bool((col["duration"] >= 5).all()) and bool((col["index_start"] >= 1).all()) and bool((col["index_end"] < T).all())
+    assert bool(((col["index_peak"] >= col["index_start"]) & (col["index_peak"] <= col["index_end"])).all())
+    assert bool((col["cell"][1:] >= col["cell"][:-1]).all())
+    same = col["cell"][1:] == col["cell"][:-1]
+    assert bool(((col["index_start"][1:] - col["index_end"][:-1] - 1)[same] > 2).all())     # gaps > maxGap after joining
+    assert bool((col["duration_moderate"] + col["duration_strong"] + col["duration_severe"]
+                 + col["duration_extreme"] <= col["duration"]).all())
+    assert bool((col["category"] >= 1).all()) and bool((col["category"] <= 4).all())
+    assert bool((ev.column("intensity_max") > 0).all())
+    assert not bool(land_d[col["cell"].long()].any())                                       # no event on land
+    counts = torch.bincount(col["cell"].long(), minlength=ngrid)
+    assert torch.equal(counts, ev.offsets[1:] - ev.offsets[:-1])
+    # oracle spot check: 20 ocean + 4 land cells spread over the grid
+    rng = np.random.default_rng(3)
+    cells = np.sort(np.concatenate([rng.choice(np.flatnonzero(land == 0), 20, replace=False),
+                                    rng.choice(np.flatnonzero(land == 1), 4, replace=False)]))
+    idx = torch.from_numpy(cells).cuda()
+    ts_h = ts[:, idx].cpu().numpy()
+    th_h, se_h = th[:, idx].cpu().numpy(), se[:, idx].cpu().numpy()
+    oth, ose = O.threshold(ts_h, doy, 366)
+    assert bit_equal(th_h, oth)
+    assert np.nanmax(np.abs(se_h - ose)) <= 1e-9 and np.array_equal(np.isnan(se_h), np.isnan(ose))
+    exp = O.detect(ts_h, doy, th_h, se_h)
+    sel = torch.isin(col["cell"].long(), idx)
+    keep = sel.nonzero().squeeze(1)
+    from xmhw_b200.core import EI_FIELDS, EF_FIELDS
+    got = {f: ev.i32[k, :n][keep].cpu().numpy().astype(np.int64) for k, f in enumerate(EI_FIELDS)}
+    got.update({f: ev.f64[k, :n][keep].cpu().numpy() for k, f in enumerate(EF_FIELDS)})
+    got["cell"] = np.searchsorted(cells, got["cell"])
+    assert_events_match(got, exp, _float_fields())
+    del ts, th, se, ev
+    torch.cuda.empty_cache()
+
+
 def test_series_without_leap_year(core):
     """doy 60 never occurs (2001-2003): absent from the reference's groupby output, so feb29 /
     runavg act on the compacted 365-doy axis and doy 60 comes back NaN."""
