@@ -298,7 +298,7 @@ def main():
     ap.add_argument("--workload", default="global025_30yr", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-cells", type=int, default=400, help="cells per host process in the CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--slabs", type=int, default=8, help="column blocks of the host-buffer (e2e) pipeline")
+    ap.add_argument("--slabs", type=int, default=24, help="column blocks of the host-buffer (e2e) pipeline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
