@@ -68,6 +68,25 @@ void emul_event_stats(const float* col, const double* th, const double* se, cons
   event_stats(col, th, se, doy, ngrid, T, s, e, oi, of, 1);
 }
 
+// placement of a pivot in a descending sorted key array (halving search through selects)
+void emul_partition_sorted(const uint32_t* k, int n, uint32_t pivot, int32_t* out) {
+  int ptr = -1; uint32_t cinc = 0, cexc = 0;
+  if (n == 8) { uint32_t a[8]; for (int i = 0; i < 8; ++i) a[i] = k[i]; partition_sorted<8>(a, pivot, ptr, cinc, cexc); }
+  else if (n == 32) { uint32_t a[32]; for (int i = 0; i < 32; ++i) a[i] = k[i]; partition_sorted<32>(a, pivot, ptr, cinc, cexc); }
+  else if (n == 40) { uint32_t a[40]; for (int i = 0; i < 40; ++i) a[i] = k[i]; partition_sorted<40>(a, pivot, ptr, cinc, cexc); }
+  out[0] = ptr; out[1] = (int32_t)cinc; out[2] = (int32_t)cexc;
+}
+
+// the 4-entry front: insert a stream of (key, tag), then replace the head `nrep` times
+void emul_front(const uint32_t* keys, const int32_t* tags, int n, const uint32_t* rkeys, const int32_t* rtags, int nrep,
+                uint32_t* f_out, int32_t* g_out) {
+  uint32_t f[4]; int g[4];
+  for (int i = 0; i < 4; ++i) { f[i] = 0xffffffffu; g[i] = 0; }
+  for (int i = 0; i < n; ++i) front_insert<4>(keys[i], tags[i], f, g);
+  for (int i = 0; i < nrep; ++i) front_replace_head<4>(rkeys[i], rtags[i], f, g);
+  for (int i = 0; i < 4; ++i) { f_out[i] = f[i]; g_out[i] = g[i]; }
+}
+
 uint32_t emul_f32_key(float f) { return f32_key(f); }
 float emul_key_f32(uint32_t k) { return key_f32(k); }
 }

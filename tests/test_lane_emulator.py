@@ -113,6 +113,47 @@ def test_plan_rejects_unsupported():
     assert ptr.tolist() == [0, 2, 4, 5] and tidx.tolist() == [1, 4, 0, 2, 3]
 
 
+def test_partition_sorted_and_front_helpers(em):
+    """The branch-free building blocks of the sweep walk against plain numpy: placement of the cut
+    in a sorted list (halving search through selects) and the sorted 4-entry front."""
+    lib, _ = em
+    rng = np.random.default_rng(11)
+    out = np.zeros(3, np.int32)
+    for trial in range(600):
+        n = (8, 32, 40)[trial % 3]
+        nvalid = int(rng.integers(0, n + 1))
+        k = np.zeros(n, np.uint32)
+        k[:nvalid] = np.sort(rng.integers(1, 50 if trial % 2 else 2 ** 32 - 1, nvalid, dtype=np.uint64))[::-1]
+        piv = np.uint32(rng.choice([0, 0xffffffff, int(rng.integers(0, 2 ** 32 - 1)), int(k[rng.integers(0, n)])]))
+        lib.emul_partition_sorted(_vp(k), n, C.c_uint32(int(piv)), _vp(out))
+        ptr = int((k > piv).sum())
+        assert out[0] == ptr
+        assert np.uint32(out[1]) == (k[ptr - 1] if ptr > 0 else np.uint32(0xffffffff))
+        assert np.uint32(out[2]) == (k[ptr] if ptr < n else np.uint32(0))
+    f = np.zeros(4, np.uint32)
+    g = np.zeros(4, np.int32)
+    for trial in range(400):
+        n = int(rng.integers(0, 14))
+        keys = rng.integers(0, 40 if trial % 2 else 2 ** 32 - 2, n, dtype=np.uint64).astype(np.uint32)
+        tags = np.arange(1, n + 1, dtype=np.int32)
+        nrep = int(rng.integers(0, 6))
+        rkeys = rng.integers(0, 60, nrep, dtype=np.uint64).astype(np.uint32)
+        rkeys[rng.random(nrep) < 0.4] = 0xffffffff                      # "nothing enters"
+        rtags = np.arange(100, 100 + nrep, dtype=np.int32)
+        lib.emul_front(_vp(keys), _vp(tags), n, _vp(rkeys), _vp(rtags), nrep, _vp(f), _vp(g))
+        # reference: stable sort by key (earlier entries first among ties), keep 4; replace = drop head, insert
+        ref = sorted(zip(keys.tolist(), tags.tolist()), key=lambda kv: kv[0])[:4]
+        for rk, rt in zip(rkeys.tolist(), rtags.tolist()):
+            ref = ref[1:]
+            if rk != 0xffffffff:
+                pos = sum(1 for kv in ref if kv[0] <= rk)
+                ref.insert(pos, (rk, rt))
+            ref = ref[:4]
+        for i, (kk, tt) in enumerate(ref):
+            assert f[i] == kk and g[i] == tt, (trial, i)
+        assert np.all(f[len(ref):] == 0xffffffff)
+
+
 def test_run_finder_fuzz(em):
     lib, _ = em
     rng = np.random.default_rng(5)

@@ -42,6 +42,22 @@ def test_runavg():
         O.runavg(a, 2)
 
 
+def test_runavg_block_order_is_a_plain_circular_mean():
+    """The oracle fixes a block suffix/prefix summation order (shared with the CUDA kernel); it must
+    agree with the direct window mean to rounding, for any width, wrap-around and NaN placement."""
+    rng = np.random.default_rng(7)
+    for nd, w in ((366, 31), (366, 5), (73, 5), (12, 3), (40, 39), (7, 1), (366, 61)):
+        x = rng.normal(15.0, 5.0, (nd, 9))
+        x[rng.integers(0, nd), 3] = np.nan
+        got = O.runavg(x, w)
+        h = (w - 1) // 2
+        idx = (np.arange(nd)[:, None] + np.arange(-h, h + 1)[None, :]) % nd
+        ref = x[idx].mean(axis=1)
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert np.abs(got[ok] - ref[ok]).max() < 1e-13 * 20
+
+
 def test_window_roll_order(oisst):
     # test_identify.py:80-87 + fixture tstack (xmhw_fixtures.py:96-98): z order is window-major
     ts = oisst["sst"][:3, 1, 2]
