@@ -76,3 +76,39 @@ def test_flip_cold():
     assert np.array_equal(out["intensity_sum_dummy"], -y, equal_nan=True)
     assert np.array_equal(out["intensity_var_dummy"], y, equal_nan=True)
     assert np.array_equal(out["dummy"], y, equal_nan=True)
+
+
+def test_save_and_load_dataset_roundtrip(tmp_path):
+    """xmhw_b200.io: what threshold()/detect() return goes to a NetCDF-3 file and back."""
+    from xmhw_b200 import io, labeled
+    rng = np.random.default_rng(0)
+    doy = np.arange(1, 367)
+    lat, lon = np.array([-42.5, -42.25]), np.array([148.0, 148.25, 148.5])
+    ds = labeled.Dataset(coords={"doy": doy, "lat": lat, "lon": lon, "quantile": np.float64(0.9)},
+                         attrs={"xmhw_parameters": "pctile: 90; windowHalfWidth: 5", "smooth": True})
+    ds["thresh"] = labeled.DataArray(rng.normal(18, 2, (366, 2, 3)), ("doy", "lat", "lon"), attrs={"units": "degree_C"})
+    ds["seas"] = labeled.DataArray(rng.normal(16, 2, (366, 2, 3)), ("doy", "lat", "lon"))
+    p = tmp_path / "clim.nc"
+    io.save_dataset(ds, str(p))
+    back = io.load_dataset(str(p))
+    assert np.array_equal(back["thresh"].values, ds["thresh"].values) and back["thresh"].dims == ("doy", "lat", "lon")
+    assert np.array_equal(back.coords["doy"], doy) and np.array_equal(back.coords["lat"], lat)
+    assert back["thresh"].attrs["units"] == "degree_C" and back.attrs["coord_quantile"] == 0.9
+    # compact event table: int64 indices, datetime64 times, float32 statistics
+    ev = labeled.Dataset(coords={"event": np.arange(5)})
+    ev["cell"] = labeled.DataArray(np.array([0, 0, 3, 3, 5], np.int64), ("event",))
+    ev["index_start"] = labeled.DataArray(np.array([1, 75, 11, 52, 613], np.int64), ("event",))
+    ev["time_start"] = labeled.DataArray(np.array(["2003-01-02", "2003-03-17", "2003-01-12", "2003-02-22", "NaT"],
+                                                  "datetime64[D]"), ("event",))
+    ev["intensity_max"] = labeled.DataArray(rng.normal(2, 0.5, 5), ("event",))
+    p2 = tmp_path / "events.nc"
+    io.save_dataset(ev, str(p2), float32=True)
+    b2 = io.load_dataset(str(p2))
+    assert b2["cell"].values.dtype == np.int32 and np.array_equal(b2["index_start"].values, ev["index_start"].values)
+    assert b2["intensity_max"].values.dtype == np.float32
+    t = b2["time_start"].values
+    assert t[0] == 12054.0 and np.isnan(t[4]) and b2["time_start"].attrs["units"].startswith("days since 1970")
+    with pytest.raises(TypeError):
+        bad = labeled.Dataset()
+        bad["s"] = labeled.DataArray(np.array(["a", "b"]), ("x",))
+        io.save_dataset(bad, str(tmp_path / "bad.nc"))
