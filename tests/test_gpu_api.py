@@ -47,6 +47,17 @@ def test_oisst_end_to_end(api, oisst, clim_gold):
     assert len(comp["event"].values) == len(exp["cell"])
     np.testing.assert_allclose(np.sort(comp["intensity_cumulative"].values), np.sort(exp["intensity_cumulative"]),
                                rtol=1e-9)
+    # the returned Datasets go to NetCDF-3 files and back (xmhw_b200/io.py)
+    import os
+    import tempfile
+    from xmhw_b200 import io
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, ds in (("clim", clim), ("events", comp), ("dense", mhw)):
+            io.save_dataset(ds, os.path.join(tmp, name + ".nc"))
+        back = io.load_dataset(os.path.join(tmp, "events.nc"))
+        assert np.array_equal(back["index_start"].values, comp["index_start"].values)
+        assert np.array_equal(back["intensity_max"].values, comp["intensity_max"].values)
+        assert np.array_equal(io.load_dataset(os.path.join(tmp, "clim.nc"))["thresh"].values, th.values, equal_nan=True)
 
 
 def test_point_series_and_cold_spells(api, oisst):
