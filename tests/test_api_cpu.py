@@ -112,3 +112,25 @@ def test_save_and_load_dataset_roundtrip(tmp_path):
         bad = labeled.Dataset()
         bad["s"] = labeled.DataArray(np.array(["a", "b"]), ("x",))
         io.save_dataset(bad, str(tmp_path / "bad.nc"))
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU stand-in for the reference, needs no GPU): exactly one
+    JSON line on stdout with the contract keys, whatever libraries write to file descriptor 1."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-cells", "4", "--workload", "small"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "cell-years/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"] == "small"
