@@ -38,7 +38,7 @@ extern "C" {
 #define XMHW_E_PLAN  (-2)   /* inconsistent climatology plan               */
 #define XMHW_E_SMEM  (-3)   /* plan needs more shared memory than one SM has */
 
-#define XMHW_ABI_VERSION 1
+#define XMHW_ABI_VERSION 2
 
 /* event table columns (struct-of-arrays, column c of event i at [c * cap + i]) */
 enum xmhw_event_i32 {
@@ -90,26 +90,63 @@ typedef struct xmhw_clim_plan {
   double q;                     /* quantile in [0,1] (numpy 'linear': (n-1) q)   */
 } xmhw_clim_plan;
 
+/* Plan of the two-stack top-K climatology sweep (xmhw_b200/plan2.py, csrc/xmhw_topk.h): the time
+ * rows ordered into atoms (rows that enter and leave the doy windows together) such that every
+ * doy's window is a contiguous range of atoms; per doy a fixed-size step record says which unit
+ * slots leave, which atoms enter and where the front array of the query lives.  All arrays are
+ * device-resident int32.                                                                     */
+typedef struct xmhw_clim_plan2 {
+  int32_t nsteps;               /* sweep steps (doys computed by the sweep)        */
+  int32_t kp;                   /* top-K capacity: 8, 16, 24, 36 or 48             */
+  int32_t max_size;             /* rows of the largest atom, <= 48                 */
+  int32_t slot_rows;            /* shared-memory rows (128 B) per unit slot        */
+  int32_t nslots;               /* unit slots per 32-cell warp, <= 32              */
+  int32_t n_init;               /* atoms pushed before the first step              */
+  int32_t pool_rows;            /* nslots * slot_rows                              */
+  int32_t reserved_;
+  const int32_t* rows;          /* time indices of all atoms, push order           */
+  const int32_t* atoms;         /* [natoms + 1][4] atom records (zero record last) */
+  const int32_t* step_rec;      /* [nsteps][32] step records                       */
+  const int32_t* flip;          /* flip entries, 2 words each                      */
+  double q;                     /* quantile in [0,1] (numpy 'linear': (n-1) q)     */
+} xmhw_clim_plan2;
+
 int xmhw_abi_version(void);
 const char* xmhw_strerror(int code);
 
 /* identify.py:184-270 window_roll + calculate_thresh + calculate_seas (before the
- * Feb-29 rule and smoothing) for every grid cell.
- * ts [T][ngrid] f32 -> thresh_raw, seas_raw [nsteps][ngrid] f64 (NaN = no sample).
+ * Feb-29 rule and smoothing) for every grid cell: the general sorted-list sweep (any calendar,
+ * any quantile).  ts [T][ngrid] f32 -> thresh_raw, seas_raw [nsteps][ngrid] f64 (NaN = no
+ * sample), nempty [ngrid] i32 = number of doys without any sample.
  * scratch: caller-owned workspace of ceil(ngrid/32) * plan->scratch_rows * 128 bytes
  * (sorted list tails; stays L2-resident while a warp needs it).                       */
 int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan* plan,
-                        double* thresh_raw, double* seas_raw, uint32_t* scratch, void* stream);
+                        double* thresh_raw, double* seas_raw, int32_t* nempty, uint32_t* scratch, void* stream);
 
-/* identify.py:137-151 feb29 (if feb29 != 0: doy 60 <- mean of doys 59,60,61) then
+/* Same reference lines (identify.py:184-270) by the two-stack top-K sweep: every doy is the same
+ * straight-line sorting / merging network code for all cells (no data-dependent walk).  Writes
+ * the rows of thresh_raw / seas_raw [ndoy][ngrid] named by the plan's step records and
+ * nempty [ngrid] i32 = number of those doys without any sample.
+ * scratch: ceil(ngrid/32) * plan->nslots * 256 bytes (f64 sums of the unit slots).
+ * The few doys the plan excludes (doy 60 of the 366-day calendar: its window holds leap years
+ * only) are computed by xmhw_clim_direct_f32 from their row list: rows [nrows] i32 time indices,
+ * thresh_row / seas_row = that doy's row of the raw arrays, nempty += 1 where it has no sample. */
+int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan2* plan,
+                         double* thresh_raw, double* seas_raw, int32_t* nempty, uint32_t* scratch, void* stream);
+int xmhw_clim_direct_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* rows, int32_t nrows, int32_t kp,
+                         double q, double* thresh_row, double* seas_row, int32_t* nempty, void* stream);
+
+/* identify.py:137-151 feb29 (if feb29 != 0: doy 60 <- mean of the doys 59,60,61 present) then
  * identify.py:154-181 runavg (circular centred mean, odd smooth_width; <= 1 = off).
- * raw, out [ndoy][ngrid] f64, out must not alias raw.                           */
+ * raw, out [ndoy][ngrid] f64, out must not alias raw.  nempty [ngrid] (from the sweep): a cell
+ * in which some doys have no sample is smoothed over its own compacted doy axis, as the
+ * reference's groupby output lacks those doys (identify.py:175-180, :233-241); they stay NaN. */
 int xmhw_clim_finish_f64(const double* raw, double* out, int32_t ndoy, int64_t ngrid,
-                         int32_t feb29, int32_t smooth_width, void* stream);
+                         int32_t feb29, int32_t smooth_width, const int32_t* nempty, void* stream);
 /* same for thresh and seas in one call (one fused launch for the default width 31) */
 int xmhw_clim_finish2_f64(const double* thresh_raw, double* thresh_out, const double* seas_raw,
                           double* seas_out, int32_t ndoy, int64_t ngrid, int32_t feb29,
-                          int32_t smooth_width, void* stream);
+                          int32_t smooth_width, const int32_t* nempty, void* stream);
 
 /* identify.py:367-372: bthresh = ts > thresh[doy] (strict, float64 compare, NaN -> false).
  * doy_ptr [ndoy+1], doy_tidx [T]: CSR of time indices per doy label.

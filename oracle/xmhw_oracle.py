@@ -244,19 +244,34 @@ def threshold(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercentile=True
         x = ts[idx]
         thresh[d - 1] = quantile_linear(x, q)
         seas[d - 1] = seasonal_mean(x)
-    # a doy that never occurs in the series is absent from the reference's groupby output:
-    # feb29 / runavg act on the compacted doy axis (identify.py:233-241, :175-180)
-    present = np.isin(np.arange(1, ndoy + 1), np.unique(doy))
-    t_c, s_c = thresh[present], seas[present]
-    if not tstep and ndoy >= 61 and present[58:61].all():
-        i60 = int(np.sum(present[:59]))
-        sub = np.stack([t_c[i60 - 1], t_c[i60], t_c[i60 + 1]]), np.stack([s_c[i60 - 1], s_c[i60], s_c[i60 + 1]])
-        t_c[i60] = feb29(np.concatenate([np.full((58,) + sub[0].shape[1:], np.nan), sub[0]]))
-        s_c[i60] = feb29(np.concatenate([np.full((58,) + sub[1].shape[1:], np.nan), sub[1]]))
-    if smoothPercentile:
-        t_c = runavg(t_c, smoothPercentileWidth)
-        s_c = runavg(s_c, smoothPercentileWidth)
-    thresh[present], seas[present] = t_c, s_c
+    # A (cell, doy) without samples is absent from that cell's groupby output (identify.py:233,
+    # :263 after the dropna at :208), so feb29 acts on the doy LABELS that are present
+    # (`where(doy != 60, feb29(...))`, identify.py:137-151, :237-240) and runavg pads / rolls over
+    # the cell's own compacted doy axis (identify.py:175-180).  Cells are grouped by their
+    # presence pattern (almost always "all present").
+    pres = ~np.isnan(thresh)
+    pat, inv = np.unique(pres.T, axis=0, return_inverse=True)
+    inv = np.asarray(inv).reshape(-1)
+    for k in range(len(pat)):
+        present = pat[k]
+        if not present.any():
+            continue
+        cells = np.nonzero(inv == k)[0]
+        didx = np.nonzero(present)[0]
+        t_c, s_c = thresh[np.ix_(didx, cells)], seas[np.ix_(didx, cells)]
+        if not tstep and ndoy >= 61 and present[59]:
+            members = [int(np.searchsorted(didx, d)) for d in (58, 59, 60) if present[d]]
+            i60 = int(np.searchsorted(didx, 59))
+            for arr in (t_c, s_c):
+                acc = np.zeros(len(cells))
+                for m_ in members:
+                    acc = acc + arr[m_]
+                arr[i60] = acc / len(members)
+        if smoothPercentile:
+            t_c = runavg(t_c, smoothPercentileWidth)
+            s_c = runavg(s_c, smoothPercentileWidth)
+        thresh[np.ix_(didx, cells)] = t_c
+        seas[np.ix_(didx, cells)] = s_c
     return thresh, seas
 
 

@@ -8,6 +8,7 @@
 // library only (xmhw_b200/_cabi.py raises if it is missing).
 #include <vector>
 #include "../../xmhw_b200/csrc/xmhw_lane.h"
+#include "../../xmhw_b200/csrc/xmhw_topk.h"
 
 using namespace xmhw;
 
@@ -39,7 +40,73 @@ static void sweep_cells(const float* ts, int64_t ngrid, const ClimPlan* plan, do
   }
 }
 
+template <int KP, int MAXN>
+static void sweep2_cells(const float* ts, int64_t ngrid, const ClimPlan2* plan, double* thr, double* seas,
+                         int32_t* nzero) {
+  std::vector<uint32_t> pool((size_t)plan->pool_rows * 32);
+  std::vector<uint32_t> scratch((size_t)plan->nslots * 64);
+  HostEnv env;
+  for (int64_t cell = 0; cell < ngrid; ++cell) {
+    const int lane = (int)(cell & 31);
+    TopkSweeper<HostEnv, KP, MAXN> sw(env, *plan, pool.data(), scratch.data(), lane, ts + cell, ngrid, true);
+    sw.init();
+    for (int s = -1; s < plan->nsteps; ++s) {
+      double a, b;
+      int row;
+      sw.step(s, a, b, row);
+      if (s < 0) continue;
+      thr[(int64_t)row * ngrid + cell] = a;
+      seas[(int64_t)row * ngrid + cell] = b;
+    }
+    nzero[cell] = sw.nzero;
+  }
+}
+
+template <int KP>
+static void direct_cells(const float* ts, int64_t ngrid, const int32_t* rows, int nrows, double q, double* thr,
+                         double* seas, int32_t* nzero) {
+  for (int64_t cell = 0; cell < ngrid; ++cell) {
+    DirectSelect<KP> ds;
+    for (int r0 = 0; r0 < nrows; r0 += 8) {
+      float v[8];
+      for (int i = 0; i < 8; ++i) v[i] = r0 + i < nrows ? ts[(int64_t)rows[r0 + i] * ngrid + cell] : 0.0f;
+      ds.add8(v, nrows - r0 < 8 ? nrows - r0 : 8, true);
+    }
+    ds.result(q, thr[cell], seas[cell]);
+    if (ds.n == 0) nzero[cell] += 1;
+  }
+}
+
 extern "C" {
+
+int emul_clim_sweep2(const float* ts, int64_t T, int64_t ngrid, const ClimPlan2* plan, double* thr, double* seas,
+                     int32_t* nzero) {
+  (void)T;
+  const bool big = plan->max_size > 32;
+  switch (plan->kp) {
+    case 8: if (big) sweep2_cells<8, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<8, 32>(ts, ngrid, plan, thr, seas, nzero); break;
+    case 16: if (big) sweep2_cells<16, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<16, 32>(ts, ngrid, plan, thr, seas, nzero); break;
+    case 24: if (big) sweep2_cells<24, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<24, 32>(ts, ngrid, plan, thr, seas, nzero); break;
+    case 36: if (big) sweep2_cells<36, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<36, 32>(ts, ngrid, plan, thr, seas, nzero); break;
+    case 48: if (big) sweep2_cells<48, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<48, 32>(ts, ngrid, plan, thr, seas, nzero); break;
+    default: return -1;
+  }
+  return 0;
+}
+
+// one exceptional doy: thr / seas point at that doy's output row
+int emul_clim_direct(const float* ts, int64_t ngrid, const int32_t* rows, int nrows, int kp, double q, double* thr,
+                     double* seas, int32_t* nzero) {
+  switch (kp) {
+    case 8: direct_cells<8>(ts, ngrid, rows, nrows, q, thr, seas, nzero); break;
+    case 16: direct_cells<16>(ts, ngrid, rows, nrows, q, thr, seas, nzero); break;
+    case 24: direct_cells<24>(ts, ngrid, rows, nrows, q, thr, seas, nzero); break;
+    case 36: direct_cells<36>(ts, ngrid, rows, nrows, q, thr, seas, nzero); break;
+    case 48: direct_cells<48>(ts, ngrid, rows, nrows, q, thr, seas, nzero); break;
+    default: return -1;
+  }
+  return 0;
+}
 
 int emul_clim_sweep(const float* ts, int64_t T, int64_t ngrid, const ClimPlan* plan, double* thr, double* seas) {
   (void)T;

@@ -70,6 +70,88 @@ def test_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct, keep):
     assert hp.rows_loaded < len(doy) * 1.1 and hp.max_size <= 48
 
 
+def sweep2(em, ts, doy, ndoy, w, q):
+    """two-stack top-K sweep (csrc/xmhw_topk.h) + the direct selection of the exceptional doys"""
+    from xmhw_b200 import plan2 as P2
+    lib, cabi = em
+    hp = P2.build_clim_plan2(doy, ndoy, w, q)
+    if hp is None:
+        return None, None, None, None
+    s, keep = cabi.numpy_plan2_struct(hp)
+    ts = np.ascontiguousarray(ts, np.float32)
+    T, ng = ts.shape
+    thr = np.full((ndoy, ng), np.nan)
+    se = np.full((ndoy, ng), np.nan)
+    nz = np.zeros(ng, np.int32)
+    assert lib.emul_clim_sweep2(_vp(ts), C.c_int64(T), C.c_int64(ng), C.byref(s), _vp(thr), _vp(se), _vp(nz)) == 0
+    for k, d in enumerate(hp.exc_doy):
+        rows = np.ascontiguousarray(hp.exc_rows[hp.exc_off[k]:hp.exc_off[k + 1]], np.int32)
+        off = (int(d) - 1) * ng * 8
+        assert lib.emul_clim_direct(_vp(ts), C.c_int64(ng), _vp(rows), C.c_int(len(rows)), C.c_int(hp.kp),
+                                    C.c_double(q), C.c_void_p(thr.ctypes.data + off),
+                                    C.c_void_p(se.ctypes.data + off), _vp(nz)) == 0
+    return hp, thr, se, nz
+
+
+CASES2 = CASES + [
+    ("30yr_p95_w7", (1982, 2011), 16, 8000, 7, 95),
+    ("13yr_from_leap", (1984, 1996), 16, 0, 5, 90),
+    ("30yr_w3_p80", (1990, 2019), 8, 3000, 3, 80),
+]
+
+
+@pytest.mark.parametrize("name,years,ncell,nan_ppm,w,pct", CASES2, ids=[c[0] for c in CASES2])
+def test_topk_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct):
+    """The two-stack top-K sweep is bit-equal to the oracle wherever its plan accepts the calendar;
+    the cases it declines (huge K, very wide windows) are the general sweep's (test above)."""
+    tm = S.daily_time(*years)
+    doy = S.doy366(tm)
+    ts = S.synth_sst(len(tm), ncell, S.season_table(tm), nan_ppm=nan_ppm)
+    if nan_ppm:
+        ts[100:300, 3] = np.nan
+        ts[:, 5] = np.nan
+        ts[700:, 7] = np.nan
+    hp, thr, se, nz = sweep2(em, ts, doy, 366, w, pct / 100.0)
+    if name in ("70yr_two_pieces", "w15_p10"):
+        assert hp is None
+        return
+    assert hp is not None and hp.smem_bytes() <= 227 * 1024
+    oth, ose = O.threshold(ts, doy, 366, pctile=pct, windowHalfWidth=w, smoothPercentile=False, tstep=True)
+    assert bit_equal(thr, oth)
+    assert np.nanmax(np.abs(se - ose), initial=0) <= 1e-12
+    assert np.array_equal(nz + (366 - hp.nsteps - len(hp.exc_doy)), np.isnan(oth).sum(axis=0))     # + absent labels
+    if name == "30yr":
+        assert hp.kp == 36 and list(hp.exc_doy) == [60] and hp.pool_rows <= 444      # 4 warps per SM
+
+
+def test_topk_sweep_infinite_pentad_cube(em, oisst):
+    tm = S.daily_time(2001, 2012)
+    doy = S.doy366(tm)
+    ts = S.synth_sst(len(tm), 6, S.season_table(tm))
+    ts[500, 1] = np.inf
+    ts[900, 2] = -np.inf
+    ts[1300, 3] = np.inf
+    ts[1302, 3] = -np.inf
+    hp, thr, se, nz = sweep2(em, ts, doy, 366, 5, 0.9)
+    with np.errstate(invalid="ignore"):
+        oth, ose = O.threshold(ts, doy, 366, smoothPercentile=False, tstep=True)
+    assert bit_equal(thr, oth)
+    assert np.array_equal(np.isnan(se), np.isnan(ose)) and np.array_equal(np.isinf(se), np.isinf(ose))
+    fin = np.isfinite(ose)
+    assert np.abs(se[fin] - ose[fin]).max() <= 1e-12
+    doy = np.tile(np.arange(1, 74), 30)                       # pentads, tstep calendar
+    ts = S.synth_sst(len(doy), 16, S.season_table(len(doy)))
+    hp, thr, se, nz = sweep2(em, ts, doy, 73, 5, 0.9)
+    oth, ose = O.threshold(ts, doy, 73, smoothPercentile=False, tstep=True)
+    assert hp is not None and len(hp.exc_doy) == 0
+    assert bit_equal(thr, oth) and np.abs(se - ose).max() <= 1e-12
+    d = O.add_doy(oisst["time"])                              # the reference's own test cube (2 years)
+    cube = oisst["sst"].reshape(len(d), -1)
+    hp, thr, se, nz = sweep2(em, cube, d, 366, 5, 0.9)
+    oth, ose = O.threshold(cube, d, 366, smoothPercentile=False, tstep=True)
+    assert hp is not None and bit_equal(thr, oth) and bit_equal(se, ose)
+
+
 def test_sweep_infinite_samples(em):
     """+-inf samples poison the running window sum only while they are inside the window."""
     tm = S.daily_time(2001, 2012)

@@ -41,6 +41,17 @@ class ClimPlanStruct(C.Structure):
                 ("step_rec", C.c_void_p), ("q", C.c_double)]
 
 
+class ClimPlan2Struct(C.Structure):
+    """Mirror of `xmhw_clim_plan2` (include/xmhw_b200.h): the two-stack top-K sweep."""
+    _fields_ = [("nsteps", C.c_int32), ("kp", C.c_int32), ("max_size", C.c_int32), ("slot_rows", C.c_int32),
+                ("nslots", C.c_int32), ("n_init", C.c_int32), ("pool_rows", C.c_int32), ("reserved_", C.c_int32),
+                ("rows", C.c_void_p), ("atoms", C.c_void_p), ("step_rec", C.c_void_p), ("flip", C.c_void_p),
+                ("q", C.c_double)]
+
+
+PLAN2_ARRAYS = ("rows", "atoms", "step_rec", "flip")
+
+
 INTERMEDIATE_FIELDS = (("events", "f8"), ("seas", "f8"), ("thresh", "f8"), ("relSeas", "f8"),
                        ("relThresh", "f8"), ("relThreshNorm", "f8"), ("severity", "f8"), ("cats", "f8"),
                        ("mabs", "f4"), ("bthresh", "u1"), ("duration_moderate", "u1"),
@@ -59,11 +70,15 @@ _SIGNATURES = {
     "xmhw_abi_version": (C.c_int, []),
     "xmhw_strerror": (C.c_char_p, [C.c_int]),
     "xmhw_clim_sweep_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlanStruct),
-                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xmhw_clim_sweep2_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlan2Struct),
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xmhw_clim_direct_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                       C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_clim_finish_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
-                                       C.c_int32, C.c_void_p]),
+                                       C.c_int32, C.c_void_p, C.c_void_p]),
     "xmhw_clim_finish2_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
-                                        C.c_int32, C.c_int32, C.c_void_p]),
+                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "xmhw_exceed_mask_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_events_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
@@ -110,7 +125,8 @@ def _load():
 
 
 lib = _load()
-if lib.xmhw_abi_version() != 1:
+ABI_VERSION = 2
+if lib.xmhw_abi_version() != ABI_VERSION:
     raise ImportError("xmhw_b200: ABI version mismatch in %s" % LIB_PATH)
 
 
@@ -134,6 +150,24 @@ def plan_struct(host_plan, pointers):
     for name in PLAN_ARRAYS:
         setattr(s, name, pointers[name])
     return s
+
+
+def plan2_struct(host_plan, pointers):
+    """Build a ClimPlan2Struct from a plan2.ClimPlan2Host and {array name: address}."""
+    s = ClimPlan2Struct()
+    for f in ("nsteps", "kp", "max_size", "slot_rows", "nslots", "n_init", "pool_rows"):
+        setattr(s, f, int(getattr(host_plan, f)))
+    s.q = float(host_plan.q)
+    for name in PLAN2_ARRAYS:
+        setattr(s, name, pointers[name])
+    return s
+
+
+def numpy_plan2_struct(host_plan):
+    """Plan struct over HOST arrays (used only by the test-side lane emulator)."""
+    keep = {n: np.ascontiguousarray(getattr(host_plan, n)) for n in PLAN2_ARRAYS}
+    s = plan2_struct(host_plan, {n: a.ctypes.data for n, a in keep.items()})
+    return s, keep
 
 
 def numpy_plan_struct(host_plan):

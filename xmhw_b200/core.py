@@ -18,6 +18,7 @@ import torch
 
 from . import _cabi
 from . import plan as _plan
+from . import plan2 as _plan2
 from ._cabi import EF_COUNT, EF_FIELDS, EI_COUNT, EI_FIELDS, check, lib
 
 _plan_cache = {}
@@ -26,7 +27,7 @@ _plan_cache = {}
 # bracketed by CUDA events on the launch stream and (name, start, end) is appended.
 TRACE = None
 LAUNCHES = {"n": 0}
-_KERNELS_PER_CALL = {"xmhw_exclusive_scan_i32": 3, "xmhw_intermediate_f32": 2}      # finish2: 1 (width 31) or 2 launches
+_KERNELS_PER_CALL = {"xmhw_exclusive_scan_i32": 3, "xmhw_intermediate_f32": 2, "xmhw_clim_finish2_f64": 2}
 
 
 def _call(name, *args):
@@ -82,6 +83,41 @@ def device_plan(doy, ndoy, w, q, device):
                for n in _cabi.PLAN_ARRAYS}
     struct = _cabi.plan_struct(host, {n: _ptr(t) for n, t in tensors.items()})
     dp = DevicePlan(host, tensors, struct)
+    if len(_plan_cache) > 16:
+        _plan_cache.clear()
+    _plan_cache[key] = dp
+    return dp
+
+
+@dataclass
+class DevicePlan2:
+    host: _plan2.ClimPlan2Host
+    tensors: dict
+    struct: _cabi.ClimPlan2Struct
+    exc_rows: object            # device int32: window rows of the exceptional doys (CSR by host.exc_off)
+
+
+def sweep_mode():
+    """Development knob XMHW_B200_SWEEP: "topk" (default: the two-stack top-K sweep when the calendar
+    fits, else the general one) or "general" (always the sorted-list sweep of plan.py)."""
+    import os
+    return os.environ.get("XMHW_B200_SWEEP", "topk")
+
+
+def device_plan2(doy, ndoy, w, q, device):
+    """Plan of the two-stack top-K sweep on `device`, or None when the calendar / quantile needs
+    the general sweep (plan2.build_clim_plan2 returns None)."""
+    doy = np.ascontiguousarray(doy, dtype=np.int64)
+    key = ("topk", hashlib.sha1(doy.tobytes()).hexdigest(), int(ndoy), int(w), float(q), str(device))
+    if key in _plan_cache:
+        return _plan_cache[key]
+    host = _plan2.build_clim_plan2(doy, ndoy, w, q)
+    dp = None
+    if host is not None:
+        tensors = {n: torch.from_numpy(np.ascontiguousarray(getattr(host, n))).to(device)
+                   for n in _cabi.PLAN2_ARRAYS}
+        struct = _cabi.plan2_struct(host, {n: _ptr(t) for n, t in tensors.items()})
+        dp = DevicePlan2(host, tensors, struct, torch.from_numpy(np.ascontiguousarray(host.exc_rows)).to(device))
     if len(_plan_cache) > 16:
         _plan_cache.clear()
     _plan_cache[key] = dp
@@ -144,13 +180,34 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
             outs.append(full)
         return tuple(outs)
     with torch.cuda.device(ts.device):
-        dp = device_plan(doy, ndoy, windowHalfWidth, pctile / 100.0, ts.device)
         st = _stream()
-        raw_t = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
-        raw_s = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
+        q = pctile / 100.0
         ncg = (ngrid + 31) // 32
-        scratch = torch.empty(max(1, ncg * dp.host.scratch_rows * 32), dtype=torch.int32, device=ts.device)
-        _call("xmhw_clim_sweep_f32", _ptr(ts), T, ngrid, dp.struct, _ptr(raw_t), _ptr(raw_s), _ptr(scratch), st)
+        nempty = torch.empty(ngrid, dtype=torch.int32, device=ts.device)
+        dp2 = device_plan2(doy, ndoy, windowHalfWidth, q, ts.device) if sweep_mode() == "topk" else None
+        if dp2 is not None:
+            # two-stack top-K sweep; rows of the doys it does not cover (absent labels) stay NaN
+            h = dp2.host
+            full = h.nsteps + len(h.exc_doy) == ndoy
+            alloc = torch.empty if full else (lambda *a, **k: torch.full(*a, float("nan"), **k))
+            raw_t = alloc((ndoy, ngrid), dtype=torch.float64, device=ts.device)
+            raw_s = alloc((ndoy, ngrid), dtype=torch.float64, device=ts.device)
+            scratch = torch.empty(ncg * h.nslots * 64, dtype=torch.int32, device=ts.device)
+            _call("xmhw_clim_sweep2_f32", _ptr(ts), T, ngrid, dp2.struct, _ptr(raw_t), _ptr(raw_s), _ptr(nempty),
+                  _ptr(scratch), st)
+            for k, d in enumerate(h.exc_doy):
+                a, b = int(h.exc_off[k]), int(h.exc_off[k + 1])
+                _call("xmhw_clim_direct_f32", _ptr(ts), T, ngrid, _ptr(dp2.exc_rows) + 4 * a, b - a, h.kp, float(q),
+                      _ptr(raw_t) + (int(d) - 1) * ngrid * 8, _ptr(raw_s) + (int(d) - 1) * ngrid * 8, _ptr(nempty), st)
+            if not full:
+                nempty += ndoy - h.nsteps - len(h.exc_doy)
+        else:
+            dp = device_plan(doy, ndoy, windowHalfWidth, q, ts.device)
+            raw_t = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
+            raw_s = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
+            scratch = torch.empty(max(1, ncg * dp.host.scratch_rows * 32), dtype=torch.int32, device=ts.device)
+            _call("xmhw_clim_sweep_f32", _ptr(ts), T, ngrid, dp.struct, _ptr(raw_t), _ptr(raw_s), _ptr(nempty),
+                  _ptr(scratch), st)
         W = int(smoothPercentileWidth) if smoothPercentile else 1
         do_feb = bool(feb29) and ndoy >= 61
         if W <= 1 and not do_feb:
@@ -158,7 +215,7 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
         out_t = torch.empty_like(raw_t)
         out_s = torch.empty_like(raw_s)
         _call("xmhw_clim_finish2_f64", _ptr(raw_t), _ptr(out_t), _ptr(raw_s), _ptr(out_s), ndoy, ngrid,
-              int(do_feb), W, st)
+              int(do_feb), W, _ptr(nempty), st)
     return (out_t, out_s, raw_t, raw_s) if return_raw else (out_t, out_s)
 
 

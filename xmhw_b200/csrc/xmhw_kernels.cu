@@ -13,6 +13,7 @@
 
 #include "../../include/xmhw_b200.h"
 #include "xmhw_lane.h"
+#include "xmhw_topk.h"
 
 namespace {
 
@@ -41,6 +42,7 @@ struct WarpEnv {
 };
 
 static_assert(sizeof(xmhw_clim_plan) == sizeof(ClimPlan), "plan ABI mismatch");
+static_assert(sizeof(xmhw_clim_plan2) == sizeof(ClimPlan2), "plan2 ABI mismatch");
 static_assert((int)XMHW_EI_COUNT == (int)EI_COUNT && (int)XMHW_EF_COUNT == (int)EF_COUNT, "event ABI mismatch");
 
 // ---------------------------------------------------------------------------
@@ -53,7 +55,7 @@ static_assert((int)XMHW_EI_COUNT == (int)EI_COUNT && (int)XMHW_EF_COUNT == (int)
 template <int MAXN, int MINB>
 __global__ void __launch_bounds__(32, MINB) clim_sweep_kernel(
     ClimPlan p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr, double* __restrict__ seas,
-    uint32_t* __restrict__ scratch) {
+    int32_t* __restrict__ nempty, uint32_t* __restrict__ scratch) {
   extern __shared__ uint32_t pool[];
   const int lane = threadIdx.x;
   const int64_t cell = (int64_t)blockIdx.x * 32 + lane;
@@ -70,6 +72,59 @@ __global__ void __launch_bounds__(32, MINB) clim_sweep_kernel(
       seas[(int64_t)s * ngrid + cell] = b;
     }
   }
+  if (ok) nempty[cell] = sw.nzero;
+}
+
+// ---------------------------------------------------------------------------
+// K1'  two-stack top-K climatology sweep (xmhw_topk.h): one warp = 32 cells, straight-line
+// sorting / merging networks per doy, the unit slots of the window in shared memory.
+// ---------------------------------------------------------------------------
+template <int KP, int MAXN, int MINB>
+__global__ void __launch_bounds__(32, MINB) clim_sweep2_kernel(
+    ClimPlan2 p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr, double* __restrict__ seas,
+    int32_t* __restrict__ nempty, uint32_t* __restrict__ scratch) {
+  extern __shared__ uint32_t pool[];
+  const int lane = threadIdx.x;
+  const int64_t cell = (int64_t)blockIdx.x * 32 + lane;
+  const bool ok = cell < ngrid;
+  const float* col = ts + (ok ? cell : 0);
+  WarpEnv env;
+  TopkSweeper<WarpEnv, KP, MAXN> sw(env, p, pool, scratch + (size_t)blockIdx.x * p.nslots * 64, lane, col, ngrid, ok);
+  sw.init();
+  for (int s = -1; s < p.nsteps; ++s) {          // s = -1: initial fill of the first window
+    double a, b;
+    int row;
+    sw.step(s, a, b, row);
+    if (ok && s >= 0) {
+      thr[(int64_t)row * ngrid + cell] = a;
+      seas[(int64_t)row * ngrid + cell] = b;
+    }
+  }
+  if (ok) nempty[cell] = sw.nzero;
+}
+
+// doys whose window is not a range of the atom order (doy 60): direct selection, one thread = one cell
+template <int KP>
+__global__ void __launch_bounds__(128) clim_direct_kernel(const float* __restrict__ ts, int64_t ngrid,
+                                                          const int32_t* __restrict__ rows, int nrows, double q,
+                                                          double* __restrict__ thr_row, double* __restrict__ seas_row,
+                                                          int32_t* __restrict__ nempty) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = cell < ngrid;
+  const float* col = ts + (ok ? cell : 0);
+  DirectSelect<KP> ds;
+  for (int r0 = 0; r0 < nrows; r0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(col + (int64_t)__ldg(rows + min(r0 + i, nrows - 1)) * ngrid);
+    ds.add8(v, nrows - r0 < 8 ? nrows - r0 : 8, ok);
+  }
+  if (!ok) return;
+  double a, b;
+  ds.result(q, a, b);
+  thr_row[cell] = a;
+  seas_row[cell] = b;
+  if (ds.n == 0) nempty[cell] += 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -122,10 +177,12 @@ __device__ __forceinline__ double div_const(double x) {
 
 // generic odd width: W slots per thread in shared memory (column = thread: conflict free)
 __global__ void clim_finish_kernel(const double* __restrict__ raw, double* __restrict__ out, int ndoy,
-                                   int64_t ngrid, int feb29, int W) {
+                                   int64_t ngrid, int feb29, int W, const int32_t* __restrict__ nempty) {
   extern __shared__ double slots[];
   const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= ngrid) return;
+  const int ne = nempty[cell];
+  if (ne > 0 && ne < ndoy) return;          // some doys without samples: clim_finish_compact_kernel
   FinishSrc src;
   src.init(raw + cell, ngrid, ndoy, feb29);
   double* __restrict__ o = out + cell;
@@ -162,9 +219,12 @@ __global__ void clim_finish_kernel(const double* __restrict__ raw, double* __res
 template <int W>
 __global__ void __launch_bounds__(128) clim_finish_reg_kernel(const double* __restrict__ raw0, double* __restrict__ out0,
                                                               const double* __restrict__ raw1, double* __restrict__ out1,
-                                                              int ndoy, int64_t ngrid, int feb29) {
+                                                              int ndoy, int64_t ngrid, int feb29,
+                                                              const int32_t* __restrict__ nempty) {
   const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= ngrid) return;
+  const int ne = nempty[cell];
+  if (ne > 0 && ne < ndoy) return;          // some doys without samples: clim_finish_compact_kernel
   FinishSrc src;
   src.init((blockIdx.y ? raw1 : raw0) + cell, ngrid, ndoy, feb29);
   double* __restrict__ o = (blockIdx.y ? out1 : out0) + cell;
@@ -218,6 +278,78 @@ __global__ void __launch_bounds__(128) clim_finish_reg_kernel(const double* __re
 #pragma unroll
       for (int i = W - 2; i >= 0; --i) slot[i] = slot[i] + slot[i + 1];
     }
+  }
+}
+
+// Cells in which SOME doys have no sample (e.g. a sea-ice season that is NaN every year): the
+// reference's groupby output simply lacks those doys for that cell, so feb29 acts on the labels
+// that are present and runavg pads / rolls over the cell's own compacted doy axis
+// (identify.py:137-151, :175-180, :233-241).  One warp = one such cell: the column is compacted
+// into shared memory, every lane then evaluates outputs in the summation order of the block
+// scheme above (oracle/xmhw_oracle.py:runavg on the compacted axis), absent doys become NaN.
+constexpr int FINC_WARPS = 4;
+__global__ void __launch_bounds__(FINC_WARPS * 32) clim_finish_compact_kernel(
+    const double* __restrict__ raw0, double* __restrict__ out0, const double* __restrict__ raw1,
+    double* __restrict__ out1, int ndoy, int64_t ngrid, int feb29, int W, const int32_t* __restrict__ nempty) {
+  extern __shared__ double fc_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t cell = (int64_t)blockIdx.x * FINC_WARPS + wib;
+  if (cell >= ngrid) return;
+  const int ne = nempty[cell];
+  if (ne <= 0 || ne >= ndoy) return;
+  double* c = fc_smem + (size_t)wib * ndoy * 2;              // compacted values
+  int* lab = (int*)(c + ndoy);                               // their doy index (0-based)
+  for (int var = 0; var < 2; ++var) {
+    const double* raw = (var ? raw1 : raw0) + cell;
+    double* o = (var ? out1 : out0) + cell;
+    if (!raw || !o) continue;
+    int m = 0;
+    for (int d0 = 0; d0 < ndoy; d0 += 32) {
+      const int d = d0 + lane;
+      double v = d < ndoy ? raw[(int64_t)d * ngrid] : qnan();
+      const bool pres = v == v;
+      if (pres && feb29 && ndoy >= 61 && d == 59) {          // label 60 <- mean of the labels 59, 60, 61 present
+        double acc = 0.0; int n = 0;
+        for (int dd = 58; dd <= 60; ++dd) {
+          const double x = raw[(int64_t)dd * ngrid];
+          if (x == x) { acc = acc + x; ++n; }
+        }
+        v = acc / (double)n;
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, pres);
+      const int pos = m + __popc(bal & ((1u << lane) - 1u));
+      if (pres) { c[pos] = v; lab[pos] = d; }
+      else if (d < ndoy) o[(int64_t)d * ngrid] = qnan();
+      m += __popc(bal);
+    }
+    __syncwarp();
+    const int h = W > 1 ? (W - 1) / 2 : 0;
+    const int L = m + W - 1;
+    const double w = (double)W;
+    for (int i = lane; i < m; i += 32) {
+      double S;
+      if (W <= 1) {
+        S = c[i];
+      } else {
+        // e[j] = c[(j - h) mod m]; block b = i / W: suffix of block b from i (right to left)
+        // plus prefix of block b + 1 up to i + W - 1 (left to right)
+        const int b = i / W, p = i - b * W;
+        const int hi = min(L, (b + 1) * W);
+        int k = (((hi - 1 - h) % m) + m) % m;                 // index of e[hi - 1]
+        double acc = c[k];
+        for (int j = hi - 2; j >= i; --j) { k = k == 0 ? m - 1 : k - 1; acc = c[k] + acc; }
+        S = acc;
+        if (p > 0) {
+          k = ((((b + 1) * W - h) % m) + m) % m;              // index of e[(b + 1) W]
+          double pre = c[k];
+          for (int j = (b + 1) * W + 1; j <= i + W - 1; ++j) { k = k + 1 == m ? 0 : k + 1; pre = pre + c[k]; }
+          S = S + pre;
+        }
+        S = S / w;
+      }
+      o[(int64_t)lab[i] * ngrid] = S;
+    }
+    __syncwarp();
   }
 }
 
@@ -703,8 +835,8 @@ const char* xmhw_strerror(int code) {
 }
 
 int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan* plan,
-                        double* thresh_raw, double* seas_raw, uint32_t* scratch, void* stream) {
-  if (!ts || !plan || !thresh_raw || !seas_raw || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
+                        double* thresh_raw, double* seas_raw, int32_t* nempty, uint32_t* scratch, void* stream) {
+  if (!ts || !plan || !thresh_raw || !seas_raw || !nempty || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
   if (plan->scratch_rows < 0 || (plan->scratch_rows > 0 && !scratch)) return XMHW_E_ARG;
   if (ngrid > 0xffffffffll || T > 0x7fffffffll) return XMHW_E_ARG;
   if (plan->nsteps <= 0 || plan->pool_rows <= 0 || plan->max_size > 48 || plan->nmax <= 0) return XMHW_E_PLAN;
@@ -722,7 +854,7 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
     e = cudaFuncSetAttribute(clim_sweep_kernel<N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return (int)e;                                                                            \
     clim_sweep_kernel<N, B><<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw,  \
-                                                                               scratch);                           \
+                                                                               nempty, scratch);                   \
   }
   if (plan->max_size <= 32) {
     if (minb >= 24) XMHW_SWEEP(32, 24) else if (minb >= 20) XMHW_SWEEP(32, 20) else if (minb >= 16) XMHW_SWEEP(32, 16)
@@ -734,35 +866,111 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
   return cuda_status();
 }
 
-int xmhw_clim_finish_f64(const double* raw, double* out, int32_t ndoy, int64_t ngrid, int32_t feb29,
-                         int32_t smooth_width, void* stream) {
-  if (!raw || !out || raw == out || ndoy <= 0 || ngrid <= 0) return XMHW_E_ARG;
-  if (smooth_width > 1 && smooth_width % 2 == 0) return XMHW_E_ARG;
+int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan2* plan,
+                         double* thresh_raw, double* seas_raw, int32_t* nempty, uint32_t* scratch, void* stream) {
+  if (!ts || !plan || !thresh_raw || !seas_raw || !nempty || !scratch || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
+  if (ngrid > 0xffffffffll || T > 0x7fffffffll) return XMHW_E_ARG;
+  if (plan->nsteps <= 0 || plan->nslots <= 0 || plan->nslots > 32 || plan->slot_rows <= plan->kp ||
+      plan->pool_rows != plan->nslots * plan->slot_rows || plan->max_size <= 0 || plan->max_size > 48 || plan->n_init <= 0 ||
+      !plan->rows || !plan->atoms || !plan->step_rec || !plan->flip)
+    return XMHW_E_PLAN;
+  const size_t smem = (size_t)plan->pool_rows * 128;
+  if (smem > 227 * 1024) return XMHW_E_SMEM;
+  ClimPlan2 p;
+  memcpy(&p, plan, sizeof(p));
+  const int64_t ncg = (ngrid + 31) / 32;
+  cudaError_t e;
+#define XMHW_SWEEP2(K, N, B)                                                                                         \
+  {                                                                                                                  \
+    e = cudaFuncSetAttribute(clim_sweep2_kernel<K, N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) return (int)e;                                                                             \
+    clim_sweep2_kernel<K, N, B><<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw,         \
+                                                                                   seas_raw, nempty, scratch);      \
+  }
+  const bool big = plan->max_size > 32;
+  switch (plan->kp) {
+    case 8: if (big) XMHW_SWEEP2(8, 48, 4) else XMHW_SWEEP2(8, 32, 6) break;
+    case 16: if (big) XMHW_SWEEP2(16, 48, 4) else XMHW_SWEEP2(16, 32, 6) break;
+    case 24: if (big) XMHW_SWEEP2(24, 48, 4) else XMHW_SWEEP2(24, 32, 5) break;
+    case 36: if (big) XMHW_SWEEP2(36, 48, 3) else XMHW_SWEEP2(36, 32, 4) break;
+    case 48: if (big) XMHW_SWEEP2(48, 48, 3) else XMHW_SWEEP2(48, 32, 3) break;
+    default: return XMHW_E_PLAN;
+  }
+#undef XMHW_SWEEP2
+  return cuda_status();
+}
+
+int xmhw_clim_direct_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* rows, int32_t nrows, int32_t kp,
+                         double q, double* thresh_row, double* seas_row, int32_t* nempty, void* stream) {
+  if (!ts || !rows || !thresh_row || !seas_row || !nempty || T <= 0 || ngrid <= 0 || nrows <= 0) return XMHW_E_ARG;
+  const int nt = 128;
+  const unsigned nb = (unsigned)((ngrid + nt - 1) / nt);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (kp) {
+    case 8: clim_direct_kernel<8><<<nb, nt, 0, st>>>(ts, ngrid, rows, nrows, q, thresh_row, seas_row, nempty); break;
+    case 16: clim_direct_kernel<16><<<nb, nt, 0, st>>>(ts, ngrid, rows, nrows, q, thresh_row, seas_row, nempty); break;
+    case 24: clim_direct_kernel<24><<<nb, nt, 0, st>>>(ts, ngrid, rows, nrows, q, thresh_row, seas_row, nempty); break;
+    case 36: clim_direct_kernel<36><<<nb, nt, 0, st>>>(ts, ngrid, rows, nrows, q, thresh_row, seas_row, nempty); break;
+    case 48: clim_direct_kernel<48><<<nb, nt, 0, st>>>(ts, ngrid, rows, nrows, q, thresh_row, seas_row, nempty); break;
+    default: return XMHW_E_PLAN;
+  }
+  return cuda_status();
+}
+
+// cells with some (not all) doys empty: per-cell compacted doy axis
+static int finish_compact(const double* raw0, double* out0, const double* raw1, double* out1, int32_t ndoy,
+                          int64_t ngrid, int32_t feb29, int32_t W, const int32_t* nempty, cudaStream_t st) {
+  const size_t smem = (size_t)FINC_WARPS * ndoy * 2 * sizeof(double);
+  if (smem > 227 * 1024) return XMHW_E_SMEM;
+  cudaError_t e = cudaFuncSetAttribute(clim_finish_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  clim_finish_compact_kernel<<<(unsigned)((ngrid + FINC_WARPS - 1) / FINC_WARPS), FINC_WARPS * 32, smem, st>>>(
+      raw0, out0, raw1, out1, ndoy, ngrid, feb29, W, nempty);
+  return cuda_status();
+}
+
+static int finish_one(const double* raw, double* out, int32_t ndoy, int64_t ngrid, int32_t feb29,
+                      int32_t smooth_width, const int32_t* nempty, cudaStream_t st) {
   const int nt = 128;
   const size_t smem = smooth_width > 1 ? (size_t)smooth_width * nt * sizeof(double) : 0;
   if (smem > 227 * 1024) return XMHW_E_SMEM;
   cudaError_t e = cudaFuncSetAttribute(clim_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  clim_finish_kernel<<<(unsigned)((ngrid + nt - 1) / nt), nt, smem, (cudaStream_t)stream>>>(
-      raw, out, ndoy, ngrid, feb29, smooth_width);
+  clim_finish_kernel<<<(unsigned)((ngrid + nt - 1) / nt), nt, smem, st>>>(raw, out, ndoy, ngrid, feb29, smooth_width,
+                                                                           nempty);
   return cuda_status();
 }
 
-int xmhw_clim_finish2_f64(const double* thresh_raw, double* thresh_out, const double* seas_raw, double* seas_out,
-                          int32_t ndoy, int64_t ngrid, int32_t feb29, int32_t smooth_width, void* stream) {
-  if (!thresh_raw || !thresh_out || !seas_raw || !seas_out || thresh_raw == thresh_out || seas_raw == seas_out ||
-      ndoy <= 0 || ngrid <= 0) return XMHW_E_ARG;
+int xmhw_clim_finish_f64(const double* raw, double* out, int32_t ndoy, int64_t ngrid, int32_t feb29,
+                         int32_t smooth_width, const int32_t* nempty, void* stream) {
+  if (!raw || !out || !nempty || raw == out || ndoy <= 0 || ngrid <= 0) return XMHW_E_ARG;
   if (smooth_width > 1 && smooth_width % 2 == 0) return XMHW_E_ARG;
+  int rc = finish_one(raw, out, ndoy, ngrid, feb29, smooth_width, nempty, (cudaStream_t)stream);
+  if (rc) return rc;
+  return finish_compact(raw, out, nullptr, nullptr, ndoy, ngrid, feb29, smooth_width, nempty, (cudaStream_t)stream);
+}
+
+int xmhw_clim_finish2_f64(const double* thresh_raw, double* thresh_out, const double* seas_raw, double* seas_out,
+                          int32_t ndoy, int64_t ngrid, int32_t feb29, int32_t smooth_width, const int32_t* nempty,
+                          void* stream) {
+  if (!thresh_raw || !thresh_out || !seas_raw || !seas_out || !nempty || thresh_raw == thresh_out ||
+      seas_raw == seas_out || ndoy <= 0 || ngrid <= 0) return XMHW_E_ARG;
+  if (smooth_width > 1 && smooth_width % 2 == 0) return XMHW_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
   if (smooth_width == 31) {
     const int nt = 128;
     dim3 grid((unsigned)((ngrid + nt - 1) / nt), 2);
-    clim_finish_reg_kernel<31><<<grid, nt, 0, (cudaStream_t)stream>>>(thresh_raw, thresh_out, seas_raw, seas_out,
-                                                                      ndoy, ngrid, feb29);
-    return cuda_status();
+    clim_finish_reg_kernel<31><<<grid, nt, 0, st>>>(thresh_raw, thresh_out, seas_raw, seas_out, ndoy, ngrid, feb29,
+                                                    nempty);
+    int rc = cuda_status();
+    if (rc) return rc;
+  } else {
+    int rc = finish_one(thresh_raw, thresh_out, ndoy, ngrid, feb29, smooth_width, nempty, st);
+    if (rc) return rc;
+    rc = finish_one(seas_raw, seas_out, ndoy, ngrid, feb29, smooth_width, nempty, st);
+    if (rc) return rc;
   }
-  int rc = xmhw_clim_finish_f64(thresh_raw, thresh_out, ndoy, ngrid, feb29, smooth_width, stream);
-  if (rc) return rc;
-  return xmhw_clim_finish_f64(seas_raw, seas_out, ndoy, ngrid, feb29, smooth_width, stream);
+  return finish_compact(thresh_raw, thresh_out, seas_raw, seas_out, ndoy, ngrid, feb29, smooth_width, nempty, st);
 }
 
 int xmhw_exceed_mask_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy_ptr,

@@ -312,10 +312,11 @@ struct Sweeper {
   uint32_t pivot;        // cut value (key of the smallest sample above the cut)
   float pv[MAXN];        // prefetched rows of the next instance to load (MAXN = 32 or 48 keys per list)
   int total_enter;
+  int nzero;             // steps without any sample (per-cell doy compaction of the smoothing)
   Vec rec_next, use_next;   // step record / list bases of the next step (prefetched)
 
   XMHW_HD Sweeper(const Env& e, const ClimPlan& pl, uint32_t* po, uint32_t* sc, int ln, const float* c, int64_t ng, bool k)
-      : env(e), p(pl), pool(po), scratch(sc), lane(ln), col(c), ngrid(ng), ok(k), C(0), n(0), wsum(0.0), pivot(0xffffffffu) {}
+      : env(e), p(pl), pool(po), scratch(sc), lane(ln), col(c), ngrid(ng), ok(k), C(0), n(0), wsum(0.0), pivot(0xffffffffu), nzero(0) {}
 
   XMHW_HD uint32_t& at(int row) { return pool[row * 32 + lane]; }
 
@@ -559,6 +560,7 @@ struct Sweeper {
     env.vstage(ub, usev, m, m4, lane);
 
     const bool live = n > 0;
+    nzero += live ? 0 : 1;
     if (!env.any(live)) {                                             // all-land warp
       wsum = wsum - f64_from(plo, phi);
       thresh = qnan(); seas = qnan();
@@ -667,7 +669,7 @@ struct Sweeper {
 // ---------------------------------------------------------------------------
 // event finding (identify.py:415-479 mhw_filter, :273-325 join_gaps)
 // ---------------------------------------------------------------------------
-// Plain rules (fuzz-verified against the reference, tests/test_oracle_vs_reference.py):
+// Plain rules (fuzz-verified against the reference pandas code, tests/test_oracle_vs_reference.py):
 // index 0 is never in an event; maximal exceedance runs of length >= minDuration
 // qualify; consecutive qualified events with start - prev_end - 1 <= maxGap merge.
 struct RunFinder {
