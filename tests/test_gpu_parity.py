@@ -113,6 +113,42 @@ def test_synth_daily(core, years, ncell, nan_ppm, pctile):
     assert_events_match(ev.to_numpy(), exp, _float_fields())
 
 
+def test_config4_skipna99_winter_blocks(core):
+    """BASELINE config 4(i) exactly as SURVEY 8d states it, on 4608 cells (144 whole warps):
+    1 % i.i.d. NaN, 2 % of the cells with a 60-120-day NaN block EVERY winter, pctile 99.  The block
+    cells have doys without any sample: the reference smooths those cells on their own compacted
+    doy axis (identify.py:175-180, :233-241) -- clim_finish_compact_kernel vs the oracle."""
+    from oracle import parallel as OP
+    from xmhw_b200 import synth
+    time = synth.daily_time(1982, 2011)
+    doy = synth.doy366(time)
+    ncell = 4608
+    land = synth.land_mask(48, 96, 0.33).ravel()
+    ts_h = synth.synth_sst(len(time), ncell, synth.season_table(time), land=land, nan_ppm=10000)
+    rng = np.random.default_rng(44)
+    blocks = rng.choice(np.flatnonzero(land == 0), int(0.02 * ncell), replace=False)
+    year0 = np.flatnonzero(doy == 1)
+    for c in blocks:
+        start, length = int(rng.integers(330, 366)), int(rng.integers(60, 121))     # from late Nov / Dec on
+        for y0 in year0:
+            ts_h[max(0, y0 + start - 365):max(0, y0 + start - 365 + length), c] = np.nan
+        ts_h[year0[-1] + start:, c][:length] = np.nan
+    ts = torch.from_numpy(ts_h).cuda()
+    th, se = core.threshold_arrays(ts, doy, 366, pctile=99)
+    ev = core.detect_arrays(ts, doy, 366, th, se)
+    th_h, se_h = th.cpu().numpy(), se.cpu().numpy()
+    oth, ose, exp = OP.threshold_detect(ts_h, doy, 366, tkw=dict(pctile=99))
+    partial = np.isnan(oth[:, blocks]).any(0) & ~np.isnan(oth[:, blocks]).all(0)
+    assert partial.sum() >= 0.9 * len(blocks)              # the block cells really lack some doys
+    assert bit_equal(th_h, oth), "thresh differs in %d cells" % (np.abs(th_h - oth) > 0).any(0).sum()
+    assert np.array_equal(np.isnan(se_h), np.isnan(ose)) and np.nanmax(np.abs(se_h - ose)) <= 1e-9
+    # the doys next to a cell's empty season stay finite (the old behaviour made them NaN)
+    c = blocks[np.flatnonzero(partial)[0]]
+    gap = np.flatnonzero(np.isnan(oth[:, c]))
+    assert np.isfinite(th_h[(gap[0] - 1) % 366, c]) and np.isfinite(th_h[(gap[-1] + 1) % 366, c])
+    assert_events_match(ev.to_numpy(), exp, _float_fields())
+
+
 def test_pentad_tstep(core):
     """BASELINE config 4(ii): 73 steps/yr, windowHalfWidth=5, smoothPercentileWidth=5, maxGap=1."""
     from xmhw_b200 import synth
@@ -264,15 +300,17 @@ def test_regional_properties(core):
     ev2 = core.detect_arrays(ts, doy, 366, th, se).to_numpy()
     for k in got:
         assert np.array_equal(got[k], ev2[k], equal_nan=True), k
-    # oracle spot check
-    cells = np.sort(np.random.default_rng(1).choice(ngrid, 48, replace=False))
-    ts_h = ts[:, torch.from_numpy(cells).cuda()].cpu().numpy()
-    oth, ose = O.threshold(ts_h, doy, 366)
-    th_h = th[:, torch.from_numpy(cells).cuda()].cpu().numpy()
-    se_h = se[:, torch.from_numpy(cells).cuda()].cpu().numpy()
+    # oracle check on 4096 cells taken as WHOLE WARPS (128 groups of 32 adjacent cells incl. the first
+    # and the last of the grid): lane interactions (ballots, shared slots) show per warp, not per cell
+    from oracle import parallel as OP
+    groups = np.unique(np.concatenate([[0, ngrid // 32 - 1], np.random.default_rng(1).choice(ngrid // 32, 126, replace=False)]))
+    cells = (groups[:, None] * 32 + np.arange(32)[None, :]).ravel()
+    idx = torch.from_numpy(cells).cuda()
+    ts_h = ts[:, idx].cpu().numpy()
+    oth, ose, exp = OP.threshold_detect(ts_h, doy, 366)
+    th_h, se_h = th[:, idx].cpu().numpy(), se[:, idx].cpu().numpy()
     assert bit_equal(th_h, oth)
     assert np.abs(se_h - ose).max() <= 1e-9
-    exp = O.detect(ts_h, doy, th_h, se_h)
     sel = np.isin(got["cell"], cells)
     sub = {k: v[sel] for k, v in got.items()}
     sub["cell"] = np.searchsorted(cells, sub["cell"])
@@ -318,17 +356,23 @@ def test_global_config3_properties(core):
     assert not bool(land_d[col["cell"].long()].any())                                       # no event on land
     counts = torch.bincount(col["cell"].long(), minlength=ngrid)
     assert torch.equal(counts, ev.offsets[1:] - ev.offsets[:-1])
-    # oracle spot check: 20 ocean + 4 land cells spread over the grid
+    # oracle check on >= 4096 cells taken as WHOLE WARPS: 60 coast warps (land and ocean lanes mixed),
+    # 60 all-ocean warps, 6 all-land warps, the first and the last warp of the grid
+    from oracle import parallel as OP
     rng = np.random.default_rng(3)
-    cells = np.sort(np.concatenate([rng.choice(np.flatnonzero(land == 0), 20, replace=False),
-                                    rng.choice(np.flatnonzero(land == 1), 4, replace=False)]))
+    per_warp = (land.reshape(-1, 32) == 0).sum(1)
+    groups = np.unique(np.concatenate([
+        [0, ngrid // 32 - 1],
+        rng.choice(np.flatnonzero((per_warp > 0) & (per_warp < 32)), 60, replace=False),
+        rng.choice(np.flatnonzero(per_warp == 32), 60, replace=False),
+        rng.choice(np.flatnonzero(per_warp == 0), 6, replace=False)]))
+    cells = (groups[:, None] * 32 + np.arange(32)[None, :]).ravel()
     idx = torch.from_numpy(cells).cuda()
     ts_h = ts[:, idx].cpu().numpy()
     th_h, se_h = th[:, idx].cpu().numpy(), se[:, idx].cpu().numpy()
-    oth, ose = O.threshold(ts_h, doy, 366)
-    assert bit_equal(th_h, oth)
+    oth, ose, exp = OP.threshold_detect(ts_h, doy, 366)
+    assert len(cells) >= 4096 and bit_equal(th_h, oth)
     assert np.nanmax(np.abs(se_h - ose)) <= 1e-9 and np.array_equal(np.isnan(se_h), np.isnan(ose))
-    exp = O.detect(ts_h, doy, th_h, se_h)
     sel = torch.isin(col["cell"].long(), idx)
     keep = sel.nonzero().squeeze(1)
     from xmhw_b200.core import EI_FIELDS, EF_FIELDS
