@@ -93,22 +93,30 @@ typedef struct xmhw_clim_plan {
 /* Plan of the two-stack top-K climatology sweep (xmhw_b200/plan2.py, csrc/xmhw_topk.h): the time
  * rows ordered into atoms (rows that enter and leave the doy windows together) such that every
  * doy's window is a contiguous range of atoms; per doy a fixed-size step record says which unit
- * slots leave, which atoms enter and where the front array of the query lives.  All arrays are
- * device-resident int32.                                                                     */
+ * slots leave, which atoms enter and where the front array of the query lives.  ONE plain HOST
+ * struct (no pointers): the library copies it into the kernel's launch parameters, so the kernel
+ * reads the plan with constant loads and there is no plan array in device memory.
+ * Word layouts: csrc/xmhw_topk.h.                                                            */
+#define XMHW_SC_MAX_STEPS 366
+#define XMHW_SC_REC_WORDS 12
+#define XMHW_SC_MAX_FLIP  768
+#define XMHW_SC_MAX_PAT   16
+#define XMHW_SC_PAT_LEN   48
+#define XMHW_SC_MAX_INIT  32
 typedef struct xmhw_clim_plan2 {
   int32_t nsteps;               /* sweep steps (doys computed by the sweep)        */
   int32_t kp;                   /* top-K capacity: 8, 16, 24, 36 or 48             */
   int32_t max_size;             /* rows of the largest atom, <= 48                 */
-  int32_t slot_rows;            /* shared-memory rows (128 B) per unit slot        */
+  int32_t slot_rows;            /* shared-memory rows (128 B) per unit slot = cap + 3 */
   int32_t nslots;               /* unit slots per 32-cell warp, <= 32              */
   int32_t n_init;               /* atoms pushed before the first step              */
-  int32_t pool_rows;            /* nslots * slot_rows                              */
+  int32_t cap;                  /* key rows per slot                               */
   int32_t reserved_;
-  const int32_t* rows;          /* time indices of all atoms, push order           */
-  const int32_t* atoms;         /* [natoms + 1][4] atom records (zero record last) */
-  const int32_t* step_rec;      /* [nsteps][32] step records                       */
-  const int32_t* flip;          /* flip entries, 2 words each                      */
   double q;                     /* quantile in [0,1] (numpy 'linear': (n-1) q)     */
+  uint32_t rec[XMHW_SC_MAX_STEPS][XMHW_SC_REC_WORDS];   /* step records            */
+  uint32_t flip[XMHW_SC_MAX_FLIP];                      /* flip entries            */
+  int32_t pat[XMHW_SC_MAX_PAT][XMHW_SC_PAT_LEN];        /* row patterns            */
+  uint32_t init[XMHW_SC_MAX_INIT][2];                   /* atoms of the first window */
 } xmhw_clim_plan2;
 
 int xmhw_abi_version(void);
@@ -126,13 +134,12 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
 /* Same reference lines (identify.py:184-270) by the two-stack top-K sweep: every doy is the same
  * straight-line sorting / merging network code for all cells (no data-dependent walk).  Writes
  * the rows of thresh_raw / seas_raw [ndoy][ngrid] named by the plan's step records and
- * nempty [ngrid] i32 = number of those doys without any sample.
- * scratch: ceil(ngrid/32) * plan->nslots * 256 bytes (f64 sums of the unit slots).
+ * nempty [ngrid] i32 = number of those doys without any sample.  `plan` is a HOST pointer.
  * The few doys the plan excludes (doy 60 of the 366-day calendar: its window holds leap years
  * only) are computed by xmhw_clim_direct_f32 from their row list: rows [nrows] i32 time indices,
  * thresh_row / seas_row = that doy's row of the raw arrays, nempty += 1 where it has no sample. */
 int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan2* plan,
-                         double* thresh_raw, double* seas_raw, int32_t* nempty, uint32_t* scratch, void* stream);
+                         double* thresh_raw, double* seas_raw, int32_t* nempty, void* stream);
 int xmhw_clim_direct_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* rows, int32_t nrows, int32_t kp,
                          double q, double* thresh_row, double* seas_row, int32_t* nempty, void* stream);
 

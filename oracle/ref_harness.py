@@ -7,9 +7,11 @@ in `xmhw/identify.py` are pure pandas.  With stub `xarray`/`dask` modules in
 import unchanged, and the reference's own code can be driven with the
 DataFrame that `ds.to_dataframe()` would yield at `identify.py:377`.
 
-Used to (a) pin oracle/xmhw_oracle.py (fuzz), (b) generate golden event
-tables (oracle/make_golden.py).  It cannot travel to the GPU box
-(/root/reference does not exist there) -- callers must check `available()`.
+Used to (a) pin oracle/xmhw_oracle.py (tests/test_oracle_vs_reference.py), (b) generate
+golden event tables (oracle/make_golden.py), (c) time the reference's own pandas detect as
+the CPU arm of bench.py.  /root/reference does not exist on the GPU box: there the
+unmodified copies under oracle/_ref (oracle/build_ref.py) are loaded instead; callers
+must check `available()`.
 """
 import importlib.util
 import os
@@ -20,6 +22,11 @@ import numpy as np
 import pandas as pd
 
 REF_ROOT = os.environ.get("XMHW_REFERENCE_ROOT", "/root/reference")
+# the unmodified copies made by oracle/build_ref.py (git-ignored; they travel to the GPU box)
+_COPY_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+if not os.path.isfile(os.path.join(REF_ROOT, "xmhw", "identify.py")) and \
+        os.path.isfile(os.path.join(_COPY_ROOT, "xmhw", "identify.py")):
+    REF_ROOT = _COPY_ROOT
 _mods = None
 
 

@@ -43,13 +43,11 @@ static void sweep_cells(const float* ts, int64_t ngrid, const ClimPlan* plan, do
 template <int KP, int MAXN>
 static void sweep2_cells(const float* ts, int64_t ngrid, const ClimPlan2* plan, double* thr, double* seas,
                          int32_t* nzero) {
-  std::vector<uint32_t> pool((size_t)plan->pool_rows * 32);
-  std::vector<uint32_t> scratch((size_t)plan->nslots * 64);
+  std::vector<uint32_t> pool((size_t)plan->nslots * plan->slot_rows * 32);
   HostEnv env;
   for (int64_t cell = 0; cell < ngrid; ++cell) {
     const int lane = (int)(cell & 31);
-    TopkSweeper<HostEnv, KP, MAXN> sw(env, *plan, pool.data(), scratch.data(), lane, ts + cell, ngrid, true);
-    sw.init();
+    TopkSweeper<HostEnv, KP, MAXN> sw(env, *plan, pool.data(), lane, ts + cell, ngrid, true);
     for (int s = -1; s < plan->nsteps; ++s) {
       double a, b;
       int row;

@@ -41,15 +41,17 @@ class ClimPlanStruct(C.Structure):
                 ("step_rec", C.c_void_p), ("q", C.c_double)]
 
 
+SC_MAX_STEPS, SC_REC_WORDS, SC_MAX_FLIP, SC_MAX_PAT, SC_PAT_LEN, SC_MAX_INIT = 366, 12, 768, 16, 48, 32
+
+
 class ClimPlan2Struct(C.Structure):
-    """Mirror of `xmhw_clim_plan2` (include/xmhw_b200.h): the two-stack top-K sweep."""
+    """Mirror of `xmhw_clim_plan2` (include/xmhw_b200.h): the two-stack top-K sweep, one plain host
+    struct that the library copies into the kernel's launch parameters."""
     _fields_ = [("nsteps", C.c_int32), ("kp", C.c_int32), ("max_size", C.c_int32), ("slot_rows", C.c_int32),
-                ("nslots", C.c_int32), ("n_init", C.c_int32), ("pool_rows", C.c_int32), ("reserved_", C.c_int32),
-                ("rows", C.c_void_p), ("atoms", C.c_void_p), ("step_rec", C.c_void_p), ("flip", C.c_void_p),
-                ("q", C.c_double)]
-
-
-PLAN2_ARRAYS = ("rows", "atoms", "step_rec", "flip")
+                ("nslots", C.c_int32), ("n_init", C.c_int32), ("cap", C.c_int32), ("reserved_", C.c_int32),
+                ("q", C.c_double),
+                ("rec", C.c_uint32 * SC_REC_WORDS * SC_MAX_STEPS), ("flip", C.c_uint32 * SC_MAX_FLIP),
+                ("pat", C.c_int32 * SC_PAT_LEN * SC_MAX_PAT), ("init", C.c_uint32 * 2 * SC_MAX_INIT)]
 
 
 INTERMEDIATE_FIELDS = (("events", "f8"), ("seas", "f8"), ("thresh", "f8"), ("relSeas", "f8"),
@@ -72,7 +74,7 @@ _SIGNATURES = {
     "xmhw_clim_sweep_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlanStruct),
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_clim_sweep2_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlan2Struct),
-                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_clim_direct_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_clim_finish_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
@@ -152,22 +154,24 @@ def plan_struct(host_plan, pointers):
     return s
 
 
-def plan2_struct(host_plan, pointers):
-    """Build a ClimPlan2Struct from a plan2.ClimPlan2Host and {array name: address}."""
+def plan2_struct(host_plan):
+    """Build a ClimPlan2Struct (host memory) from a plan2.ClimPlan2Host."""
     s = ClimPlan2Struct()
-    for f in ("nsteps", "kp", "max_size", "slot_rows", "nslots", "n_init", "pool_rows"):
+    for f in ("nsteps", "kp", "max_size", "slot_rows", "nslots", "n_init", "cap"):
         setattr(s, f, int(getattr(host_plan, f)))
     s.q = float(host_plan.q)
-    for name in PLAN2_ARRAYS:
-        setattr(s, name, pointers[name])
+
+    def fill(dst, src):
+        src = np.ascontiguousarray(src)
+        if src.nbytes > C.sizeof(dst):
+            raise ValueError("plan array larger than its slot in xmhw_clim_plan2")
+        C.memmove(C.addressof(dst), src.ctypes.data, src.nbytes)
+
+    fill(s.rec, host_plan.rec.astype(np.uint32))
+    fill(s.flip, host_plan.flip.astype(np.uint32))
+    fill(s.pat, host_plan.pat.astype(np.int32))
+    fill(s.init, host_plan.init.astype(np.uint32))
     return s
-
-
-def numpy_plan2_struct(host_plan):
-    """Plan struct over HOST arrays (used only by the test-side lane emulator)."""
-    keep = {n: np.ascontiguousarray(getattr(host_plan, n)) for n in PLAN2_ARRAYS}
-    s = plan2_struct(host_plan, {n: a.ctypes.data for n, a in keep.items()})
-    return s, keep
 
 
 def numpy_plan_struct(host_plan):

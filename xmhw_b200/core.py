@@ -92,7 +92,6 @@ def device_plan(doy, ndoy, w, q, device):
 @dataclass
 class DevicePlan2:
     host: _plan2.ClimPlan2Host
-    tensors: dict
     struct: _cabi.ClimPlan2Struct
     exc_rows: object            # device int32: window rows of the exceptional doys (CSR by host.exc_off)
 
@@ -114,10 +113,8 @@ def device_plan2(doy, ndoy, w, q, device):
     host = _plan2.build_clim_plan2(doy, ndoy, w, q)
     dp = None
     if host is not None:
-        tensors = {n: torch.from_numpy(np.ascontiguousarray(getattr(host, n))).to(device)
-                   for n in _cabi.PLAN2_ARRAYS}
-        struct = _cabi.plan2_struct(host, {n: _ptr(t) for n, t in tensors.items()})
-        dp = DevicePlan2(host, tensors, struct, torch.from_numpy(np.ascontiguousarray(host.exc_rows)).to(device))
+        dp = DevicePlan2(host, _cabi.plan2_struct(host),
+                         torch.from_numpy(np.ascontiguousarray(host.exc_rows)).to(device))
     if len(_plan_cache) > 16:
         _plan_cache.clear()
     _plan_cache[key] = dp
@@ -192,9 +189,7 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
             alloc = torch.empty if full else (lambda *a, **k: torch.full(*a, float("nan"), **k))
             raw_t = alloc((ndoy, ngrid), dtype=torch.float64, device=ts.device)
             raw_s = alloc((ndoy, ngrid), dtype=torch.float64, device=ts.device)
-            scratch = torch.empty(ncg * h.nslots * 64, dtype=torch.int32, device=ts.device)
-            _call("xmhw_clim_sweep2_f32", _ptr(ts), T, ngrid, dp2.struct, _ptr(raw_t), _ptr(raw_s), _ptr(nempty),
-                  _ptr(scratch), st)
+            _call("xmhw_clim_sweep2_f32", _ptr(ts), T, ngrid, dp2.struct, _ptr(raw_t), _ptr(raw_s), _ptr(nempty), st)
             for k, d in enumerate(h.exc_doy):
                 a, b = int(h.exc_off[k]), int(h.exc_off[k + 1])
                 _call("xmhw_clim_direct_f32", _ptr(ts), T, ngrid, _ptr(dp2.exc_rows) + 4 * a, b - a, h.kp, float(q),

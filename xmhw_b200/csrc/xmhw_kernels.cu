@@ -81,16 +81,15 @@ __global__ void __launch_bounds__(32, MINB) clim_sweep_kernel(
 // ---------------------------------------------------------------------------
 template <int KP, int MAXN, int MINB>
 __global__ void __launch_bounds__(32, MINB) clim_sweep2_kernel(
-    ClimPlan2 p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr, double* __restrict__ seas,
-    int32_t* __restrict__ nempty, uint32_t* __restrict__ scratch) {
+    const __grid_constant__ ClimPlan2 p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr,
+    double* __restrict__ seas, int32_t* __restrict__ nempty) {
   extern __shared__ uint32_t pool[];
   const int lane = threadIdx.x;
   const int64_t cell = (int64_t)blockIdx.x * 32 + lane;
   const bool ok = cell < ngrid;
   const float* col = ts + (ok ? cell : 0);
   WarpEnv env;
-  TopkSweeper<WarpEnv, KP, MAXN> sw(env, p, pool, scratch + (size_t)blockIdx.x * p.nslots * 64, lane, col, ngrid, ok);
-  sw.init();
+  TopkSweeper<WarpEnv, KP, MAXN> sw(env, p, pool, lane, col, ngrid, ok);
   for (int s = -1; s < p.nsteps; ++s) {          // s = -1: initial fill of the first window
     double a, b;
     int row;
@@ -867,17 +866,16 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
 }
 
 int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan2* plan,
-                         double* thresh_raw, double* seas_raw, int32_t* nempty, uint32_t* scratch, void* stream) {
-  if (!ts || !plan || !thresh_raw || !seas_raw || !nempty || !scratch || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
+                         double* thresh_raw, double* seas_raw, int32_t* nempty, void* stream) {
+  if (!ts || !plan || !thresh_raw || !seas_raw || !nempty || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
   if (ngrid > 0xffffffffll || T > 0x7fffffffll) return XMHW_E_ARG;
-  if (plan->nsteps <= 0 || plan->nslots <= 0 || plan->nslots > 32 || plan->slot_rows <= plan->kp ||
-      plan->pool_rows != plan->nslots * plan->slot_rows || plan->max_size <= 0 || plan->max_size > 48 || plan->n_init <= 0 ||
-      !plan->rows || !plan->atoms || !plan->step_rec || !plan->flip)
+  if (plan->nsteps <= 0 || plan->nsteps > SC_MAX_STEPS || plan->nslots <= 0 || plan->nslots > 32 ||
+      plan->cap < plan->kp || plan->slot_rows != plan->cap + 3 || plan->max_size <= 0 || plan->max_size > 48 ||
+      plan->n_init <= 0 || plan->n_init >= SC_MAX_INIT)
     return XMHW_E_PLAN;
-  const size_t smem = (size_t)plan->pool_rows * 128;
+  const size_t smem = (size_t)plan->nslots * plan->slot_rows * 128;
   if (smem > 227 * 1024) return XMHW_E_SMEM;
-  ClimPlan2 p;
-  memcpy(&p, plan, sizeof(p));
+  const ClimPlan2& p = *reinterpret_cast<const ClimPlan2*>(plan);      // copied into the launch parameters
   const int64_t ncg = (ngrid + 31) / 32;
   cudaError_t e;
 #define XMHW_SWEEP2(K, N, B)                                                                                         \
@@ -885,7 +883,7 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
     e = cudaFuncSetAttribute(clim_sweep2_kernel<K, N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     if (e != cudaSuccess) return (int)e;                                                                             \
     clim_sweep2_kernel<K, N, B><<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw,         \
-                                                                                   seas_raw, nempty, scratch);      \
+                                                                                   seas_raw, nempty);               \
   }
   const bool big = plan->max_size > 32;
   switch (plan->kp) {

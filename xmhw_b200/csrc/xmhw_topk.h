@@ -28,69 +28,54 @@
 
 namespace xmhw {
 
-// plan of the two-stack sweep (host side: xmhw_b200/plan2.py; C mirror: xmhw_clim_plan2)
+// Plan of the two-stack sweep (host side: xmhw_b200/plan2.py; C mirror: xmhw_clim_plan2).  The
+// whole plan is ONE plain struct of ~24 KB that travels in the kernel's parameter space
+// (__grid_constant__): every field is read with warp-uniform constant loads that do not touch
+// the load scoreboards the sample prefetch sits on, and there is no plan array in global memory.
+enum { SC_MAX_STEPS = 366, SC_REC_WORDS = 12, SC_MAX_FLIP = 768, SC_MAX_PAT = 16, SC_PAT_LEN = 48, SC_MAX_INIT = 32 };
 struct ClimPlan2 {
   int32_t nsteps;        // sweep steps (regular doys, in doy order)
-  int32_t kp;            // capacity of the top-K arrays the plan needs (max rank + 1 over all n)
+  int32_t kp;            // capacity of the top-K arrays the plan needs (max rank over all sample counts)
   int32_t max_size;      // rows of the largest atom
-  int32_t slot_rows;     // shared-memory rows per unit slot: 1 (len | guard) + max(kp, unit rows)
+  int32_t slot_rows;     // shared-memory rows per unit slot: 1 (len | guard) + cap + 2 (f64 sum)
   int32_t nslots;        // slots (= units alive at once)
   int32_t n_init;        // atoms pushed before the first step
-  int32_t pool_rows;     // nslots * slot_rows
+  int32_t cap;           // key rows per slot = max(kp, rows of the largest unit)
   int32_t reserved_;
-  const int32_t* rows;       // time indices of all atoms, in push order
-  const int32_t* atoms;      // [natoms][4] atom records in push order (ATOM_*)
-  const int32_t* step_rec;   // [nsteps][32] step records (REC_*)
-  const int32_t* flip;       // flip entries, 2 words each (FLIP_*)
-  double q;                  // quantile in [0,1]; numpy 'linear': v = (n-1) q
+  double q;              // quantile in [0,1]; numpy 'linear': v = (n-1) q
+  uint32_t rec[SC_MAX_STEPS][SC_REC_WORDS];   // step records (REC_*)
+  uint32_t flip[SC_MAX_FLIP];                 // flip entries (FLIP_*)
+  int32_t pat[SC_MAX_PAT][SC_PAT_LEN];        // row patterns: time index of row i of an atom = first row + pat[id][i]
+  uint32_t init[SC_MAX_INIT][2];              // atoms of the first window, then the first atom pushed by the sweep
 };
 
-// atom record: 4 words
-enum { ATOM_ROWS_OFF = 0,   // offset of its time indices in plan.rows
-       ATOM_SIZE = 1,       // rows | JOB_F_* flags << 8
-       ATOM_DEST = 2,       // first pool row of its stash | slot base row << 16
-       ATOM_SLOT = 3,       // slot index (scratch rows 2 slot, 2 slot + 1 hold the unit's f64 sum)
-       ATOM_WORDS = 4 };
-
-// step record: 32 words, loaded with one coalesced warp load one step ahead
-enum { REC_COUNTS = 0,      // n_pop | n_push << 4 | flip_after_push << 8 | n_flip << 16
-       REC_FLIP_OFF = 1,    // first flip entry (index into plan.flip / 2)
-       REC_FRONT = 2,       // slot base row of the front array used by this step's query
-       REC_OUT = 3,         // output row (doy - 1)
-       REC_POP = 4,         // 4 words: slot base row | slot index << 16
-       REC_PUSH = 8,        // 3 x ATOM_WORDS
-       REC_NEXT = 20,       // 3 x 2 words: (rows offset, size) of the atom to prefetch after push j (size 0: none)
-       REC_ALIVE = 26,      // bit mask of the slots alive at the query (sum rebuild for non-finite samples)
-       REC_WORDS = 32, REC_MAX_POP = 4, REC_MAX_PUSH = 3 };
-
-// flip entry: 2 words
-enum { FLIP_SRC = 0,        // first pool row of the stashed atom | rows << 16 | JOB_F_* flags << 24
-       FLIP_SLOT = 1 };     // slot base row the accumulator is stored to (JOB_F_STORE / JOB_F_STOREP)
+// atom descriptor, 2 words:
+//   word 0  first row [0:24] | rows [24:30] | JOB_F_COPY, JOB_F_FIRST [30:32]
+//   word 1  pattern [0:5] | slot [5:10] | key-row offset in the slot [10:17] | ragged [17] (rows != size class)
+// step record, SC_REC_WORDS words:
+//   word 0  n_pop [0:3] | n_push [3:5] | flip after the pushes [5] | n_flip [6:12] | front slot [12:17] | output row [17:32]
+//   word 1  popped slots, 5 bits each        word 2  bit mask of the slots alive at the query
+//   word 3  first flip entry                 words 4..9  up to 3 pushed atoms
+//   words 10, 11  the atom pushed after this step's last push (prefetch target; rows 0 = none)
+// flip entry, 1 word: source slot [0:5] | key-row offset [5:12] | rows [12:18] | JOB_F_* [18:24] | destination slot [24:29]
+enum { REC_POPS = 1, REC_ALIVE = 2, REC_FLIP_OFF = 3, REC_PUSH = 4, REC_NEXT = 10 };
 
 // job flags (pushes and flip entries)
 enum { JOB_F_COPY = 1,      // the accumulator is empty: accumulator := this list (first push after a flip / first of a chain)
        JOB_F_FIRST = 2,     // push: first atom of its unit (initialises the slot's len row and f64 sum)
        JOB_F_STORE = 4,     // flip: store the accumulator over the unit's slot after merging this atom
        JOB_F_STOREP = 8,    // flip, no atom: store the accumulator as it is (the oldest unit's array = everything pushed)
-       JOB_F_CLEAR = 16 };  // flip, no atom: accumulator := empty
+       JOB_F_CLEAR = 16,    // flip, no atom: accumulator := empty
+       JOB_F_RAGGED = 32 }; // the atom has fewer rows than its size class: predicated stash stores / loads
 
 #define XMHW_GUARD 0xffffff00u          // len row = guard | len: above every real key (key(+inf) = 0xff800000)
 
 template <int N> XMHW_HD void bitonic_valley_desc(uint32_t (&k)[N]);
-#define XMHW_BITONIC_IMPL(N)                                              \
-  template <> XMHW_HD void bitonic_valley_desc<N>(uint32_t (&k)[N]) {     \
-    XMHW_BITONIC_##N                                                      \
-    const int perm[N] = XMHW_BITONIC_PERM_##N;                            \
-    uint32_t t[N];                                                        \
-    _Pragma("unroll") for (int i = 0; i < N; ++i) t[i] = k[perm[i]];      \
-    _Pragma("unroll") for (int i = 0; i < N; ++i) k[i] = t[i];            \
-  }
-XMHW_BITONIC_IMPL(8)
-XMHW_BITONIC_IMPL(16)
-XMHW_BITONIC_IMPL(24)
-XMHW_BITONIC_IMPL(36)
-XMHW_BITONIC_IMPL(48)
-#undef XMHW_BITONIC_IMPL
+template <> XMHW_HD void bitonic_valley_desc<8>(uint32_t (&k)[8]) { XMHW_BITONIC_8 }
+template <> XMHW_HD void bitonic_valley_desc<16>(uint32_t (&k)[16]) { XMHW_BITONIC_16 }
+template <> XMHW_HD void bitonic_valley_desc<24>(uint32_t (&k)[24]) { XMHW_BITONIC_24 }
+template <> XMHW_HD void bitonic_valley_desc<36>(uint32_t (&k)[36]) { XMHW_BITONIC_36 }
+template <> XMHW_HD void bitonic_valley_desc<48>(uint32_t (&k)[48]) { XMHW_BITONIC_48 }
 
 template <> XMHW_HD void sort_desc<30>(uint32_t* k) { XMHW_SORTNET_30 }
 
@@ -108,11 +93,9 @@ XMHW_HD void merge_topk(uint32_t (&A)[KP], const uint32_t (&L)[N]) {
 
 template <class Env, int KP, int MAXN>
 struct TopkSweeper {
-  typedef typename Env::Vec Vec;
   const Env& env;
   const ClimPlan2& p;
   uint32_t* pool;        // this warp's shared-memory rows (32 words each; word = lane)
-  uint32_t* scratch;     // this warp's global rows: f64 sum of every unit (2 rows per slot)
   const int lane;
   const float* col;
   const int64_t ngrid;
@@ -122,33 +105,39 @@ struct TopkSweeper {
   int n;                 // valid samples in the window
   int nzero;             // steps without any sample (feeds the per-cell compaction of the smoothing)
   double wsum;           // f64 sum of the window (+ pushed unit sums, - popped)
-  Vec rec_next;
 
-  XMHW_HD TopkSweeper(const Env& e, const ClimPlan2& pl, uint32_t* po, uint32_t* sc, int ln, const float* c,
-                      int64_t ng, bool k)
-      : env(e), p(pl), pool(po), scratch(sc), lane(ln), col(c), ngrid(ng), ok(k), n(0), nzero(0), wsum(0.0) {}
+  XMHW_HD TopkSweeper(const Env& e, const ClimPlan2& pl, uint32_t* po, int ln, const float* c, int64_t ng, bool k)
+      : env(e), p(pl), pool(po), lane(ln), col(c), ngrid(ng), ok(k), n(0), nzero(0), wsum(0.0) {
+#pragma unroll
+    for (int i = 0; i < KP; ++i) A[i] = 0u;
+  }
 
   XMHW_HD uint32_t& at(int row) { return pool[row * 32 + lane]; }
 
-  XMHW_HD void prefetch_rows(const Vec& rv, int size) {
+  // issue the loads of the atom (d0, d1): row i = first row + pattern[i]
+  XMHW_HD void prefetch(uint32_t d0, uint32_t d1) {
     const uint32_t ng32 = (uint32_t)ngrid;
+    const uint32_t first = d0 & 0xffffffu;
+    const int32_t* const pt = p.pat[d1 & 31u];
+    const int size = (int)((d0 >> 24) & 63u);
+    // unconditional loads (rows past the atom repeat its first row and are masked in the job)
     if (MAXN == 32 || size <= 32) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(uint32_t)env.vget(rv, i) * ng32);
+      for (int i = 0; i < 32; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(first + (uint32_t)pt[i]) * ng32);
     } else {
 #pragma unroll
-      for (int i = 0; i < MAXN; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(uint32_t)env.vget(rv, i) * ng32);
+      for (int i = 0; i < MAXN; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(first + (uint32_t)pt[i]) * ng32);
     }
   }
 
   // One list of at most N keys goes into the accumulator.  PUSH: the prefetched atom -- keys, f64
   // sum, register sort, stash in its unit's slot.  Otherwise (flip): a stashed atom read back from
-  // its slot; the accumulator is then stored over the slot when the unit is complete.  Both kinds
-  // share ONE merge site per size class (the merges are the bulk of the code).
+  // its slot.  Both kinds share ONE merge site per size class (the merges are the bulk of the code).
   template <int N>
-  XMHW_HD void job(bool push, int size, int flags, int row, int slot_base, int slot, bool alive) {
+  XMHW_HD void job(bool push, int size, int flags, int slot_base, int off, bool alive) {
     uint32_t k[N];
     bool acc = alive;
+    uint32_t* const srow = pool + (slot_base + 1 + off) * 32 + lane;
     if (push) {
       int len = 0;
       double sum = 0.0;
@@ -162,25 +151,32 @@ struct TopkSweeper {
       }
       acc = env.any(len > 0);
       if (acc) sort_desc<N>(k);
-      uint32_t* const srow = pool + row * 32 + lane;
+      if (flags & JOB_F_RAGGED) {
 #pragma unroll
-      for (int i = 0; i < N; ++i)
-        if (i < size) srow[i * 32] = k[i];
-      uint32_t* const sc = scratch + (size_t)slot * 64 + lane;
-      if (flags & JOB_F_FIRST) {
-        at(slot_base) = XMHW_GUARD | (uint32_t)len;
-        sc[0] = f64_lo(sum); sc[32] = f64_hi(sum);
+        for (int i = 0; i < N; ++i)
+          if (i < size) srow[i * 32] = k[i];
       } else {
-        at(slot_base) = at(slot_base) + (uint32_t)len;
-        const double s2 = f64_from(sc[0], sc[32]) + sum;
-        sc[0] = f64_lo(s2); sc[32] = f64_hi(s2);
+#pragma unroll
+        for (int i = 0; i < N; ++i) srow[i * 32] = k[i];
+      }
+      uint32_t* const lrow = pool + slot_base * 32 + lane;
+      uint32_t* const sum_row = pool + (slot_base + 1 + p.cap) * 32 + lane;
+      if (flags & JOB_F_FIRST) {
+        lrow[0] = XMHW_GUARD | (uint32_t)len;
+        sum_row[0] = f64_lo(sum); sum_row[32] = f64_hi(sum);
+      } else {
+        lrow[0] = lrow[0] + (uint32_t)len;
+        const double s2 = f64_from(sum_row[0], sum_row[32]) + sum;
+        sum_row[0] = f64_lo(s2); sum_row[32] = f64_hi(s2);
       }
       n += len;
       wsum = wsum + sum;
-    } else {
-      const uint32_t* const srow = pool + row * 32 + lane;
+    } else if (flags & JOB_F_RAGGED) {
 #pragma unroll
       for (int i = 0; i < N; ++i) k[i] = i < size ? srow[i * 32] : 0u;
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) k[i] = srow[i * 32];
     }
     if (flags & JOB_F_COPY) {
 #pragma unroll
@@ -192,97 +188,84 @@ struct TopkSweeper {
 
   XMHW_HD void store_acc(int slot_base, bool alive) {
     uint32_t* const srow = pool + (slot_base + 1) * 32 + lane;
+    if (alive) {
 #pragma unroll
-    for (int i = 0; i < KP; ++i) srow[i * 32] = alive ? A[i] : 0u;
+      for (int i = 0; i < KP; ++i) srow[i * 32] = A[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < KP; ++i) srow[i * 32] = 0u;
+    }
   }
 
   // Pops, then the step's jobs (a flip's entries before or after the pushes), then the query.
-  // s = -1 is the initial fill: the atoms of the first window, read from the plan's atom array.
+  // s = -1 is the initial fill: the atoms of the first window (plan.init).
   XMHW_HD void step(int s, double& thresh, double& seas, int& out_row) {
     const bool fill = s < 0;
-    const Vec rec = rec_next;
-    if (s + 1 < p.nsteps) rec_next = env.vload(p.step_rec + (size_t)(s + 1) * REC_WORDS, REC_WORDS, lane);
-    const uint32_t w0 = fill ? 0u : (uint32_t)env.vget(rec, REC_COUNTS);
-    const int n_pop = (int)(w0 & 15u), n_push = fill ? p.n_init : (int)((w0 >> 4) & 15u), n_flip = (int)(w0 >> 16);
-    const bool flip_late = ((w0 >> 8) & 1u) != 0u;
-    out_row = fill ? 0 : env.vget(rec, REC_OUT);
+    const uint32_t* const rec = p.rec[fill ? 0 : s];
+    const uint32_t w0 = fill ? 0u : rec[0];
+    const int n_pop = (int)(w0 & 7u), n_push = fill ? p.n_init : (int)((w0 >> 3) & 3u), n_flip = (int)((w0 >> 6) & 63u);
+    const bool flip_late = ((w0 >> 5) & 1u) != 0u;
+    const int front_base = (int)((w0 >> 12) & 31u) * p.slot_rows;
+    out_row = (int)(w0 >> 17);
     // pops: only the unit's sample count and sum leave the window (its keys live in no summary
     // that is still used: the front arrays are suffixes, the accumulator is younger)
     double psum = 0.0;
-    for (int j = 0; j < n_pop; ++j) {
-      const uint32_t pw = (uint32_t)env.vget(rec, REC_POP + j);
-      n -= (int)(at((int)(pw & 0xffffu)) & 0xffu);
-      const uint32_t* sc = scratch + (size_t)(pw >> 16) * 64 + lane;
-      psum = psum + f64_from(sc[0], sc[32]);
+    {
+      const uint32_t pw = fill ? 0u : rec[REC_POPS];
+      for (int j = 0; j < n_pop; ++j) {
+        const int sb = (int)((pw >> (5 * j)) & 31u) * p.slot_rows;
+        n -= (int)(at(sb) & 0xffu);
+        psum = psum + f64_from(at(sb + 1 + p.cap), at(sb + 2 + p.cap));
+      }
     }
-    // row indices of the atom that is prefetched after this step's first push, and the flip
-    // program: requested now so that they are here when needed (no dependent-load wait)
-    int early_size = 0;
-    Vec early_rows = rec;
-    if (fill) {
-      const int off0 = XMHW_LDG(p.atoms + ATOM_ROWS_OFF), size0 = XMHW_LDG(p.atoms + ATOM_SIZE) & 0xff;
-      prefetch_rows(env.vload(p.rows + off0, size0, lane), size0);
-    } else if (n_push > 0) {
-      early_size = env.vget(rec, REC_NEXT + 1);
-      if (early_size > 0) early_rows = env.vload(p.rows + env.vget(rec, REC_NEXT), early_size, lane);
-    }
-    Vec fv = rec;
-    if (n_flip > 0) fv = env.vload(p.flip + 2 * env.vget(rec, REC_FLIP_OFF), 2 * n_flip, lane);
+    if (fill) prefetch(p.init[0][0], p.init[0][1]);
+    const int flip_off = fill ? 0 : (int)rec[REC_FLIP_OFF];
     bool alive = true;
     const int n_jobs = n_push + n_flip;
 #pragma unroll 1
     for (int jb = 0; jb < n_jobs; ++jb) {
       const bool push = flip_late ? jb < n_push : jb >= n_flip;
-      int size, flags, row, slot_base, slot = 0;
+      int size, flags, slot_base, off;
+      uint32_t nx0 = 0u, nx1 = 0u;              // push: the atom to prefetch afterwards
       if (push) {
         const int j = flip_late ? jb : jb - n_flip;
-        int sz, dst;
-        if (fill) {
-          const int32_t* r = p.atoms + (size_t)j * ATOM_WORDS;
-          sz = XMHW_LDG(r + ATOM_SIZE); dst = XMHW_LDG(r + ATOM_DEST); slot = XMHW_LDG(r + ATOM_SLOT);
-        } else {
-          sz = env.vget(rec, REC_PUSH + ATOM_WORDS * j + ATOM_SIZE);
-          dst = env.vget(rec, REC_PUSH + ATOM_WORDS * j + ATOM_DEST);
-          slot = env.vget(rec, REC_PUSH + ATOM_WORDS * j + ATOM_SLOT);
-        }
-        size = sz & 0xff; flags = sz >> 8; row = dst & 0xffff; slot_base = dst >> 16;
+        const uint32_t d0 = fill ? p.init[j][0] : rec[REC_PUSH + 2 * j];
+        const uint32_t d1 = fill ? p.init[j][1] : rec[REC_PUSH + 2 * j + 1];
+        const bool last = j + 1 == n_push;
+        nx0 = fill ? p.init[j + 1][0] : (last ? rec[REC_NEXT] : rec[REC_PUSH + 2 * j + 2]);
+        nx1 = fill ? p.init[j + 1][1] : (last ? rec[REC_NEXT + 1] : rec[REC_PUSH + 2 * j + 3]);
+        size = (int)((d0 >> 24) & 63u);
+        flags = (int)(d0 >> 30) | (int)(((d1 >> 17) & 1u) * JOB_F_RAGGED);
+        slot_base = (int)((d1 >> 5) & 31u) * p.slot_rows;
+        off = (int)((d1 >> 10) & 127u);
       } else {
         const int e = flip_late ? jb - n_push : jb;
         if (e == 0) alive = env.any(n > 0);         // the window as it is when the flip starts
-        const uint32_t f0 = (uint32_t)env.vget(fv, 2 * e + FLIP_SRC);
-        slot_base = env.vget(fv, 2 * e + FLIP_SLOT);
-        row = (int)(f0 & 0xffffu); size = (int)((f0 >> 16) & 0xffu); flags = (int)(f0 >> 24);
+        const uint32_t f0 = p.flip[flip_off + e];
+        slot_base = (int)(f0 & 31u) * p.slot_rows;
+        off = (int)((f0 >> 5) & 127u);
+        size = (int)((f0 >> 12) & 63u);
+        flags = (int)((f0 >> 18) & 63u);
+        const int dst_base = (int)((f0 >> 24) & 31u) * p.slot_rows;
         if (flags & JOB_F_CLEAR) {
 #pragma unroll
           for (int i = 0; i < KP; ++i) A[i] = 0u;
           continue;
         }
-        if (flags & JOB_F_STOREP) { store_acc(slot_base, alive); continue; }
+        if (flags & JOB_F_STOREP) { store_acc(dst_base, alive); continue; }
       }
-      if (size <= 8) job<8>(push, size, flags, row, slot_base, slot, alive);
+      if (size <= 8) job<8>(push, size, flags, slot_base, off, alive);
       else if (MAXN == 32) {
-        if (size <= 30) job<30>(push, size, flags, row, slot_base, slot, alive);
-        else job<32>(push, size, flags, row, slot_base, slot, alive);
+        if (size <= 30) job<30>(push, size, flags, slot_base, off, alive);
+        else job<32>(push, size, flags, slot_base, off, alive);
       }
-      else if (size <= 32) job<(MAXN > 32 ? 32 : 8)>(push, size, flags, row, slot_base, slot, alive);
-      else if (size <= 40) job<(MAXN > 32 ? 40 : 8)>(push, size, flags, row, slot_base, slot, alive);
-      else job<(MAXN > 32 ? 48 : 8)>(push, size, flags, row, slot_base, slot, alive);
+      else if (size <= 32) job<(MAXN > 32 ? 32 : 8)>(push, size, flags, slot_base, off, alive);
+      else if (size <= 40) job<(MAXN > 32 ? 40 : 8)>(push, size, flags, slot_base, off, alive);
+      else job<(MAXN > 32 ? 48 : 8)>(push, size, flags, slot_base, off, alive);
       if (push) {
-        // prefetch the atom pushed next (push order = the plan's atom array)
-        Vec rv = early_rows;
-        int rsize = early_size;
-        if (fill) {
-          const int32_t* nx = p.atoms + (size_t)(jb + 1) * ATOM_WORDS;        // a zero record ends the array
-          rsize = XMHW_LDG(nx + ATOM_SIZE) & 0xff;
-          if (rsize > 0) rv = env.vload(p.rows + XMHW_LDG(nx + ATOM_ROWS_OFF), rsize, lane);
-        } else if (jb != (flip_late ? 0 : n_flip)) {
-          const int j = flip_late ? jb : jb - n_flip;
-          rsize = env.vget(rec, REC_NEXT + 2 * j + 1);
-          if (rsize > 0) rv = env.vload(p.rows + env.vget(rec, REC_NEXT + 2 * j), rsize, lane);
-        }
-        if (rsize > 0) prefetch_rows(rv, rsize);
+        if ((nx0 >> 24) & 63u) prefetch(nx0, nx1);
       } else if (flags & JOB_F_STORE) {
-        store_acc(slot_base, alive);
+        store_acc(slot_base, alive);               // a unit's array lives in the unit's own slot
       }
     }
     if (fill) { thresh = qnan(); seas = qnan(); return; }
@@ -292,13 +275,12 @@ struct TopkSweeper {
     if (!env.any(live)) { thresh = qnan(); seas = qnan(); return; }
     // a non-finite running sum (inf samples) is rebuilt from the sums of the units alive
     if (env.any(!(wsum - wsum == 0.0))) {
-      uint32_t alive_slots = (uint32_t)env.vget(rec, REC_ALIVE);
+      uint32_t alive_slots = rec[REC_ALIVE];
       double fresh = 0.0;
       while (alive_slots) {
-        const int sl = ctz32(alive_slots);
+        const int sb = ctz32(alive_slots) * p.slot_rows;
         alive_slots &= alive_slots - 1u;
-        const uint32_t* sc = scratch + (size_t)sl * 64 + lane;
-        fresh = fresh + f64_from(sc[0], sc[32]);
+        fresh = fresh + f64_from(at(sb + 1 + p.cap), at(sb + 2 + p.cap));
       }
       if (!(wsum - wsum == 0.0)) wsum = fresh;
     }
@@ -317,14 +299,14 @@ struct TopkSweeper {
     // len | guard row sits at S[-1]); rows past the guard are clamped onto it, their terms are
     // dominated.  s_i = S[target-1-i] serves R(target) with A[i-1] and R(target-1) with A[i-2].
     const int kk = target < KP ? target : KP;
-    const uint32_t* const srow = pool + env.vget(rec, REC_FRONT) * 32 + lane;
+    const uint32_t* const srow = pool + front_base * 32 + lane;
+    int woff = kk * 32;                            // word offset of S[target - 1 - i] from the guard row
     uint32_t r1 = 0u, r2 = 0u;
     uint32_t am1 = 0xffffffffu, am2 = 0u;         // A[i-1], A[i-2]
 #pragma unroll
     for (int i = 0; i <= KP; ++i) {
-      int row = kk - i;
-      row = row > 0 ? row : 0;
-      const uint32_t sv = srow[row * 32];
+      const uint32_t sv = srow[woff > 0 ? woff : 0];
+      woff -= 32;
       r1 = umax32(r1, umin32(am1, sv));
       if (i >= 1) r2 = umax32(r2, umin32(am2, sv));
       am2 = am1;
@@ -338,12 +320,6 @@ struct TopkSweeper {
       thresh = qnan();
       seas = qnan();
     }
-  }
-
-  XMHW_HD void init() {
-#pragma unroll
-    for (int i = 0; i < KP; ++i) A[i] = 0u;
-    rec_next = env.vload(p.step_rec, REC_WORDS, lane);
   }
 };
 

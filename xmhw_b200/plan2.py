@@ -26,10 +26,11 @@ import numpy as np
 
 KP_CLASSES = (8, 16, 24, 36, 48)       # top-K capacities the CUDA library instantiates
 MAX_ATOM = 48                          # rows per atom (register sorting network)
-REC_WORDS = 32
-JOB_F_COPY, JOB_F_FIRST, JOB_F_STORE, JOB_F_STOREP, JOB_F_CLEAR = 1, 2, 4, 8, 16      # csrc/xmhw_topk.h
+JOB_F_COPY, JOB_F_FIRST, JOB_F_STORE, JOB_F_STOREP, JOB_F_CLEAR, JOB_F_RAGGED = 1, 2, 4, 8, 16, 32   # csrc/xmhw_topk.h
 MAX_POP, MAX_PUSH = 4, 3
 SMEM_LIMIT = 227 * 1024
+# static sizes of the plan block that travels in the kernel's parameter space (xmhw_clim_plan2)
+SC_MAX_STEPS, SC_REC_WORDS, SC_MAX_FLIP, SC_MAX_PAT, SC_PAT_LEN, SC_MAX_INIT = 366, 12, 768, 16, 48, 32
 
 
 @dataclass
@@ -40,11 +41,12 @@ class ClimPlan2Host:
     slot_rows: int
     nslots: int
     n_init: int
+    cap: int                               # key rows per slot
     pool_rows: int
-    rows: np.ndarray
-    atoms: np.ndarray
-    step_rec: np.ndarray
-    flip: np.ndarray
+    rec: np.ndarray                        # [nsteps][SC_REC_WORDS] uint32 step records
+    flip: np.ndarray                       # [n] uint32 flip entries
+    pat: np.ndarray                        # [npat][SC_PAT_LEN] int32 row patterns (rows of an atom - its first row)
+    init: np.ndarray                       # [n_init + 1][2] uint32 atoms of the first window (+ the first push)
     q: float
     nmax: int
     step_doy: np.ndarray                   # [nsteps] doy label of every sweep step
@@ -56,9 +58,6 @@ class ClimPlan2Host:
 
     def smem_bytes(self):
         return self.pool_rows * 128
-
-    def scratch_rows(self):
-        return 2 * self.nslots
 
 
 LAST_FAIL = {"code": 0}
@@ -189,19 +188,38 @@ def build_clim_plan2(doy, ndoy, w, q):
         unit_of[i:j + 1] = len(units) - 1
         i = j + 1
     unit_rows = [int(sizes[u0:u1].sum()) for u0, u1 in units]
-    slot_rows = 1 + max(kp, max(unit_rows))
-    if slot_rows > 250:
+    cap = max(kp, max(unit_rows))                 # key rows of a slot
+    slot_rows = 1 + cap + 2                       # len | guard row, keys, f64 sum of the unit (lo, hi)
+    if cap > 127:
         return _fail(6)
+    # row patterns: rows of an atom relative to its first row (a handful of distinct ones)
+    pat_id = {}
+    pats = []
+    atom_pat = np.zeros(natoms, np.int64)
+    for i, (_, _, rws) in enumerate(atoms):
+        rel = tuple(int(x) for x in (rws - rws[0]))
+        if rel not in pat_id:
+            pat_id[rel] = len(pats)
+            pats.append(rel)
+        atom_pat[i] = pat_id[rel]
+    if len(pats) > SC_MAX_PAT or max_size > SC_PAT_LEN or nsteps > SC_MAX_STEPS or int(rows_max := max(int(r[2][0]) for r in atoms)) >= (1 << 24):
+        return _fail(17)
 
     # ---- simulate the queue
-    rows_flat = np.concatenate([x[2] for x in atoms]).astype(np.int32)
-    rows_off = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int64)
+    cls = lambda n: 8 if n <= 8 else ((30 if n <= 30 else 32) if maxn == 32 else (32 if n <= 32 else (40 if n <= 40 else 48)))
+
+    def atom_words(i, flags, slot, off):
+        """two-word atom descriptor: first row | size << 24 | flags << 30, pattern | slot << 5 | offset << 10 | ragged << 17"""
+        sz = int(sizes[i])
+        return (int(atoms[i][2][0]) | (sz << 24) | (flags << 30),
+                int(atom_pat[i]) | (slot << 5) | (off << 10) | ((1 if sz != cls(sz) else 0) << 17))
+
     free_slots = []
     nslots = 0
     slot_of_unit = {}
     stash_fill = {}                      # unit -> rows already stashed in its slot
-    atom_rec = np.zeros((natoms + 1, 4), np.int64)      # trailing zero record ends the init list
-    rec = np.zeros((nsteps, REC_WORDS), np.int64)
+    atom_desc = np.zeros((natoms + 1, 2), np.int64)     # trailing zero descriptor: nothing left to prefetch
+    rec = np.zeros((nsteps, SC_REC_WORDS), np.int64)
     flip_entries = []
     front = []                           # units with a front array, oldest first
     back = []                            # units stashed since the last flip, oldest first
@@ -212,7 +230,7 @@ def build_clim_plan2(doy, ndoy, w, q):
     next_pop_unit = 0
 
     def slot_base(u):
-        return slot_of_unit[u] * slot_rows
+        return slot_of_unit[u]           # flip entries / records name slots; the kernel multiplies by slot_rows
 
     def is_partial(u):
         return len(back_atoms[u]) != units[u][1] - units[u][0]
@@ -230,7 +248,7 @@ def build_clim_plan2(doy, ndoy, w, q):
         chain = list(reversed(full))                     # youngest first
         if allow_storep and partial is None:
             # the oldest unit's array = everything pushed since the last flip = the accumulator as it is
-            flip_entries.append((0, 0, JOB_F_STOREP, slot_base(full[0])))
+            flip_entries.append((0, 0, 0, JOB_F_STOREP, slot_base(full[0])))
             chain = chain[:-1]
         first = True
         for u in chain:
@@ -242,16 +260,19 @@ def build_clim_plan2(doy, ndoy, w, q):
                 first = False
                 if m == len(ats) - 1:
                     fl |= JOB_F_STORE
-                flip_entries.append((dest, size, fl, slot_base(u)))
+                if size != cls(size):
+                    fl |= JOB_F_RAGGED
+                flip_entries.append((slot_base(u), dest, size, fl, slot_base(u)))
         front.extend(full)
         back.clear()
         if partial is None:
-            flip_entries.append((0, 0, JOB_F_CLEAR, 0))
+            flip_entries.append((0, 0, 0, JOB_F_CLEAR, 0))
             accumulator_empty = True
         else:
             back.append(partial)
             for m, (dest, size) in enumerate(back_atoms[partial]):
-                flip_entries.append((dest, size, JOB_F_COPY if m == 0 else 0, 0))
+                flip_entries.append((slot_base(partial), dest, size,
+                                     (JOB_F_COPY if m == 0 else 0) | (JOB_F_RAGGED if size != cls(size) else 0), 0))
                 if m:
                     n_merges += 1
             accumulator_empty = False
@@ -281,11 +302,11 @@ def build_clim_plan2(doy, ndoy, w, q):
             accumulator_empty = False
         else:
             n_merges += 1
-        dest = slot_base(u) + 1 + stash_fill[u]
+        dest = stash_fill[u]             # key-row offset inside the slot
         stash_fill[u] += int(sizes[i])
         back_atoms[u].append((dest, int(sizes[i])))
-        r = (int(rows_off[i]), int(sizes[i]) | (flags << 8), dest | (slot_base(u) << 16), slot_of_unit[u])
-        atom_rec[i] = r
+        r = atom_words(i, flags, slot_of_unit[u], dest)
+        atom_desc[i] = r
         return r
 
     def do_pop():
@@ -301,8 +322,9 @@ def build_clim_plan2(doy, ndoy, w, q):
         sl = slot_of_unit.pop(u)
         free_slots.append(sl)
         free_slots.sort()
-        return (sl * slot_rows) | (sl << 16)
+        return sl
 
+    push_idx = []
     try:
         # initial fill: every atom of the first window
         n_init = int(np.searchsorted(a_arr, 0, side="right"))
@@ -336,39 +358,39 @@ def build_clim_plan2(doy, ndoy, w, q):
                     return _fail(10)          # two flips in one step: not representable
                 flip_off, n_flip = do_flip(True)
                 flip_late = 1
-            if not front or n_flip > 32:        # the kernel holds a flip program in one 64-word warp vector
+            if not front or n_flip > 63:
                 return _fail(11)
-            rec[s, 0] = len(pops) | (len(pushes) << 4) | (flip_late << 8) | (n_flip << 16)
-            rec[s, 1] = flip_off
-            rec[s, 2] = slot_base(front[0])
-            rec[s, 3] = regular[s] - 1
-            for j, pw in enumerate(pops):
-                rec[s, 4 + j] = pw
+            rec[s, 0] = (len(pops) | (len(pushes) << 3) | (flip_late << 5) | (n_flip << 6) | (slot_base(front[0]) << 12)
+                         | ((regular[s] - 1) << 17))
+            rec[s, 1] = sum(sl << (5 * j) for j, sl in enumerate(pops))
+            rec[s, 3] = flip_off
             for j, r in enumerate(pushes):
-                rec[s, 8 + 4 * j:12 + 4 * j] = r
-                nx = next_push - (len(pushes) - 1 - j)       # the atom pushed after push j
-                if nx < natoms:
-                    rec[s, 20 + 2 * j] = int(rows_off[nx])
-                    rec[s, 21 + 2 * j] = int(sizes[nx])
+                rec[s, 4 + 2 * j], rec[s, 5 + 2 * j] = r
+            push_idx.append((s, next_push))      # the atom pushed after this step's last push: filled in below
             alive = 0
             for u in front + back:
                 alive |= 1 << slot_of_unit[u]
-            rec[s, 26] = alive
+            rec[s, 2] = alive
             # consistency: the units alive are exactly the window of position s
             expect = {int(unit_of[i]) for i in range(natoms) if a_arr[i] <= s <= b_arr[i]}
             if set(front + back) != expect:
                 return _fail(12)
     except RuntimeError:
         return _fail(13)
-    if nslots > 32:
+    if nslots > 32 or regular[-1] >= (1 << 15):
         return _fail(14)
     pool_rows = nslots * slot_rows
-    if pool_rows * 128 > SMEM_LIMIT or pool_rows >= (1 << 16):
+    if pool_rows * 128 > SMEM_LIMIT or n_init > SC_MAX_INIT - 1 or len(flip_entries) > SC_MAX_FLIP:
         return _fail(15)
-    fl = np.zeros((max(1, len(flip_entries)), 2), np.int64)
-    for k, (src, size, flags, sb) in enumerate(flip_entries):
-        fl[k, 0] = src | (size << 16) | (flags << 24)
-        fl[k, 1] = sb
+    # the descriptor of the atom to prefetch after a step's last push (push order = atom order)
+    for s_, nx in push_idx:
+        rec[s_, 10], rec[s_, 11] = atom_desc[nx]
+    fl = np.zeros(max(1, len(flip_entries)), np.int64)
+    for k, (ssl, soff, size, flags, dsl) in enumerate(flip_entries):
+        fl[k] = ssl | (soff << 5) | (size << 12) | (flags << 18) | (dsl << 24)
+    pat = np.zeros((len(pats), SC_PAT_LEN), np.int32)
+    for k, rel in enumerate(pats):
+        pat[k, :len(rel)] = rel
     # exceptional doys: their window rows, straight from the signatures
     exc_list = sorted(exc_used)
     exc_off = [0]
@@ -381,10 +403,9 @@ def build_clim_plan2(doy, ndoy, w, q):
         if max_rank(max(1, nmax_d), q) > kp:
             return _fail(16)
     return ClimPlan2Host(
-        nsteps=nsteps, kp=kp, max_size=max_size, slot_rows=slot_rows, nslots=nslots, n_init=n_init,
-        pool_rows=pool_rows, rows=rows_flat, atoms=atom_rec.astype(np.uint32).view(np.int32).reshape(-1),
-        step_rec=rec.astype(np.uint32).view(np.int32).reshape(-1),
-        flip=fl.astype(np.uint32).view(np.int32).reshape(-1), q=float(q), nmax=nmax,
+        nsteps=nsteps, kp=kp, max_size=max_size, slot_rows=slot_rows, nslots=nslots, n_init=n_init, cap=cap,
+        pool_rows=pool_rows, rec=rec.astype(np.uint32), flip=fl.astype(np.uint32), pat=pat,
+        init=atom_desc[:n_init + 1].astype(np.uint32), q=float(q), nmax=nmax,
         step_doy=np.asarray(regular, np.int32),
         exc_doy=np.asarray(exc_list, np.int32), exc_off=np.asarray(exc_off, np.int32),
         exc_rows=np.asarray(exc_rows if exc_rows else [0], np.int32),
