@@ -15,6 +15,7 @@ using namespace xmhw;
 struct HostEnv {
   struct Vec { const int32_t* p; int n; };
   bool any(bool p) const { return p; }
+  int max_all(int v) const { return v; }
   Vec vload(const int32_t* src, int count, int) const { return Vec{src, count}; }
   int32_t vget(const Vec& v, int i) const { return i < v.n ? v.p[i] : 0; }
   void vstage(uint32_t* ub, const Vec& v, int m, int m4, int) const {

@@ -96,11 +96,19 @@ class DevicePlan2:
     exc_rows: object            # device int32: window rows of the exceptional doys (CSR by host.exc_off)
 
 
+# The two-stack top-K sweep is chosen when its plan fits AND the top-K capacity is small (high
+# percentiles: pctile 99 needs 5 of 337 keys): there its merges are nearly free.  At pctile 90
+# (36 keys) it measured 65 ms against 55 ms of the general sorted-list sweep on the global grid
+# (profiles/ncu_r02_sweep2_*.txt: one warp per scheduler because the unit slots fill shared memory),
+# so the general sweep stays the default there.
+TOPK_AUTO_MAX_KP = 16
+
+
 def sweep_mode():
-    """Development knob XMHW_B200_SWEEP: "topk" (default: the two-stack top-K sweep when the calendar
-    fits, else the general one) or "general" (always the sorted-list sweep of plan.py)."""
+    """XMHW_B200_SWEEP: "auto" (default, see TOPK_AUTO_MAX_KP), "topk" (the two-stack top-K sweep
+    whenever the calendar fits) or "general" (always the sorted-list sweep of plan.py)."""
     import os
-    return os.environ.get("XMHW_B200_SWEEP", "topk")
+    return os.environ.get("XMHW_B200_SWEEP", "auto")
 
 
 def device_plan2(doy, ndoy, w, q, device):
@@ -181,7 +189,10 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
         q = pctile / 100.0
         ncg = (ngrid + 31) // 32
         nempty = torch.empty(ngrid, dtype=torch.int32, device=ts.device)
-        dp2 = device_plan2(doy, ndoy, windowHalfWidth, q, ts.device) if sweep_mode() == "topk" else None
+        mode = sweep_mode()
+        dp2 = device_plan2(doy, ndoy, windowHalfWidth, q, ts.device) if mode in ("topk", "auto") else None
+        if dp2 is not None and mode == "auto" and dp2.host.kp > TOPK_AUTO_MAX_KP:
+            dp2 = None
         if dp2 is not None:
             # two-stack top-K sweep; rows of the doys it does not cover (absent labels) stay NaN
             h = dp2.host

@@ -23,6 +23,7 @@ struct WarpEnv {
   // small int vector spread over the lanes: entry i lives in lane (i & 31), word (i >> 5)
   struct Vec { int32_t a, b; };
   __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
+  __device__ __forceinline__ int max_all(int v) const { return (int)__reduce_max_sync(0xffffffffu, (unsigned)v); }
   __device__ __forceinline__ Vec vload(const int32_t* src, int count, int lane) const {
     Vec v;
     v.a = lane < count ? __ldg(src + lane) : 0;
@@ -79,17 +80,20 @@ __global__ void __launch_bounds__(32, MINB) clim_sweep_kernel(
 // K1'  two-stack top-K climatology sweep (xmhw_topk.h): one warp = 32 cells, straight-line
 // sorting / merging networks per doy, the unit slots of the window in shared memory.
 // ---------------------------------------------------------------------------
-template <int KP, int MAXN, int MINB>
-__global__ void __launch_bounds__(32, MINB) clim_sweep2_kernel(
+// WPB warps per block: with WPB > 1 the warps of a block step in lockstep (one barrier per doy), so
+// the SM's four resident warps stream the SAME ~30 KB of straight-line code through the 32 KB
+// instruction cache instead of four different positions of it.
+template <int KP, int MAXN, int WPB, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB) clim_sweep2_kernel(
     const __grid_constant__ ClimPlan2 p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr,
     double* __restrict__ seas, int32_t* __restrict__ nempty) {
   extern __shared__ uint32_t pool[];
-  const int lane = threadIdx.x;
-  const int64_t cell = (int64_t)blockIdx.x * 32 + lane;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t cell = ((int64_t)blockIdx.x * WPB + wib) * 32 + lane;
   const bool ok = cell < ngrid;
   const float* col = ts + (ok ? cell : 0);
   WarpEnv env;
-  TopkSweeper<WarpEnv, KP, MAXN> sw(env, p, pool, lane, col, ngrid, ok);
+  TopkSweeper<WarpEnv, KP, MAXN> sw(env, p, pool + (size_t)wib * p.nslots * p.slot_rows * 32, lane, col, ngrid, ok);
   for (int s = -1; s < p.nsteps; ++s) {          // s = -1: initial fill of the first window
     double a, b;
     int row;
@@ -98,6 +102,7 @@ __global__ void __launch_bounds__(32, MINB) clim_sweep2_kernel(
       thr[(int64_t)row * ngrid + cell] = a;
       seas[(int64_t)row * ngrid + cell] = b;
     }
+    if (WPB > 1) __syncthreads();
   }
   if (ok) nempty[cell] = sw.nzero;
 }
@@ -873,28 +878,39 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
       plan->cap < plan->kp || plan->slot_rows != plan->cap + 3 || plan->max_size <= 0 || plan->max_size > 48 ||
       plan->n_init <= 0 || plan->n_init >= SC_MAX_INIT)
     return XMHW_E_PLAN;
-  const size_t smem = (size_t)plan->nslots * plan->slot_rows * 128;
-  if (smem > 227 * 1024) return XMHW_E_SMEM;
+  const size_t smem1 = (size_t)plan->nslots * plan->slot_rows * 128;      // per warp
+  if (smem1 > 227 * 1024) return XMHW_E_SMEM;
+  if ((uint64_t)ngrid * 4u > 0xffffffffull) return XMHW_E_ARG;              // byte offset of a time row in 32 bits
   const ClimPlan2& p = *reinterpret_cast<const ClimPlan2*>(plan);      // copied into the launch parameters
   const int64_t ncg = (ngrid + 31) / 32;
+  // development knob: warps per block (lockstep group).  Default: as many as fit one SM, at most 4.
+  static const int wpb_env = getenv("XMHW_B200_SWEEP2_WPB") ? atoi(getenv("XMHW_B200_SWEEP2_WPB")) : 0;
+  int fit = (int)((227 * 1024) / (smem1 + 256));
+  int wpb = wpb_env > 0 ? wpb_env : (fit >= 4 ? 4 : (fit >= 2 ? 2 : 1));
+  if (wpb != 1 && wpb != 2 && wpb != 4) wpb = 1;
+  if (wpb > fit) wpb = fit >= 2 ? 2 : 1;
+  const size_t smem = smem1 * wpb;
   cudaError_t e;
-#define XMHW_SWEEP2(K, N, B)                                                                                         \
+#define XMHW_SWEEP2_W(K, N, W)                                                                                       \
   {                                                                                                                  \
-    e = cudaFuncSetAttribute(clim_sweep2_kernel<K, N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    e = cudaFuncSetAttribute(clim_sweep2_kernel<K, N, W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return (int)e;                                                                             \
-    clim_sweep2_kernel<K, N, B><<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw,         \
-                                                                                   seas_raw, nempty);               \
+    clim_sweep2_kernel<K, N, W, 1><<<(unsigned)((ncg + W - 1) / W), 32 * W, smem, (cudaStream_t)stream>>>(           \
+        p, ts, ngrid, thresh_raw, seas_raw, nempty);                                                                 \
   }
+#define XMHW_SWEEP2(K, N)                                                                                            \
+  { if (wpb == 4) XMHW_SWEEP2_W(K, N, 4) else if (wpb == 2) XMHW_SWEEP2_W(K, N, 2) else XMHW_SWEEP2_W(K, N, 1) }
   const bool big = plan->max_size > 32;
   switch (plan->kp) {
-    case 8: if (big) XMHW_SWEEP2(8, 48, 4) else XMHW_SWEEP2(8, 32, 6) break;
-    case 16: if (big) XMHW_SWEEP2(16, 48, 4) else XMHW_SWEEP2(16, 32, 6) break;
-    case 24: if (big) XMHW_SWEEP2(24, 48, 4) else XMHW_SWEEP2(24, 32, 5) break;
-    case 36: if (big) XMHW_SWEEP2(36, 48, 3) else XMHW_SWEEP2(36, 32, 4) break;
-    case 48: if (big) XMHW_SWEEP2(48, 48, 3) else XMHW_SWEEP2(48, 32, 3) break;
+    case 8: if (big) XMHW_SWEEP2(8, 48) else XMHW_SWEEP2(8, 32) break;
+    case 16: if (big) XMHW_SWEEP2(16, 48) else XMHW_SWEEP2(16, 32) break;
+    case 24: if (big) XMHW_SWEEP2(24, 48) else XMHW_SWEEP2(24, 32) break;
+    case 36: if (big) XMHW_SWEEP2(36, 48) else XMHW_SWEEP2(36, 32) break;
+    case 48: if (big) XMHW_SWEEP2(48, 48) else XMHW_SWEEP2(48, 32) break;
     default: return XMHW_E_PLAN;
   }
 #undef XMHW_SWEEP2
+#undef XMHW_SWEEP2_W
   return cuda_status();
 }
 

@@ -116,18 +116,14 @@ struct TopkSweeper {
 
   // issue the loads of the atom (d0, d1): row i = first row + pattern[i]
   XMHW_HD void prefetch(uint32_t d0, uint32_t d1) {
-    const uint32_t ng32 = (uint32_t)ngrid;
+    const uint32_t ng4 = (uint32_t)ngrid * 4u;           // bytes per time row (ngrid < 2^30)
     const uint32_t first = d0 & 0xffffffu;
     const int32_t* const pt = p.pat[d1 & 31u];
-    const int size = (int)((d0 >> 24) & 63u);
+    const char* const cb = reinterpret_cast<const char*>(col);
     // unconditional loads (rows past the atom repeat its first row and are masked in the job)
-    if (MAXN == 32 || size <= 32) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(first + (uint32_t)pt[i]) * ng32);
-    } else {
-#pragma unroll
-      for (int i = 0; i < MAXN; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(first + (uint32_t)pt[i]) * ng32);
-    }
+    for (int i = 0; i < MAXN; ++i)
+      pv[i] = XMHW_LDG(reinterpret_cast<const float*>(cb + (uint64_t)(first + (uint32_t)pt[i]) * ng4));
   }
 
   // One list of at most N keys goes into the accumulator.  PUSH: the prefetched atom -- keys, f64
@@ -254,14 +250,9 @@ struct TopkSweeper {
         }
         if (flags & JOB_F_STOREP) { store_acc(dst_base, alive); continue; }
       }
-      if (size <= 8) job<8>(push, size, flags, slot_base, off, alive);
-      else if (MAXN == 32) {
-        if (size <= 30) job<30>(push, size, flags, slot_base, off, alive);
-        else job<32>(push, size, flags, slot_base, off, alive);
-      }
-      else if (size <= 32) job<(MAXN > 32 ? 32 : 8)>(push, size, flags, slot_base, off, alive);
-      else if (size <= 40) job<(MAXN > 32 ? 40 : 8)>(push, size, flags, slot_base, off, alive);
-      else job<(MAXN > 32 ? 48 : 8)>(push, size, flags, slot_base, off, alive);
+      // ONE size class (MAXN keys, shorter atoms padded): a second instantiation of the sort / merge
+      // code in this loop costs register shuffles at every call and doubles the instruction footprint
+      job<MAXN>(push, size, flags, slot_base, off, alive);
       if (push) {
         if ((nx0 >> 24) & 63u) prefetch(nx0, nx1);
       } else if (flags & JOB_F_STORE) {
@@ -296,21 +287,28 @@ struct TopkSweeper {
       target = n - (int)fl;               // rank from the top of s[floor v]; s[floor v + 1] is rank target - 1
     }
     // R(k) = k-th largest of S u A = max_i min(A[i-1], S[k-1-i]), A[-1] = S[-1] = +inf (the slot's
-    // len | guard row sits at S[-1]); rows past the guard are clamped onto it, their terms are
-    // dominated.  s_i = S[target-1-i] serves R(target) with A[i-1] and R(target-1) with A[i-2].
-    const int kk = target < KP ? target : KP;
+    // len | guard row sits at S[-1]; rows past it are clamped onto it, their terms are dominated).  s_i = S[k-1-i]
+    // serves R(k) with A[i-1] and R(k-1) with A[i-2].  The rank k = target differs between lanes
+    // only where samples are missing, so the warp loops over its DISTINCT ranks: inside the loop
+    // every shared-memory row index is warp-uniform (no per-lane addressing).
     const uint32_t* const srow = pool + front_base * 32 + lane;
-    int woff = kk * 32;                            // word offset of S[target - 1 - i] from the guard row
     uint32_t r1 = 0u, r2 = 0u;
-    uint32_t am1 = 0xffffffffu, am2 = 0u;         // A[i-1], A[i-2]
+    int todo = live ? (target < KP ? target : KP) : 0;         // 0: nothing (left) to compute for this lane
+    while (true) {
+      const int kk = env.max_all(todo);
+      if (kk == 0) break;
+      uint32_t q1 = 0u, q2 = 0u;
+      uint32_t am1 = 0xffffffffu, am2 = 0u;                    // A[i-1], A[i-2]
 #pragma unroll
-    for (int i = 0; i <= KP; ++i) {
-      const uint32_t sv = srow[woff > 0 ? woff : 0];
-      woff -= 32;
-      r1 = umax32(r1, umin32(am1, sv));
-      if (i >= 1) r2 = umax32(r2, umin32(am2, sv));
-      am2 = am1;
-      am1 = i < KP ? A[i] : 0u;
+      for (int i = 0; i <= KP; ++i) {
+        const int row = kk - i > 0 ? kk - i : 0;               // warp-uniform; past the guard: dominated terms
+        const uint32_t sv = srow[row * 32];
+        q1 = umax32(q1, umin32(am1, sv));
+        if (i >= 1) q2 = umax32(q2, umin32(am2, sv));
+        am2 = am1;
+        am1 = i < KP ? A[i] : 0u;
+      }
+      if (todo == kk) { r1 = q1; r2 = q2; todo = 0; }
     }
     if (live) {
       const uint32_t kb = target >= 2 ? r2 : r1;

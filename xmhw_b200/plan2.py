@@ -206,13 +206,19 @@ def build_clim_plan2(doy, ndoy, w, q):
         return _fail(17)
 
     # ---- simulate the queue
-    cls = lambda n: 8 if n <= 8 else ((30 if n <= 30 else 32) if maxn == 32 else (32 if n <= 32 else (40 if n <= 40 else 48)))
+    def ragged(i_or_size, off, alone):
+        """The kernel stores / reloads an atom as `maxn` rows (its one size class, zero padded).  That is
+        only right when the atom is alone in its unit's slot and the padded rows fit: otherwise the
+        kernel takes the predicated (exact row count) path."""
+        return 0 if (alone and off + maxn <= cap) else 1
+
+    unit_len = [u1 - u0 for u0, u1 in units]
 
     def atom_words(i, flags, slot, off):
         """two-word atom descriptor: first row | size << 24 | flags << 30, pattern | slot << 5 | offset << 10 | ragged << 17"""
         sz = int(sizes[i])
         return (int(atoms[i][2][0]) | (sz << 24) | (flags << 30),
-                int(atom_pat[i]) | (slot << 5) | (off << 10) | ((1 if sz != cls(sz) else 0) << 17))
+                int(atom_pat[i]) | (slot << 5) | (off << 10) | (ragged(sz, off, unit_len[int(unit_of[i])] == 1) << 17))
 
     free_slots = []
     nslots = 0
@@ -260,7 +266,7 @@ def build_clim_plan2(doy, ndoy, w, q):
                 first = False
                 if m == len(ats) - 1:
                     fl |= JOB_F_STORE
-                if size != cls(size):
+                if ragged(size, dest, len(ats) == 1):
                     fl |= JOB_F_RAGGED
                 flip_entries.append((slot_base(u), dest, size, fl, slot_base(u)))
         front.extend(full)
@@ -272,7 +278,7 @@ def build_clim_plan2(doy, ndoy, w, q):
             back.append(partial)
             for m, (dest, size) in enumerate(back_atoms[partial]):
                 flip_entries.append((slot_base(partial), dest, size,
-                                     (JOB_F_COPY if m == 0 else 0) | (JOB_F_RAGGED if size != cls(size) else 0), 0))
+                                     (JOB_F_COPY if m == 0 else 0) | JOB_F_RAGGED, 0))
                 if m:
                     n_merges += 1
             accumulator_empty = False
