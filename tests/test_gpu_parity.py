@@ -150,6 +150,27 @@ def test_config4_skipna99_winter_blocks(core):
     assert_events_match(ev.to_numpy(), exp, _float_fields())
 
 
+@pytest.mark.parametrize("mode", ["topk", "general"])
+def test_both_sweeps_forced(core, monkeypatch, mode):
+    """The two climatology sweeps (two-stack top-K, csrc/xmhw_topk.h; general sorted lists, csrc/xmhw_lane.h)
+    forced on the same 30-year series incl. land, NaNs and a ragged last warp: bit-equal to the oracle
+    and therefore to each other (the default picks one by the top-K capacity)."""
+    from xmhw_b200 import synth
+    monkeypatch.setenv("XMHW_B200_SWEEP", mode)
+    time = synth.daily_time(1982, 2011)
+    doy = synth.doy366(time)
+    ncell = 200
+    land = synth.land_mask(5, 40).ravel()
+    ts_h = synth.synth_sst(len(time), ncell, synth.season_table(time), land=land, nan_ppm=5000)
+    ts_h[3000:3400, 17] = np.nan
+    core.TRACE = []
+    _clim_check(core, ts_h, doy, 366)
+    names = [n for n, _, _ in core.TRACE]
+    core.TRACE = None
+    assert ("xmhw_clim_sweep2_f32" in names) == (mode == "topk")
+    _clim_check(core, ts_h, doy, 366, pctile=75, windowHalfWidth=2, smoothPercentileWidth=5)
+
+
 def test_pentad_tstep(core):
     """BASELINE config 4(ii): 73 steps/yr, windowHalfWidth=5, smoothPercentileWidth=5, maxGap=1."""
     from xmhw_b200 import synth
