@@ -218,6 +218,10 @@ int xmhw_intermediate_f32(const float* ts, int64_t T, int64_t ngrid, const int32
                           const double* thresh, const double* seas, const int32_t* ev_i32,
                           int64_t nev, int64_t cap, const xmhw_intermediate* out, void* stream);
 
+/* land_check census (identify.py:522-525): nvalid [ngrid] i32 = number of non-NaN samples of every
+ * cell of ts [T][ngrid] (the array is zeroed by the call).                                     */
+int xmhw_count_valid_f32(const float* ts, int64_t T, int64_t ngrid, int32_t* nvalid, void* stream);
+
 /* Pre-step of both public functions (xmhw.py:159-160, :409-410, maxPadLength): in-place linear
  * interpolation along time of interior NaN runs of at most max_pad steps, per cell.        */
 int xmhw_interp_gaps_f32(float* ts, int64_t T, int64_t ngrid, int32_t max_pad, void* stream);

@@ -134,3 +134,42 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("port", "reference-pandas+glue-port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"] == "small"
+
+
+def test_annotate_ds_attribute_table():
+    """identify.py:539-696: per-variable long_name / units, coordinate attributes and the provenance
+    strings, byte for byte (incl. the reference's spelling); when the reference modules are present
+    every long_name of the table is checked against the reference source text."""
+    import re
+    from datetime import date
+    from xmhw_b200.features import EVENT_VARIABLES
+    ds = labeled.Dataset(coords={"events": np.arange(3), "lat": np.zeros(2), "lon": np.zeros(2)})
+    for v in EVENT_VARIABLES:
+        ds[v] = labeled.DataArray(np.zeros((3, 2, 2)), ("events", "lat", "lon"))
+    identify.annotate_ds(ds, {"ts": {"units": "K"}, "lat": {"units": "degrees_north"}}, "mhw")
+    assert ds["intensity_cumulative"].attrs == {"units": "degree_C day",
+                                                "long_name": "MHW cumulative intensity relative to seasonal climatology"}
+    assert ds["rate_onset"].attrs["units"] == "degree_C day-1" and ds["duration_strong"].attrs["units"] == "1"
+    assert ds["intensity_var_abs"].attrs["long_name"] == "MHW intensity variability abosulute magnitude"
+    assert "units" not in ds["category"].attrs and ds["category"].attrs["long_name"].endswith("4: Extreme")
+    assert ds.coord_attrs["events"]["long_name"] == "MHW event identifier: starting index"
+    assert ds.coord_attrs["lat"] == {"units": "degrees_north"}
+    assert ds.attrs["source"] == "xmhw code: https://github.com/coecms/xmhw"
+    assert ds.attrs["title"] == ("Marine heatwave events identified applying the Hobday et al. (2016) "
+                                 "marine heat wave definition")
+    assert ds.attrs["history"] == f"{date.today()}: calculated using xmhw code https://github.com/coecms/xmhw"
+    assert all(ds[v].attrs.get("long_name") for v in EVENT_VARIABLES if not v.startswith(("time_", "index_")))
+    clim = labeled.Dataset(coords={"doy": np.arange(1, 4)})
+    clim["thresh"] = labeled.DataArray(np.zeros(3), ("doy",))
+    clim["seas"] = labeled.DataArray(np.zeros(3), ("doy",))
+    identify.annotate_ds(clim, {"ts": {}}, "clim")
+    assert clim["thresh"].attrs["units"] == "degree_C" and clim.coord_attrs["doy"]["long_name"] == "Day of the year"
+    assert clim.attrs["title"] == ("Seasonal climatology and threshold calculated to detect marine heatwaves "
+                                   "following the  Hobday et al. (2016) definition")
+    from oracle import ref_harness as rh
+    if rh.available():
+        import os
+        src = open(os.path.join(rh.REF_ROOT, "xmhw", "identify.py")).read()
+        joined = re.sub(r'"\s*\n?\s*\+\s*"', "", src)            # adjacent string literals joined with +
+        for name, (long_name, _) in identify.MHW_VARIABLE_ATTRS.items():
+            assert long_name in joined, name

@@ -116,10 +116,15 @@ def test_intermediate_and_maxpad_api(api, oisst):
     assert np.allclose(inter["relSeas"].values, exp["relSeas"][:, 0], equal_nan=True)
     assert np.array_equal(inter["duration_moderate"].values, exp["duration_moderate"][:, 0])
     sst = oisst["sst"].copy()
-    sst[100:103, 1, 2] = np.nan                        # 3-day gap inside the first-year series
+    sst[100:103, 1, 2] = np.nan                        # 3-day gap inside the first-year series: filled
+    sst[300:305, 5, 3] = np.nan                        # 5-day gap: its bounding samples are 6 days apart, NOT filled
     dg = labeled.DataArray(sst, ("time", "lat", "lon"), {"time": oisst["time"], "lat": oisst["lat"], "lon": oisst["lon"]})
     c1 = xmhw.threshold(dg, maxPadLength=5)
-    filled = O.interp_gaps(sst.reshape(len(doy), -1), 5)
+    c2 = xmhw.threshold(dg, maxPadLength=np.timedelta64(5, "D"))       # what xarray wants on a datetime axis
+    assert np.array_equal(c1["thresh"].values, c2["thresh"].values, equal_nan=True)
+    # interpolate_na(max_gap=5): a run of k NaNs is filled iff k + 1 <= 5 (xarray measures coordinate distance)
+    filled = O.interp_gaps(sst.reshape(len(doy), -1), 4)
+    assert np.isnan(filled[300:305, 5 * 4 + 3]).all() and not np.isnan(filled[100:103, 1 * 4 + 2]).any()
     oth, _ = O.threshold(filled, doy, 366)
     ocean = ~np.isnan(oisst["sst"]).all(0)
     assert np.array_equal(c1["thresh"].values.reshape(366, -1),

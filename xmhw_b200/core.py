@@ -152,13 +152,14 @@ def _relabel_keeps_feb(labels):
 
 
 def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercentile=True,
-                     smoothPercentileWidth=31, feb29=True, return_raw=False):
+                     smoothPercentileWidth=31, feb29=True, return_raw=False, return_nempty=False):
     """Climatological threshold and seasonal mean for every cell of ts.
 
     ts   CUDA float32 [T, ngrid] (time-major, the reference's (time, cell) stack)
     doy  host int array [T], 1-based day-of-year labels (identify.py:28-79)
     Returns (thresh, seas): CUDA float64 [ndoy, ngrid]; NaN where a (cell, doy)
     has no sample (land).  Semantics: identify.py:184-270 + :137-181, xmhw.py:250-307.
+    return_nempty appends the int32 [ngrid] number of doys without any sample per cell (== ndoy: land).
     """
     _require_cuda(ts, "ts", torch.float32)
     if ts.dim() != 2:
@@ -176,13 +177,15 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
         sub = threshold_arrays(ts, np.searchsorted(labels, doy) + 1, len(labels), pctile, windowHalfWidth,
                                smoothPercentile, smoothPercentileWidth,
                                feb29=bool(feb29) and ndoy >= 61 and bool(np.isin([59, 60, 61], labels).all())
-                               and _relabel_keeps_feb(labels))
+                               and _relabel_keeps_feb(labels), return_nempty=return_nempty)
         rows = torch.from_numpy(labels - 1).to(ts.device)
         outs = []
-        for a in sub:
+        for a in sub[:2]:
             full = torch.full((ndoy, ngrid), float("nan"), dtype=torch.float64, device=ts.device)
             full[rows] = a
             outs.append(full)
+        if return_nempty:
+            outs.append(sub[2] + (ndoy - len(labels)))
         return tuple(outs)
     with torch.cuda.device(ts.device):
         st = _stream()
@@ -217,11 +220,15 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
         W = int(smoothPercentileWidth) if smoothPercentile else 1
         do_feb = bool(feb29) and ndoy >= 61
         if W <= 1 and not do_feb:
+            if return_nempty:
+                return raw_t, raw_s, nempty
             return (raw_t, raw_s, raw_t, raw_s) if return_raw else (raw_t, raw_s)
         out_t = torch.empty_like(raw_t)
         out_s = torch.empty_like(raw_s)
         _call("xmhw_clim_finish2_f64", _ptr(raw_t), _ptr(out_t), _ptr(raw_s), _ptr(out_s), ndoy, ngrid,
               int(do_feb), W, _ptr(nempty), st)
+    if return_nempty:
+        return out_t, out_s, nempty
     return (out_t, out_s, raw_t, raw_s) if return_raw else (out_t, out_s)
 
 
@@ -373,110 +380,215 @@ def intermediate_arrays(ts, doy, ndoy, thresh, seas, events):
 def threshold_detect_host(ts_host, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercentile=True,
                           smoothPercentileWidth=31, feb29=True, minDuration=5, joinGaps=True, maxGap=2,
                           device="cuda", out=None, slabs=24):
-    """Host-buffer entry point (what the reference-side binding calls): `ts_host` is a pinned
-    host float32 tensor [T, ngrid].  The grid is cut into `slabs` column blocks; the strided
-    host->device copy of block i+1, threshold + detect of block i and the device->host copy of
-    the results of block i-1 overlap on three streams (cells are independent, so blocks are).
-    The copy in dominates (PCIe); what the pipeline adds is the tail after the last block's copy,
-    so more, smaller blocks are better: 920 / 877 / 866 ms with 8 / 16 / 24 blocks at config 3.
-    Returns dict(thresh, seas [ndoy, ngrid] host, nvalid, ev_i32, ev_f64, n_events, byte counts);
+    """Host-buffer entry point for threshold + detect in one pass over the host series (what a
+    reference-side binding calls): see host_pipeline."""
+    return host_pipeline(ts_host, doy, ndoy, do_threshold=True, do_detect=True, pctile=pctile,
+                         windowHalfWidth=windowHalfWidth, smoothPercentile=smoothPercentile,
+                         smoothPercentileWidth=smoothPercentileWidth, feb29=feb29, minDuration=minDuration,
+                         joinGaps=joinGaps, maxGap=maxGap, device=device, out=out, slabs=slabs)
+
+
+def _pin(t):
+    """Page-lock a host tensor in place for the duration of a call (cudaHostRegister) so that the
+    strided column-block copies run asynchronously at full link speed; returns an unregister callable."""
+    if t.is_pinned() or t.numel() * t.element_size() < (64 << 20):
+        return lambda: None
+    rt = torch.cuda.cudart()
+    try:
+        rc = rt.cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+        if int(rc) != 0:
+            return lambda: None
+    except Exception:
+        return lambda: None
+    return lambda: rt.cudaHostUnregister(t.data_ptr())
+
+
+def host_pipeline(ts_host, doy, ndoy, do_threshold=True, do_detect=True, th_host=None, se_host=None,
+                  pctile=90, windowHalfWidth=5, smoothPercentile=True, smoothPercentileWidth=31, feb29=True,
+                  minDuration=5, joinGaps=True, maxGap=2, negate=False, max_pad=0, anynans=False,
+                  device="cuda", out=None, slabs=24):
+    """The hot path on a HOST series: `ts_host` float32 [T, ngrid] (pinned, or page-locked here for the
+    call).  The grid is cut into `slabs` column blocks; the strided host->device copy of block i+1,
+    the kernels of block i and the device->host copy of the results of block i-1 overlap on three
+    streams (cells are independent, so blocks are).  The copy in dominates (PCIe); what the pipeline
+    adds is the tail after the last block's copy, so more, smaller blocks are better: 920 / 877 /
+    866 ms with 8 / 16 / 24 blocks at config 3.
+
+    do_threshold   climatologies from the series (else `th_host` / `se_host` float64 [ndoy, ngrid] are uploaded per block)
+    do_detect      event table (needs climatologies from either source)
+    negate, max_pad, anynans   the public functions' pre-steps on the device block: coldSpells sign flip
+                   (xmhw.py:153-154, :412-413), maxPadLength gap interpolation (:159-160, :409-410), and
+                   cells with any NaN masked out (identify.py:522-525)
+    Returns dict(thresh, seas [ndoy, ngrid] host (do_threshold), nvalid [ngrid] (samples per cell AFTER the
+    pre-steps), nempty [ngrid] (doys without samples, do_threshold), ev_i32, ev_f64, n_events, byte counts);
     `out` may hold preallocated pinned result tensors (thresh, seas, nvalid, ev_i32, ev_f64)."""
     dev = torch.device(device)
     if isinstance(ts_host, np.ndarray):
         ts_host = torch.from_numpy(ts_host)
     if ts_host.dtype != torch.float32 or ts_host.dim() != 2 or not ts_host.is_contiguous():
         raise TypeError("ts_host must be a contiguous float32 [T, ngrid] host tensor")
+    if not do_threshold and do_detect and (th_host is None or se_host is None):
+        raise ValueError("detect without threshold needs th_host and se_host")
     T, ngrid = ts_host.shape
     out = {} if out is None else out
-    pin = ts_host.is_pinned()
+    unpin = [_pin(ts_host)]
+    pin = ts_host.is_pinned() or True
 
-    def host_buf(name, shape, dtype):
-        if name in out and tuple(out[name].shape[:1]) == tuple(shape[:1]) and out[name].shape[-1] >= shape[-1]:
-            return out[name]
-        return torch.empty(shape, dtype=dtype, pin_memory=pin)
+    def host_buf(name, shape, dtype, exact=True):
+        t = out.get(name)
+        if t is not None and t.dtype == dtype and (tuple(t.shape) == tuple(shape) if exact else
+                                                   (tuple(t.shape[:-1]) == tuple(shape[:-1]) and t.shape[-1] >= shape[-1])):
+            return t
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
 
-    th_h = host_buf("thresh", (ndoy, ngrid), torch.float64)
-    se_h = host_buf("seas", (ndoy, ngrid), torch.float64)
+    th_h = host_buf("thresh", (ndoy, ngrid), torch.float64) if do_threshold else None
+    se_h = host_buf("seas", (ndoy, ngrid), torch.float64) if do_threshold else None
     nv_h = host_buf("nvalid", (ngrid,), torch.int32)
+    ne_h = host_buf("nempty", (ngrid,), torch.int32) if do_threshold else None
+    if not do_threshold and do_detect:
+        th_src = th_host if isinstance(th_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(th_host, np.float64))
+        se_src = se_host if isinstance(se_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(se_host, np.float64))
+        if th_src.shape != (ndoy, ngrid) or se_src.shape != (ndoy, ngrid):
+            raise ValueError("th_host / se_host must be [ndoy, ngrid]")
+        unpin += [_pin(th_src), _pin(se_src)]
     w = -(-ngrid // max(1, int(slabs)))
     w = -(-w // 32) * 32
     ranges = [(a, min(ngrid, a + w)) for a in range(0, ngrid, w)]
     ev_parts, ev_parts_all = [], []
-    with torch.cuda.device(dev):
-        main = torch.cuda.current_stream()
-        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-        bufs = [torch.empty((T, w), dtype=torch.float32, device=dev) for _ in range(2)]
-        free_ev = [None, None]
-        loaded = {}
+    nev = 0
+    ei_h = ef_h = None
+    try:
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            bufs = [torch.empty((T, w), dtype=torch.float32, device=dev) for _ in range(2)]
+            cbufs = None
+            if not do_threshold and do_detect:
+                cbufs = [[torch.empty((ndoy, w), dtype=torch.float64, device=dev) for _ in range(2)] for _ in range(2)]
+            s_in.wait_stream(main)          # the buffers were allocated on `main`
+            s_out.wait_stream(main)
+            free_ev = [None, None]
+            loaded = {}
 
-        def start_load(i):
-            a, b = ranges[i]
-            with torch.cuda.stream(s_in):
-                if free_ev[i % 2] is not None:
-                    s_in.wait_event(free_ev[i % 2])
-                dst = bufs[i % 2][:, :b - a] if b - a == w else bufs[i % 2].view(-1)[:T * (b - a)].view(T, b - a)
-                check(lib.xmhw_copy2d_async(_ptr(dst), (b - a) * 4, ts_host.data_ptr() + a * 4, ngrid * 4,
-                                            (b - a) * 4, T, 0, s_in.cuda_stream), "xmhw_copy2d_async")
-                e = torch.cuda.Event()
-                e.record(s_in)
-                loaded[i] = (dst, e)
+            def block_view(buf, rows, n):
+                return buf[:, :n] if n == w else buf.view(-1)[:rows * n].view(rows, n)
 
-        start_load(0)
-        keep_alive = []
-        # event tables stream to the host per block when the caller preallocated them (their
-        # final size is only known at the end); otherwise they are copied after the last block
-        stream_ev = "ev_i32" in out and "ev_f64" in out
-        pos = 0
+            def start_load(i):
+                a, b = ranges[i]
+                with torch.cuda.stream(s_in):
+                    if free_ev[i % 2] is not None:
+                        s_in.wait_event(free_ev[i % 2])
+                    dst = block_view(bufs[i % 2], T, b - a)
+                    check(lib.xmhw_copy2d_async(_ptr(dst), (b - a) * 4, ts_host.data_ptr() + a * 4, ngrid * 4,
+                                                (b - a) * 4, T, 0, s_in.cuda_stream), "xmhw_copy2d_async")
+                    clim = None
+                    if cbufs is not None:
+                        clim = []
+                        for src, cb in ((th_src, cbufs[0][i % 2]), (se_src, cbufs[1][i % 2])):
+                            d = block_view(cb, ndoy, b - a)
+                            check(lib.xmhw_copy2d_async(_ptr(d), (b - a) * 8, src.data_ptr() + a * 8, ngrid * 8,
+                                                        (b - a) * 8, ndoy, 0, s_in.cuda_stream), "xmhw_copy2d_async")
+                            clim.append(d)
+                    e = torch.cuda.Event()
+                    e.record(s_in)
+                    loaded[i] = (dst, clim, e)
 
-        def copy_events(a, e, pos):
-            if e.n:
-                for k in range(EI_COUNT):                   # row by row: contiguous DMAs
-                    ei_h[k, pos:pos + e.n].copy_(e.i32[k, :e.n], non_blocking=True)
-                for k in range(EF_COUNT):
-                    ef_h[k, pos:pos + e.n].copy_(e.f64[k, :e.n], non_blocking=True)
+            start_load(0)
+            keep_alive = []
+            # event tables stream to the host per block when the caller preallocated them (their
+            # final size is only known at the end); otherwise they are copied after the last block
+            stream_ev = do_detect and "ev_i32" in out and "ev_f64" in out
+            pos = 0
 
-        if stream_ev:
-            ei_h, ef_h = out["ev_i32"], out["ev_f64"]
-        for i, (a, b) in enumerate(ranges):
-            if i + 1 < len(ranges):
-                start_load(i + 1)
-            ts, e = loaded.pop(i)
-            main.wait_event(e)
-            th, se = threshold_arrays(ts, doy, ndoy, pctile, windowHalfWidth, smoothPercentile,
-                                      smoothPercentileWidth, feb29)
-            ev = detect_arrays(ts, doy, ndoy, th, se, minDuration, joinGaps, maxGap)
-            if ev.n:
-                ev.i32[0, :ev.n] += a                        # block-local -> global cell ids
-            done = torch.cuda.Event()
-            done.record(main)
-            free_ev[i % 2] = done
-            if stream_ev and pos + ev.n > ei_h.shape[1]:
-                stream_ev = False                            # preallocated table too small: defer
-                ev_parts = ev_parts_all[:]
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(done)
-                for src, dst in ((th, th_h), (se, se_h)):
-                    check(lib.xmhw_copy2d_async(dst.data_ptr() + a * 8, ngrid * 8, _ptr(src), (b - a) * 8,
-                                                (b - a) * 8, ndoy, 1, s_out.cuda_stream), "xmhw_copy2d_async")
-                nv_h[a:b].copy_(ev.nvalid, non_blocking=True)
-                if stream_ev:
-                    copy_events(a, ev, pos)
-            ev_parts_all.append((a, ev))
-            if not stream_ev:
-                ev_parts.append((a, ev))
-            pos += ev.n
-            keep_alive.append((th, se))
-        nev = pos
-        if not stream_ev:
-            ei_h = host_buf("ev_i32", (EI_COUNT, nev), torch.int32)
-            ef_h = host_buf("ev_f64", (EF_COUNT, nev), torch.float64)
-            with torch.cuda.stream(s_out):
-                p2 = 0
-                for a, e in ev_parts:
-                    copy_events(a, e, p2)
-                    p2 += e.n
-        s_out.synchronize()
-        main.synchronize()
-    return {"thresh": th_h, "seas": se_h, "nvalid": nv_h, "ev_i32": ei_h[:, :nev], "ev_f64": ef_h[:, :nev],
-            "n_events": nev, "h2d_bytes": T * ngrid * 4,
-            "d2h_bytes": 2 * ndoy * ngrid * 8 + ngrid * 4 + nev * (EI_COUNT * 4 + EF_COUNT * 8)}
+            def copy_events(e, pos):
+                if e.n:
+                    for k in range(EI_COUNT):                   # row by row: contiguous DMAs
+                        ei_h[k, pos:pos + e.n].copy_(e.i32[k, :e.n], non_blocking=True)
+                    for k in range(EF_COUNT):
+                        ef_h[k, pos:pos + e.n].copy_(e.f64[k, :e.n], non_blocking=True)
+
+            if stream_ev:
+                ei_h, ef_h = out["ev_i32"], out["ev_f64"]
+            for i, (a, b) in enumerate(ranges):
+                if i + 1 < len(ranges):
+                    start_load(i + 1)
+                ts, clim, e = loaded.pop(i)
+                main.wait_event(e)
+                # land_check comes first in the reference (xmhw.py:138, :399), on the data as given
+                nvalid = None
+                if anynans or not do_detect:
+                    nvalid = count_valid(ts)
+                if anynans:                                       # a cell with any NaN produces no output
+                    ts.masked_fill_((nvalid != T).unsqueeze(0), float("nan"))
+                    nvalid = torch.where(nvalid == T, nvalid, torch.zeros_like(nvalid))
+                if negate:
+                    ts.neg_()
+                if max_pad:
+                    interp_gaps_(ts, max_pad)
+                th = se = nempty = None
+                if do_threshold:
+                    th, se, nempty = threshold_arrays(ts, doy, ndoy, pctile, windowHalfWidth, smoothPercentile,
+                                                      smoothPercentileWidth, feb29, return_nempty=True)
+                else:
+                    th, se = clim if clim is not None else (None, None)
+                ev = None
+                if do_detect:
+                    ev = detect_arrays(ts, doy, ndoy, th, se, minDuration, joinGaps, maxGap)
+                    if ev.n:
+                        ev.i32[0, :ev.n] += a                    # block-local -> global cell ids
+                    if nvalid is None:
+                        nvalid = ev.nvalid
+                done = torch.cuda.Event()
+                done.record(main)
+                free_ev[i % 2] = done
+                if stream_ev and pos + ev.n > ei_h.shape[1]:
+                    stream_ev = False                            # preallocated table too small: defer
+                    ev_parts = ev_parts_all[:]
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(done)
+                    if do_threshold:
+                        for src, dst in ((th, th_h), (se, se_h)):
+                            check(lib.xmhw_copy2d_async(dst.data_ptr() + a * 8, ngrid * 8, _ptr(src), (b - a) * 8,
+                                                        (b - a) * 8, ndoy, 1, s_out.cuda_stream), "xmhw_copy2d_async")
+                        ne_h[a:b].copy_(nempty, non_blocking=True)
+                    nv_h[a:b].copy_(nvalid, non_blocking=True)
+                    if stream_ev:
+                        copy_events(ev, pos)
+                if do_detect:
+                    ev_parts_all.append(ev)
+                    if not stream_ev:
+                        ev_parts.append(ev)
+                    pos += ev.n
+                keep_alive.append((th, se, nvalid, nempty))
+            nev = pos
+            if do_detect and not stream_ev:
+                ei_h = host_buf("ev_i32", (EI_COUNT, nev), torch.int32, exact=False)
+                ef_h = host_buf("ev_f64", (EF_COUNT, nev), torch.float64, exact=False)
+                with torch.cuda.stream(s_out):
+                    p2 = 0
+                    for e in ev_parts:
+                        copy_events(e, p2)
+                        p2 += e.n
+            s_out.synchronize()
+            main.synchronize()
+    finally:
+        for u in unpin:
+            u()
+    res = {"nvalid": nv_h, "n_events": nev, "h2d_bytes": T * ngrid * 4 + (0 if do_threshold or not do_detect else 2 * ndoy * ngrid * 8),
+           "d2h_bytes": (2 * ndoy * ngrid * 8 + ngrid * 4 if do_threshold else 0) + ngrid * 4
+           + nev * (EI_COUNT * 4 + EF_COUNT * 8)}
+    if do_threshold:
+        res.update(thresh=th_h, seas=se_h, nempty=ne_h)
+    if do_detect:
+        res.update(ev_i32=ei_h[:, :nev], ev_f64=ef_h[:, :nev])
+    return res
+
+
+def count_valid(ts):
+    """Non-NaN samples per cell of a CUDA float32 [T, ngrid] block (land_check, identify.py:522-525)."""
+    _require_cuda(ts, "ts", torch.float32)
+    T, ngrid = ts.shape
+    nvalid = torch.empty(ngrid, dtype=torch.int32, device=ts.device)
+    with torch.cuda.device(ts.device):
+        _call("xmhw_count_valid_f32", _ptr(ts), T, ngrid, _ptr(nvalid), _stream())
+    return nvalid

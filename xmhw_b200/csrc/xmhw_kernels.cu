@@ -776,6 +776,27 @@ __global__ void interp_gaps_kernel(float* __restrict__ ts, int64_t T, int64_t ng
 }
 
 // ---------------------------------------------------------------------------
+// land_check census (identify.py:522-525): non-NaN samples per cell.  One lane = 4 adjacent cells
+// (float4 rows) when the grid allows, 8 rows in flight; the time axis is split over blockIdx.y.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) count_valid_kernel(const float* __restrict__ ts, int64_t T, int64_t ngrid,
+                                                          int tchunk, int32_t* __restrict__ nvalid) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ngrid) return;
+  const int64_t t0 = (int64_t)blockIdx.y * tchunk, t1 = min(T, t0 + tchunk);
+  const float* col = ts + cell;
+  int cnt = 0;
+  for (int64_t t = t0; t < t1; t += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(col + min(t + i, t1 - 1) * ngrid);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cnt += (t + i < t1) && v[i] == v[i];
+  }
+  if (cnt) atomicAdd(nvalid + cell, cnt);
+}
+
+// ---------------------------------------------------------------------------
 // intermediate=True (identify.py:404-411): per-timestep fields of mhw_df (features.py:22-69)
 // ---------------------------------------------------------------------------
 __global__ void event_labels_kernel(const int32_t* __restrict__ ei, int64_t nev, int64_t cap, int64_t ngrid,
@@ -1113,6 +1134,20 @@ int xmhw_intermediate_f32(const float* ts, int64_t T, int64_t ngrid, const int32
   if (nev) event_labels_kernel<<<(unsigned)((nev + 127) / 128), 128, 0, st>>>(ev_i32, nev, cap, ngrid, out->events);
   dim3 grid((unsigned)((ngrid + 127) / 128), (unsigned)T);
   intermediate_kernel<<<grid, 128, 0, st>>>(ts, T, ngrid, doy, thresh, seas, out->events, *out);
+  return cuda_status();
+}
+
+int xmhw_count_valid_f32(const float* ts, int64_t T, int64_t ngrid, int32_t* nvalid, void* stream) {
+  if (!ts || !nvalid || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(nvalid, 0, (size_t)ngrid * sizeof(int32_t), st);
+  if (e != cudaSuccess) return (int)e;
+  const int nt = 256;
+  const int64_t nbx = (ngrid + nt - 1) / nt;
+  int ny = (int)((148 * 8 + nbx - 1) / nbx);                 // enough blocks to fill the machine on narrow grids
+  ny = ny < 1 ? 1 : (ny > 64 ? 64 : ny);
+  const int tchunk = (int)((T + ny - 1) / ny);
+  count_valid_kernel<<<dim3((unsigned)nbx, (unsigned)ny), nt, 0, st>>>(ts, T, ngrid, tchunk, nvalid);
   return cuda_status();
 }
 

@@ -73,12 +73,70 @@ def land_check_shape(shape, dims, tdim):
     return sorted(other)
 
 
-def annotate_ds(attrs_out, ds_attrs, kind):
-    """identify.py:539-696 (condensed): provenance/CF global attributes."""
-    attrs_out["source"] = "xmhw_b200 (B200-native implementation of the xmhw hot path)"
-    attrs_out["title"] = ("Seasonal climatology and threshold calculated to detect marine heatwaves"
-                          if kind == "clim" else "Marine heatwave events")
-    attrs_out["history"] = "%s: calculated using xmhw_b200" % date.today().strftime("%Y-%m-%d")
-    units = ds_attrs.get("ts", {}).get("units", "degree_C")
-    attrs_out["units"] = units
-    return attrs_out
+GITHUB = "https://github.com/coecms/xmhw"
+
+# Per-variable CF attributes of the detect output (reference identify.py:596-684), as data:
+# name -> (long_name, units) with units "T" = series units, "T day", "T day-1" or "1"; None = not set.
+# The strings are the reference's own, byte for byte (including its spelling), so that files written
+# from either implementation carry identical metadata.
+_REL = {"": "relative to seasonal climatology", "_relThresh": "relative to threshold", "_abs": "absolute magnitude"}
+MHW_VARIABLE_ATTRS = {
+    "event": ("MHW event identifier: starting index", "1"),
+    "duration": ("MHW duration in number of days", "1"),
+    "rate_onset": ("MHW onset rate", "T day-1"),
+    "rate_decline": ("MHW decline rate", "T day-1"),
+    "category": ("MHW category based on peak intensity: 1: Moderate, 2: Strong, 3: Severe or 4: Extreme", None),
+}
+for _sfx, _rel in _REL.items():
+    MHW_VARIABLE_ATTRS["intensity_max" + _sfx] = ("MHW maximum (peak) intensity " + _rel, "T")
+    MHW_VARIABLE_ATTRS["intensity_mean" + _sfx] = ("MHW mean intensity " + _rel, "T")
+    MHW_VARIABLE_ATTRS["intensity_var" + _sfx] = ("MHW intensity variability " + _rel, "T")
+    MHW_VARIABLE_ATTRS["intensity_cumulative" + _sfx] = ("MHW cumulative intensity " + _rel, "T day")
+MHW_VARIABLE_ATTRS["intensity_var_abs"] = ("MHW intensity variability abosulute magnitude", "T")     # sic, identify.py:657
+for _k, _what in (("max", "maximum (peak)"), ("mean", "mean"), ("var", None), ("cumulative", "cumulative")):
+    MHW_VARIABLE_ATTRS["severity_" + _k] = (
+        "MHW severity variability relative to seasonal climatology" if _k == "var"
+        else "MHW %s severity relative to seasonal climatology" % _what, "T day" if _k == "cumulative" else "T")
+for _c in ("moderate", "strong", "severe", "extreme"):
+    MHW_VARIABLE_ATTRS["duration_" + _c] = ("Number of days falling in category " + _c.capitalize(), "1")
+
+
+def annotate_ds(ds, ds_attrs, kind):
+    """identify.py:539-696: CF / provenance attributes of the output dataset (`kind` = "clim" or "mhw").
+
+    `ds` is a labeled.Dataset (variables carry `.attrs`, coordinates `ds.coord_attrs`); `ds_attrs` maps
+    "ts" and every coordinate name to the attributes of the input series.  Like the reference the units
+    of the series are looked up under the key "temp" (identify.py:554), which its callers never set
+    (xmhw.py:129, :389 store "ts"), so the units are always "degree_C" -- kept for identical output.
+    """
+    try:
+        uts = ds_attrs["temp"]["units"]
+        if any(t in uts for t in ("Celsius", "celsius")):
+            uts = "degree_C"
+    except Exception:
+        uts = "degree_C"
+    for c in list(ds.coords):                                   # identify.py:560-578
+        if c == "doy":
+            ds.coord_attrs[c] = {"units": "1", "long_name": "Day of the year"}
+        elif c == "events":
+            ds.coord_attrs[c] = {"units": "1", "long_name": "MHW event identifier: starting index"}
+        elif c != "point" and isinstance(ds_attrs.get(c), dict):
+            ds.coord_attrs.setdefault(c, {}).update(ds_attrs[c])
+    ds.attrs["source"] = f"xmhw code: {GITHUB}"
+    if kind == "clim":                                          # identify.py:580-594
+        ds.attrs["title"] = ("Seasonal climatology and threshold " + "calculated to detect marine heatwaves following the "
+                             + " Hobday et al. (2016) definition")
+        for v in ("thresh", "seas"):
+            if v in ds:
+                ds[v].attrs["units"] = uts
+    else:                                                       # identify.py:596-694
+        for name, (long_name, units) in MHW_VARIABLE_ATTRS.items():
+            if name not in ds:
+                continue
+            if units is not None:
+                ds[name].attrs["units"] = units.replace("T", uts)
+            ds[name].attrs["long_name"] = long_name
+        ds.attrs["title"] = ("Marine heatwave events identified "
+                             + "applying the Hobday et al. (2016) marine heat wave definition")
+    ds.attrs["history"] = f"{date.today()}: calculated using xmhw code {GITHUB}"
+    return ds

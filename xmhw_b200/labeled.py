@@ -42,6 +42,7 @@ class Dataset:
         self.data_vars = dict(data_vars or {})
         self.coords = {k: np.asarray(v) for k, v in (coords or {}).items()}
         self.attrs = dict(attrs or {})
+        self.coord_attrs = {}             # coordinate name -> attributes (identify.annotate_ds)
 
     def __getitem__(self, k):
         return self.data_vars[k]
@@ -85,5 +86,8 @@ def to_xarray(ds):
     for k, v in ds.coords.items():
         if k not in out.coords and np.ndim(v) == 0:
             out = out.assign_coords({k: v})
+    for k, a in getattr(ds, "coord_attrs", {}).items():
+        if k in out.coords:
+            out[k].attrs.update(a)
     out.attrs.update(ds.attrs)
     return out

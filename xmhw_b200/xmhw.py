@@ -53,7 +53,53 @@ def _unpack(temp, tdim):
         coords[d] = np.arange(n) if c is None else c
     enc = getattr(getattr(temp, "coords", {}).get(tdim, None), "encoding", None) or getattr(temp, "encoding", {})
     tattrs = getattr(getattr(temp, "coords", {}).get(tdim, None), "attrs", None) or {}
+    # attributes of every coordinate of the input (xmhw.py:130-131, :390-391): xarray coordinates carry
+    # `.attrs`, the light containers an optional `coord_attrs` dict
+    cattrs = {}
+    for d in dims:
+        a = getattr(getattr(temp, "coords", {}).get(d, None), "attrs", None)
+        if not a:
+            a = getattr(temp, "coord_attrs", {}).get(d)
+        if a:
+            cattrs[d] = dict(a)
+    _unpack.last_coord_attrs = cattrs
     return np.ascontiguousarray(data), time, other, coords, dict(getattr(temp, "attrs", {})), enc, tattrs
+
+
+def _pad_steps(maxPadLength, time):
+    """Longest NaN run (in time steps) that `ts.interpolate_na(dim=tdim, max_gap=maxPadLength)` fills
+    (xmhw.py:159-160, :409-410).  xarray measures a gap as the COORDINATE DISTANCE between the valid
+    samples that bound it, so a run of k NaNs on a regular axis has length (k + 1) steps and is filled
+    when (k + 1) * step <= max_gap.  A number counts time steps; a timedelta-like value (what current
+    xarray requires on a datetime axis) is divided by the step of the axis."""
+    if not maxPadLength:
+        return 0
+    n = maxPadLength
+    if not isinstance(n, (int, float, np.integer, np.floating)):
+        t = np.asarray(time)
+        if not np.issubdtype(t.dtype, np.datetime64) or len(t) < 2:
+            raise XmhwException("a timedelta-like maxPadLength needs a datetime time axis")
+        step = np.median(np.diff(t)).astype("timedelta64[s]").astype(np.int64)
+        try:
+            secs = np.timedelta64(n).astype("timedelta64[s]").astype(np.int64)
+        except (TypeError, ValueError):
+            secs = int(n.total_seconds())
+        n = secs / max(1, step)
+    return max(0, int(np.floor(n)) - 1)
+
+
+def _all_land(flat):
+    """True when no sample at all is valid (identify.py:527-528), found without a pass over the array:
+    the scan stops at the first time row that holds a valid value (row 0 for any real data set)."""
+    for t0 in range(0, flat.shape[0], 64):
+        if not np.isnan(flat[t0:t0 + 64]).all():
+            return False
+    return True
+
+
+def _slabs(flat):
+    """Column blocks of the host pipeline: ~1 GB of series per block, at least one, at most 32."""
+    return int(min(32, max(1, flat.nbytes >> 30)))
 
 
 def _wrap(ds, like):
@@ -90,6 +136,7 @@ def threshold(temp, tdim="time", climatologyPeriod=[None, None], pctile=90, wind
     if smoothPercentileWidth % 2 == 0:                         # xmhw.py:103-104
         raise XmhwException("smoothPercentileWidth should be odd")
     data, time, other, coords, attrs, enc, tattrs = _unpack(temp, tdim)   # xmhw.py:105-109
+    cattrs = _unpack.last_coord_attrs
     if all(climatologyPeriod):                                 # xmhw.py:112-119
         from .identify import _ymd
         years = _ymd(time)[0]
@@ -103,23 +150,24 @@ def threshold(temp, tdim="time", climatologyPeriod=[None, None], pctile=90, wind
     doy, ndoy = add_doy(time, keep_tstep=tstep)                # xmhw.py:145
     grid_shape = data.shape[1:]
     T = data.shape[0]
-    flat = data.reshape(T, -1)
-    nan = np.isnan(flat)
-    ocean = ~nan.any(axis=0) if anynans else ~nan.all(axis=0)  # identify.py:522-525
-    if not point and not ocean.any():
+    flat = np.ascontiguousarray(data.reshape(T, -1))
+    if not point and _all_land(flat):
         raise XmhwException("All points of grid are either land or NaN")   # identify.py:527-528
     if not torch.cuda.is_available():
         raise RuntimeError("xmhw_b200 needs a CUDA device (there is no CPU path)")
-    ts = torch.from_numpy(np.ascontiguousarray(flat)).cuda()
-    if coldSpells:                                             # xmhw.py:153-154
-        ts = -ts
-    if maxPadLength:                                           # xmhw.py:159-160
-        core.interp_gaps_(ts, maxPadLength)
-    if anynans:                                                # dropped cells produce no output
-        ts[:, torch.from_numpy(~ocean).cuda()] = float("nan")
-    th, se = core.threshold_arrays(ts, doy, ndoy, pctile, windowHalfWidth, smoothPercentile,
-                                   smoothPercentileWidth, feb29=not tstep)
-    th_h, se_h = th.cpu().numpy(), se.cpu().numpy()
+    # one pipelined pass over the host series (column blocks: copy in / kernels / copy out overlap);
+    # the land census (identify.py:522-525) comes back from the device, no host pass over the array
+    try:
+        res = core.host_pipeline(torch.from_numpy(flat), doy, ndoy, do_threshold=True, do_detect=False,
+                                 pctile=pctile, windowHalfWidth=windowHalfWidth, smoothPercentile=smoothPercentile,
+                                 smoothPercentileWidth=smoothPercentileWidth, feb29=not tstep, negate=coldSpells,
+                                 max_pad=_pad_steps(maxPadLength, time), anynans=anynans, slabs=_slabs(flat))
+    except NotImplementedError as exc:                       # a calendar / window the sweep plans cannot express
+        raise XmhwException("threshold: %s" % exc)
+    ocean = res["nvalid"].numpy() > 0
+    if not point and not ocean.any():
+        raise XmhwException("All points of grid are either land or NaN")   # identify.py:527-528
+    th_h, se_h = res["thresh"].numpy(), res["seas"].numpy()
     doy_coord = np.arange(1, ndoy + 1, dtype=np.int64)
     if not point:
         keep = _present(ocean.reshape(grid_shape))
@@ -148,7 +196,7 @@ def threshold(temp, tdim="time", climatologyPeriod=[None, None], pctile=90, wind
     ds = labeled.Dataset(coords=out_coords)
     ds["thresh"] = labeled.DataArray(th_h, dims, name="threshold")      # xmhw.py:215-216
     ds["seas"] = labeled.DataArray(se_h, dims, name="seasonal")
-    annotate_ds(ds.attrs, {"ts": attrs}, "clim")
+    annotate_ds(ds, dict({"ts": attrs}, **cattrs), "clim")
     from .identify import _ymd
     yrs = _ymd(time)[0]
     params = f"""Threshold calculated using:
@@ -214,40 +262,56 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
         raise XmhwException("Maximum gap between mhw events should"
                             + " be smaller than event minimum duration")
     data, time, other, coords, attrs, enc, tattrs = _unpack(temp, tdim)
+    cattrs = _unpack.last_coord_attrs
     point = data.ndim == 1
     if not point:
         land_check_shape(data.shape, [tdim] + other, tdim)
     doy, ndoy = add_doy(time, keep_tstep=tstep)                # xmhw.py:404
     grid_shape = data.shape[1:]
     T = data.shape[0]
-    flat = data.reshape(T, -1)
-    nan = np.isnan(flat)
-    ocean = ~nan.any(axis=0) if anynans else ~nan.all(axis=0)
-    if not point and not ocean.any():
+    flat = np.ascontiguousarray(data.reshape(T, -1))
+    if not point and _all_land(flat):
         raise XmhwException("All points of grid are either land or NaN")
     th_full = _clim_to_grid(th, other, coords, grid_shape, ndoy, "th")
     se_full = _clim_to_grid(se, other, coords, grid_shape, ndoy, "se")
     if not torch.cuda.is_available():
         raise RuntimeError("xmhw_b200 needs a CUDA device (there is no CPU path)")
-    ts = torch.from_numpy(np.ascontiguousarray(flat)).cuda()
-    if maxPadLength:                                           # xmhw.py:409-410
-        core.interp_gaps_(ts, maxPadLength)
-    if coldSpells:                                             # xmhw.py:412-413
-        ts = -ts
-    if anynans:
-        ts[:, torch.from_numpy(~ocean).cuda()] = float("nan")
-    ev = core.detect_arrays(ts, doy, ndoy, torch.from_numpy(th_full).cuda(), torch.from_numpy(se_full).cuda(),
-                            minDuration, joinGaps, maxGap)
-    inter = None
-    if intermediate:                                           # identify.py:404-411
+    ts = None
+    if intermediate:
+        # the per-timestep dataset needs the whole series on the device at once (small grids only)
         nbytes = T * flat.shape[1] * 80
         if nbytes > DENSE_LIMIT_BYTES:
             raise XmhwException("the per-timestep (intermediate) dataset would need %.1f GB; "
                                 "split the grid (reference docs/dask.rst)" % (nbytes / 1e9))
+        ts = torch.from_numpy(flat).cuda()
+        nvalid = core.count_valid(ts)
+        if anynans:
+            ts[:, nvalid != T] = float("nan")
+            nvalid = torch.where(nvalid == T, nvalid, torch.zeros_like(nvalid))
+        if _pad_steps(maxPadLength, time):                     # xmhw.py:409-410
+            core.interp_gaps_(ts, _pad_steps(maxPadLength, time))
+        if coldSpells:                                         # xmhw.py:412-413
+            ts = -ts
         thd, sed = torch.from_numpy(th_full).cuda(), torch.from_numpy(se_full).cuda()
+        ev = core.detect_arrays(ts, doy, ndoy, thd, sed, minDuration, joinGaps, maxGap)
+        ocean = nvalid.cpu().numpy() > 0
+        tab = ev.to_numpy()
+    else:
+        # one pipelined pass over the host series; th / se are uploaded once, per column block
+        res = core.host_pipeline(torch.from_numpy(flat), doy, ndoy, do_threshold=False, do_detect=True,
+                                 th_host=th_full, se_host=se_full, minDuration=minDuration, joinGaps=joinGaps,
+                                 maxGap=maxGap, negate=coldSpells, max_pad=_pad_steps(maxPadLength, time), anynans=anynans,
+                                 slabs=_slabs(flat))
+        ocean = res["nvalid"].numpy() > 0
+        ei, ef = res["ev_i32"].numpy(), res["ev_f64"].numpy()
+        tab = {f: ei[k].astype(np.int64) for k, f in enumerate(core.EI_FIELDS)}
+        tab.update({f: ef[k] for k, f in enumerate(core.EF_FIELDS)})
+    if not point and not ocean.any():
+        raise XmhwException("All points of grid are either land or NaN")
+    inter = None
+    if intermediate:                                           # identify.py:404-411
         inter = {k: v.cpu().numpy() for k, v in core.intermediate_arrays(ts, doy, ndoy, thd, sed, ev).items()}
         inter["ts"] = ts.cpu().numpy()
-    tab = ev.to_numpy()
     n = len(tab["cell"])
     cols = {"event": tab["index_start"].astype(np.float64)}
     for f in ("index_start", "index_end", "index_peak", "duration", "category"):
@@ -318,7 +382,7 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
                 dense = np.full(shape, np.nan, dtype=np.float32 if col.dtype == np.float32 else np.float64)
             dense[(erow,) + tuple(pos)] = col
             ds[v] = labeled.DataArray(dense, dims)
-    annotate_ds(ds.attrs, {"ts": attrs}, "mhw")
+    annotate_ds(ds, dict({"ts": attrs}, **cattrs), "mhw")
     ds.attrs["xmhw_parameters"] = params                       # xmhw.py:487-515
     if intermediate:                                           # xmhw.py:461-463, :471-478
         if point:
