@@ -218,6 +218,36 @@ int xmhw_intermediate_f32(const float* ts, int64_t T, int64_t ngrid, const int32
                           const double* thresh, const double* seas, const int32_t* ev_i32,
                           int64_t nev, int64_t cap, const xmhw_intermediate* out, void* stream);
 
+/* Downstream statistics of the reference's stats.py over the compact event table (ordered by cell,
+ * then start; offsets [ngrid + 1] from the detect chain).  block_of_t [T] i32 maps every time step to
+ * its block of years (0 .. nblocks-1, or -1 = outside the period), built on the host.
+ *
+ * xmhw_block_average (stats.py:27-183, agg_mhw :322-368): out [XMHW_BA_NCOL][nblocks][ngrid] f64 --
+ * event count, NaN-skipping means of the 17 properties listed at XMHW_BA_MEAN0, the block maximum
+ * of intensity_max and the block sum of intensity_cumulative; an event belongs to the block of its
+ * start (use_peak = 0) or peak (1) day.
+ * xmhw_block_ts_f32 (agg_ts :400-428): out [3][nblocks][ngrid] = mean, max, min of the series.
+ * xmhw_block_cat_days_f32 (agg_cats :371-398): days [4][nblocks][ngrid] i32 = event days per category
+ * (moderate, strong, severe, extreme), each day counted in the block of ITS OWN year.
+ * xmhw_event_rank_f64 (mhw_rank :446-510): rank [nev] of every event within its cell for one property
+ * column, 1 = largest, numpy semantics len - argsort(argsort(x)).                                */
+#define XMHW_BA_COUNT_COL  0
+#define XMHW_BA_MEAN0      1     /* duration, intensity_{max,mean,var,cumulative}, the same four _relThresh, */
+#define XMHW_BA_NMEAN      17    /* the same four _abs, severity_{mean,cumulative}, rate_onset, rate_decline  */
+#define XMHW_BA_IMAX_MAX   18
+#define XMHW_BA_TOTAL_ICUM 19
+#define XMHW_BA_NCOL       20
+int xmhw_block_average(const int32_t* ev_i32, const double* ev_f64, int64_t cap, const int64_t* offsets,
+                       int64_t ngrid, const int32_t* block_of_t, int32_t nblocks, int32_t use_peak,
+                       double* out, void* stream);
+int xmhw_block_ts_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* block_of_t, int32_t nblocks,
+                      double* out, void* stream);
+int xmhw_block_cat_days_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy, const double* thresh,
+                            const double* seas, const int32_t* ev_i32, int64_t nev, int64_t cap,
+                            const int32_t* block_of_t, int32_t nblocks, int32_t* days, void* stream);
+int xmhw_event_rank_f64(const double* col, const int32_t* cells, const int64_t* offsets, int64_t nev,
+                        double* rank, void* stream);
+
 /* land_check census (identify.py:522-525): nvalid [ngrid] i32 = number of non-NaN samples of every
  * cell of ts [T][ngrid] (the array is zeroed by the call).                                     */
 int xmhw_count_valid_f32(const float* ts, int64_t T, int64_t ngrid, int32_t* nvalid, void* stream);

@@ -474,3 +474,85 @@ def detect(ts, doy, thresh, seas, minDuration=5, joinGaps=True, maxGap=2):
     for f in F64_FIELDS:
         out[f] = np.array([r[f] for r in rows], np.float64)
     return out
+
+
+# ---------------------------------------------------------------------------
+# downstream statistics (reference xmhw/stats.py; semantics stated in xmhw_b200/stats.py)
+# ---------------------------------------------------------------------------
+BLOCK_MEAN_FIELDS = ("duration", "intensity_max", "intensity_mean", "intensity_var", "intensity_cumulative",
+                     "intensity_max_relThresh", "intensity_mean_relThresh", "intensity_var_relThresh",
+                     "intensity_cumulative_relThresh", "intensity_max_abs", "intensity_mean_abs", "intensity_var_abs",
+                     "intensity_cumulative_abs", "severity_mean", "severity_cumulative", "rate_onset", "rate_decline")
+
+
+def block_average(ev, years, ncell, period=None, blockLength=1, mtime="index_start", ts=None, doy=None,
+                  thresh=None, seas=None):
+    """stats.py:27-183 with agg_mhw / agg_ts / agg_cats (:322-428) per cell, plain loops.
+    ev: event dict of `detect`; years [T] calendar year per step.  Returns dict name -> [nblocks, ncell]."""
+    years = np.asarray(years, np.int64)
+    if period is None:
+        period = (int(years[0]), int(years[-1]))
+    bins = np.arange(period[0], period[1] + blockLength + 1, blockLength)
+    nb = len(bins) - 1
+    blk = (years - bins[0]) // blockLength
+    blk = np.where((years >= bins[0]) & (blk < nb), blk, -1)
+    out = {"ecount": np.zeros((nb, ncell)), "intensity_max_max": np.full((nb, ncell), np.nan),
+           "total_icum": np.zeros((nb, ncell))}
+    for f in BLOCK_MEAN_FIELDS:
+        out[f] = np.full((nb, ncell), np.nan)
+    eb = blk[ev[mtime]] if len(ev["cell"]) else np.zeros(0, np.int64)
+    for c in range(ncell):
+        for b in range(nb):
+            m = (ev["cell"] == c) & (eb == b)
+            if not m.any():
+                continue
+            out["ecount"][b, c] = m.sum()
+            with np.errstate(all="ignore"):
+                for f in BLOCK_MEAN_FIELDS:
+                    v = ev[f][m].astype(np.float64)
+                    if (~np.isnan(v)).any():
+                        out[f][b, c] = np.nansum(v) / (~np.isnan(v)).sum()      # sequential-sum mean like pandas
+                v = ev["intensity_max"][m]
+                if (~np.isnan(v)).any():
+                    out["intensity_max_max"][b, c] = np.nanmax(v)
+                out["total_icum"][b, c] = np.nansum(ev["intensity_cumulative"][m])
+    if ts is not None:
+        ts = np.asarray(ts, np.float32)
+        for f in ("ts_mean", "ts_max", "ts_min"):
+            out[f] = np.full((nb, ncell), np.nan)
+        for b in range(nb):
+            x = ts[blk == b]
+            ok = ~np.isnan(x)
+            n = ok.sum(0)
+            with np.errstate(all="ignore"):
+                out["ts_mean"][b] = np.where(n > 0, np.where(ok, x.astype(np.float64), 0.0).sum(0) / np.maximum(n, 1), np.nan)
+                out["ts_max"][b] = np.where(n > 0, np.nanmax(np.where(ok, x, -np.inf), 0), np.nan)
+                out["ts_min"][b] = np.where(n > 0, np.nanmin(np.where(ok, x, np.inf), 0), np.nan)
+        if thresh is not None and seas is not None and doy is not None:
+            days = np.zeros((4, nb, ncell), np.int64)
+            d = np.asarray(doy) - 1
+            for i in range(len(ev["cell"])):
+                c = int(ev["cell"][i])
+                for t in range(int(ev["index_start"][i]), int(ev["index_end"][i]) + 1):
+                    if blk[t] < 0:
+                        continue
+                    x = np.float64(ts[t, c])
+                    th, se = thresh[d[t], c], seas[d[t], c]
+                    with np.errstate(all="ignore"):
+                        cat = np.floor(1.0 + (x - th) / (th - se))
+                    if cat >= 1:
+                        days[min(int(cat), 4) - 1, blk[t], c] += 1
+            for k, f in enumerate(("moderate_days", "strong_days", "severe_days", "extreme_days")):
+                out[f] = days[k]
+            out["total_days"] = days.sum(0)
+    return out, bins[:-1]
+
+
+def rank_in_cell(ev, field):
+    """stats.py:493-510 per cell: len - argsort(argsort(x)) (stable; NaN sorts last)."""
+    r = np.zeros(len(ev["cell"]))
+    for c in np.unique(ev["cell"]):
+        m = np.flatnonzero(ev["cell"] == c)
+        x = np.asarray(ev[field][m], np.float64)
+        r[m] = len(x) - np.argsort(np.argsort(x, kind="stable"), kind="stable")
+    return r

@@ -173,3 +173,40 @@ def test_annotate_ds_attribute_table():
         joined = re.sub(r'"\s*\n?\s*\+\s*"', "", src)            # adjacent string literals joined with +
         for name, (long_name, _) in identify.MHW_VARIABLE_ATTRS.items():
             assert long_name in joined, name
+
+
+def test_save_zarr_compressed_roundtrip(tmp_path):
+    """xmhw_b200.io.save_zarr: zlib + float32 encoding (docs/gettingstarted.rst:160-178) in a zarr v2
+    directory store; sparse float tables shrink, integers / times / attributes survive the round trip."""
+    import json
+    import os
+    from xmhw_b200 import io
+    rng = np.random.default_rng(1)
+    n = 4000
+    ev = labeled.Dataset(coords={"row": np.arange(n)}, attrs={"xmhw_parameters": "MHW detected using: 5 days"})
+    ev.coord_attrs["row"] = {"long_name": "event row"}
+    ev["index_start"] = labeled.DataArray(rng.integers(1, 10000, n).astype(np.float64), ("row",))
+    ev["duration_moderate"] = labeled.DataArray(rng.integers(0, 30, n), ("row",), attrs={"units": "1"})
+    dense = np.full((50, 8, 10), np.nan)
+    dense[rng.integers(0, 50, 300), rng.integers(0, 8, 300), rng.integers(0, 10, 300)] = rng.normal(2, 1, 300)
+    cube = labeled.Dataset(coords={"events": np.arange(50), "lat": np.arange(8) * 0.25, "lon": np.arange(10) * 0.25})
+    cube["intensity_max"] = labeled.DataArray(dense, ("events", "lat", "lon"), attrs={"units": "degree_C"})
+    cube["time_peak"] = labeled.DataArray(np.array(["2003-01-02", "NaT"] * 25, "datetime64[ns]"), ("events",))
+    p = str(tmp_path / "mhw.zarr")
+    io.save_zarr(cube, p)
+    meta = json.load(open(os.path.join(p, "intensity_max", ".zarray")))
+    assert meta["compressor"] == {"id": "zlib", "level": 5} and meta["dtype"] == "<f4" and meta["zarr_format"] == 2
+    assert json.load(open(os.path.join(p, "intensity_max", ".zattrs")))["_ARRAY_DIMENSIONS"] == ["events", "lat", "lon"]
+    stored = sum(os.path.getsize(os.path.join(p, "intensity_max", f)) for f in os.listdir(os.path.join(p, "intensity_max")))
+    assert stored < dense.nbytes / 10                       # sparse cube: NaNs deflate away
+    back = io.load_zarr(p)
+    assert np.array_equal(back["intensity_max"].values, dense.astype(np.float32), equal_nan=True)
+    assert back["intensity_max"].attrs["units"] == "degree_C" and back["intensity_max"].dims == ("events", "lat", "lon")
+    t = back["time_peak"].values
+    assert t[0] == np.datetime64("2003-01-02") and np.isnat(t[1])
+    p2 = str(tmp_path / "table.zarr")
+    io.save_zarr(ev, p2, float32=False, chunk_elems=1024)   # several chunks, ragged last one
+    b2 = io.load_zarr(p2)
+    assert np.array_equal(b2["index_start"].values, ev["index_start"].values)
+    assert np.array_equal(b2["duration_moderate"].values, ev["duration_moderate"].values)
+    assert b2.attrs["xmhw_parameters"].startswith("MHW detected") and b2.coord_attrs["row"]["long_name"] == "event row"

@@ -102,6 +102,13 @@ _SIGNATURES = {
                                         C.c_void_p, C.c_int64, C.c_int64, C.POINTER(IntermediateStruct),
                                         C.c_void_p]),
     "xmhw_interp_gaps_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
+    "xmhw_block_average": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                     C.c_int32, C.c_void_p, C.c_void_p]),
+    "xmhw_block_ts_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "xmhw_block_cat_days_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_void_p]),
+    "xmhw_event_rank_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "xmhw_count_valid_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "xmhw_copy2d_async": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                     C.c_int32, C.c_void_p]),

@@ -838,6 +838,138 @@ __global__ void intermediate_kernel(const float* __restrict__ ts, int64_t T, int
   out.duration_extreme[i] = (uint8_t)(in_ev && cat >= 4.0);
 }
 
+// ---------------------------------------------------------------------------
+// Downstream statistics over the compact event table (reference xmhw/stats.py; semantics: Eric
+// Oliver's blockAverage / rank, see xmhw_b200/stats.py).  Events are ordered by cell then start,
+// so the events of one (cell, block of years) are one contiguous run of that cell's range.
+// ---------------------------------------------------------------------------
+// one thread = one cell: count / mean / max / sum of the event properties per block of years
+__global__ void __launch_bounds__(128) block_average_kernel(
+    const int32_t* __restrict__ ei, const double* __restrict__ ef, int64_t cap, const int64_t* __restrict__ offsets,
+    int64_t ngrid, const int32_t* __restrict__ block_of_t, int nblocks, int time_col, double* __restrict__ out) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ngrid) return;
+  const int64_t e0 = offsets[cell], e1 = offsets[cell + 1];
+  const size_t plane = (size_t)nblocks * ngrid;
+  int64_t e = e0;
+  for (int b = 0; b < nblocks; ++b) {
+    int cnt = 0;
+    double sum[XMHW_BA_NMEAN];
+#pragma unroll
+    for (int k = 0; k < XMHW_BA_NMEAN; ++k) sum[k] = 0.0;
+    int nn[XMHW_BA_NMEAN];
+#pragma unroll
+    for (int k = 0; k < XMHW_BA_NMEAN; ++k) nn[k] = 0;
+    double imax = -INFINITY, icum = 0.0;
+    bool any_max = false;
+    // events whose block is < b were consumed (or lie outside every block: skipped)
+    while (e < e1) {
+      const int be = block_of_t[ei[(size_t)time_col * cap + e]];
+      if (be > b) break;
+      if (be == b) {
+        ++cnt;
+        const double dur = (double)ei[(size_t)EI_DURATION * cap + e];
+        const double v[XMHW_BA_NMEAN] = {
+            dur, ef[(size_t)EF_INT_MAX * cap + e], ef[(size_t)EF_INT_MEAN * cap + e], ef[(size_t)EF_INT_VAR * cap + e],
+            ef[(size_t)EF_INT_CUM * cap + e], ef[(size_t)EF_RT_MAX * cap + e], ef[(size_t)EF_RT_MEAN * cap + e],
+            ef[(size_t)EF_RT_VAR * cap + e], ef[(size_t)EF_RT_CUM * cap + e], ef[(size_t)EF_ABS_MAX * cap + e],
+            ef[(size_t)EF_ABS_MEAN * cap + e], ef[(size_t)EF_ABS_VAR * cap + e], ef[(size_t)EF_ABS_CUM * cap + e],
+            ef[(size_t)EF_SEV_MEAN * cap + e], ef[(size_t)EF_SEV_CUM * cap + e], ef[(size_t)EF_RATE_ONSET * cap + e],
+            ef[(size_t)EF_RATE_DECLINE * cap + e]};
+#pragma unroll
+        for (int k = 0; k < XMHW_BA_NMEAN; ++k)
+          if (v[k] == v[k]) { sum[k] = sum[k] + v[k]; ++nn[k]; }          // pandas mean skips NaN
+        if (v[1] == v[1]) { any_max = true; imax = v[1] > imax ? v[1] : imax; }
+        if (v[4] == v[4]) icum = icum + v[4];
+      }
+      ++e;
+    }
+    const size_t o = (size_t)b * ngrid + cell;
+    out[(size_t)XMHW_BA_COUNT_COL * plane + o] = (double)cnt;
+#pragma unroll
+    for (int k = 0; k < XMHW_BA_NMEAN; ++k) out[(size_t)(XMHW_BA_MEAN0 + k) * plane + o] = nn[k] ? sum[k] / (double)nn[k] : qnan();
+    out[(size_t)XMHW_BA_IMAX_MAX * plane + o] = any_max ? imax : qnan();
+    out[(size_t)XMHW_BA_TOTAL_ICUM * plane + o] = icum;                     // pandas sum of nothing = 0
+  }
+}
+
+// one thread = one cell: mean / max / min of the series per block of years (NaN skipped)
+__global__ void __launch_bounds__(128) block_ts_kernel(const float* __restrict__ ts, int64_t T, int64_t ngrid,
+                                                       const int32_t* __restrict__ block_of_t, int nblocks,
+                                                       double* __restrict__ out) {
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ngrid) return;
+  const size_t plane = (size_t)nblocks * ngrid;
+  for (int b = 0; b < nblocks; ++b) {
+    out[0 * plane + (size_t)b * ngrid + cell] = qnan();
+    out[1 * plane + (size_t)b * ngrid + cell] = qnan();
+    out[2 * plane + (size_t)b * ngrid + cell] = qnan();
+  }
+  int cur = -1, n = 0;
+  double sum = 0.0;
+  float mx = -INFINITY, mn = INFINITY;
+  for (int64_t t = 0; t <= T; ++t) {
+    const int b = t < T ? block_of_t[t] : -2;
+    if (b != cur) {
+      if (cur >= 0 && n > 0) {
+        out[0 * plane + (size_t)cur * ngrid + cell] = sum / (double)n;
+        out[1 * plane + (size_t)cur * ngrid + cell] = (double)mx;
+        out[2 * plane + (size_t)cur * ngrid + cell] = (double)mn;
+      }
+      cur = b; n = 0; sum = 0.0; mx = -INFINITY; mn = INFINITY;
+    }
+    if (t < T && b >= 0) {
+      const float v = ts[t * ngrid + cell];
+      if (v == v) { ++n; sum = sum + (double)v; mx = v > mx ? v : mx; mn = v < mn ? v : mn; }
+    }
+  }
+}
+
+// one thread = one event: its days counted per category into the block of years of EACH DAY
+__global__ void __launch_bounds__(128) block_cat_days_kernel(
+    const float* __restrict__ ts, int64_t ngrid, const int32_t* __restrict__ doy, const double* __restrict__ thr,
+    const double* __restrict__ seas, const int32_t* __restrict__ ei, int64_t nev, int64_t cap,
+    const int32_t* __restrict__ block_of_t, int nblocks, int32_t* __restrict__ days) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nev) return;
+  const int64_t cell = ei[(size_t)EI_CELL * cap + i];
+  const int s = ei[(size_t)EI_START * cap + i], e = ei[(size_t)EI_END * cap + i];
+  const size_t plane = (size_t)nblocks * ngrid;
+  for (int t = s; t <= e; ++t) {
+    const int b = block_of_t[t];
+    if (b < 0) continue;
+    const int d = doy[t] - 1;
+    const double x = (double)ts[(int64_t)t * ngrid + cell];
+    const double th = thr[(int64_t)d * ngrid + cell], se = seas[(int64_t)d * ngrid + cell];
+    const double cat = floor(1.0 + (x - th) / (th - se));                   // features.py:57-62
+    if (cat >= 1.0) {
+      const int c = cat >= 4.0 ? 3 : (int)cat - 1;
+      atomicAdd(days + (size_t)c * plane + (size_t)b * ngrid + cell, 1);
+    }
+  }
+}
+
+// one thread = one event: rank of its value among the events of its cell, 1 = largest
+// (numpy: len - argsort(argsort(values)); NaN sorts last, ties keep table order)
+__global__ void __launch_bounds__(128) event_rank_kernel(const double* __restrict__ col, const int32_t* __restrict__ cells,
+                                                         const int64_t* __restrict__ offsets, int64_t nev,
+                                                         double* __restrict__ rank) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nev) return;
+  const int64_t c = cells[i];
+  const int64_t e0 = offsets[c], e1 = offsets[c + 1];
+  const double v = col[i];
+  const bool vnan = v != v;
+  int64_t below = 0;                       // position in the ascending stable sort
+  for (int64_t j = e0; j < e1; ++j) {
+    const double w = col[j];
+    const bool wnan = w != w;
+    const bool lt = vnan ? (!wnan || j < i) : (!wnan && (w < v || (w == v && j < i)));
+    below += lt;
+  }
+  rank[i] = (double)((e1 - e0) - below);
+}
+
 inline int cuda_status() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
@@ -1134,6 +1266,46 @@ int xmhw_intermediate_f32(const float* ts, int64_t T, int64_t ngrid, const int32
   if (nev) event_labels_kernel<<<(unsigned)((nev + 127) / 128), 128, 0, st>>>(ev_i32, nev, cap, ngrid, out->events);
   dim3 grid((unsigned)((ngrid + 127) / 128), (unsigned)T);
   intermediate_kernel<<<grid, 128, 0, st>>>(ts, T, ngrid, doy, thresh, seas, out->events, *out);
+  return cuda_status();
+}
+
+int xmhw_block_average(const int32_t* ev_i32, const double* ev_f64, int64_t cap, const int64_t* offsets, int64_t ngrid,
+                       const int32_t* block_of_t, int32_t nblocks, int32_t use_peak, double* out, void* stream) {
+  if (!ev_i32 || !ev_f64 || !offsets || !block_of_t || !out || cap <= 0 || ngrid <= 0 || nblocks <= 0) return XMHW_E_ARG;
+  const int nt = 128;
+  block_average_kernel<<<(unsigned)((ngrid + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
+      ev_i32, ev_f64, cap, offsets, ngrid, block_of_t, nblocks, use_peak ? EI_PEAK : EI_START, out);
+  return cuda_status();
+}
+
+int xmhw_block_ts_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* block_of_t, int32_t nblocks, double* out,
+                      void* stream) {
+  if (!ts || !block_of_t || !out || T <= 0 || ngrid <= 0 || nblocks <= 0) return XMHW_E_ARG;
+  const int nt = 128;
+  block_ts_kernel<<<(unsigned)((ngrid + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(ts, T, ngrid, block_of_t, nblocks, out);
+  return cuda_status();
+}
+
+int xmhw_block_cat_days_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy, const double* thresh,
+                            const double* seas, const int32_t* ev_i32, int64_t nev, int64_t cap,
+                            const int32_t* block_of_t, int32_t nblocks, int32_t* days, void* stream) {
+  if (!ts || !doy || !thresh || !seas || !block_of_t || !days || T <= 0 || ngrid <= 0 || nblocks <= 0 || nev < 0 ||
+      (nev > 0 && !ev_i32) || cap < nev)
+    return XMHW_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(days, 0, (size_t)4 * nblocks * ngrid * sizeof(int32_t), st);
+  if (e != cudaSuccess) return (int)e;
+  if (nev == 0) return 0;
+  block_cat_days_kernel<<<(unsigned)((nev + 127) / 128), 128, 0, st>>>(ts, ngrid, doy, thresh, seas, ev_i32, nev, cap,
+                                                                        block_of_t, nblocks, days);
+  return cuda_status();
+}
+
+int xmhw_event_rank_f64(const double* col, const int32_t* cells, const int64_t* offsets, int64_t nev, double* rank,
+                        void* stream) {
+  if (!col || !cells || !offsets || !rank || nev < 0) return XMHW_E_ARG;
+  if (nev == 0) return 0;
+  event_rank_kernel<<<(unsigned)((nev + 127) / 128), 128, 0, (cudaStream_t)stream>>>(col, cells, offsets, nev, rank);
   return cuda_status();
 }
 

@@ -112,3 +112,149 @@ def load_dataset(path):
     for k, v in data_vars.items():
         out[k] = v
     return out
+
+
+# ---------------------------------------------------------------------------
+# Compressed store: zarr v2 (directory store) written and read with the standard library + numpy.
+# The reference's docs recommend `comp = dict(zlib=True, complevel=5, shuffle=True, dtype='float32')`
+# for every variable (docs/gettingstarted.rst:160-178); netCDF4 / h5py are not in this image, and
+# zarr v2 is the other container xarray reads natively (`xr.open_zarr`): a directory with one JSON
+# header per array (`.zarray`, `.zattrs` incl. xarray's `_ARRAY_DIMENSIONS`) and one zlib-deflated
+# file per chunk.  float32 + zlib is applied as the docs ask; times are CF-encoded int64 so that
+# xarray decodes them to datetime64.
+# ---------------------------------------------------------------------------
+def _zarr_dtype(a):
+    return a.dtype.str if a.dtype.byteorder != "|" else a.dtype.str
+
+
+def _write_zarr_array(root, name, arr, dims, attrs, level, chunk_elems):
+    import json
+    import os
+    import zlib
+    arr = np.ascontiguousarray(arr)
+    d = os.path.join(root, name)
+    os.makedirs(d, exist_ok=True)
+    shape = list(arr.shape)
+    if arr.ndim == 0:
+        chunks = []
+    else:
+        rows = max(1, min(shape[0], chunk_elems // max(1, int(np.prod(shape[1:])))))
+        chunks = [rows] + shape[1:]
+    fill = None
+    if arr.dtype.kind == "f":
+        fill = "NaN"
+    meta = {"zarr_format": 2, "shape": shape, "chunks": chunks if chunks else [], "dtype": arr.dtype.str,
+            "compressor": {"id": "zlib", "level": int(level)}, "fill_value": fill, "order": "C", "filters": None}
+    with open(os.path.join(d, ".zarray"), "w") as f:
+        json.dump(meta, f)
+    za = {"_ARRAY_DIMENSIONS": list(dims)}
+    for k, v in attrs.items():
+        v = _attr(v)
+        za[k] = v.tolist() if isinstance(v, np.ndarray) else (v.item() if isinstance(v, np.generic) else v)
+    with open(os.path.join(d, ".zattrs"), "w") as f:
+        json.dump(za, f)
+    if arr.ndim == 0:
+        with open(os.path.join(d, "0"), "wb") as f:
+            f.write(zlib.compress(arr.tobytes(), level))
+        return
+    nchunk = -(-shape[0] // chunks[0]) if shape[0] else 0
+    for c in range(nchunk):
+        blk = arr[c * chunks[0]:(c + 1) * chunks[0]]
+        if blk.shape[0] < chunks[0]:                      # zarr stores full-size edge chunks
+            pad = np.full([chunks[0] - blk.shape[0]] + shape[1:], np.nan if arr.dtype.kind == "f" else 0, arr.dtype)
+            blk = np.concatenate([blk, pad])
+        key = ".".join([str(c)] + ["0"] * (arr.ndim - 1))
+        with open(os.path.join(d, key), "wb") as f:
+            f.write(zlib.compress(np.ascontiguousarray(blk).tobytes(), level))
+
+
+def save_zarr(ds, path, float32=True, level=5, chunk_elems=1 << 20):
+    """Write a Dataset (labeled or xarray-like) as a zlib-compressed zarr v2 directory store
+    (readable with `xarray.open_zarr(path, consolidated=False)`).  `float32=True` stores float64
+    variables as float32, the encoding the reference's docs recommend; integer and time variables
+    keep their width (datetime64 -> int64 "seconds since 1970-01-01")."""
+    import json
+    import os
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, ".zgroup"), "w") as f:
+        json.dump({"zarr_format": 2}, f)
+    gattrs = {}
+    for k, v in dict(getattr(ds, "attrs", {})).items():
+        v = _attr(v)
+        gattrs[k] = v.tolist() if isinstance(v, np.ndarray) else (v.item() if isinstance(v, np.generic) else v)
+    with open(os.path.join(path, ".zattrs"), "w") as f:
+        json.dump(gattrs, f)
+
+    def encode(a, is_coord):
+        a = np.asarray(a)
+        extra = {}
+        if np.issubdtype(a.dtype, np.datetime64):
+            secs = (a.astype("datetime64[s]") - _EPOCH).astype(np.int64)
+            secs = np.where(np.isnat(a), np.iinfo(np.int64).min, secs)
+            return secs, {"units": "seconds since 1970-01-01 00:00:00", "calendar": "proleptic_gregorian",
+                          "_FillValue": int(np.iinfo(np.int64).min)}
+        if a.dtype == np.bool_:
+            return a.astype(np.int8), extra
+        if a.dtype == np.float64 and float32 and not is_coord:
+            return a.astype(np.float32), extra
+        if a.dtype.kind in "iuf":
+            return a, extra
+        raise TypeError("cannot store dtype %s" % a.dtype)
+
+    cattrs = dict(getattr(ds, "coord_attrs", {}))
+    for name, c in dict(ds.coords).items():
+        arr, extra = encode(getattr(c, "values", c), True)
+        at = dict(cattrs.get(name, {}))
+        at.update(extra)
+        _write_zarr_array(path, name, arr, (name,) if arr.ndim == 1 else (), at, level, chunk_elems)
+    for name, v in dict(ds.data_vars).items():
+        arr, extra = encode(v.values, False)
+        at = dict(getattr(v, "attrs", {}))
+        at.update(extra)
+        _write_zarr_array(path, name, arr, tuple(v.dims), at, level, chunk_elems)
+
+
+def load_zarr(path):
+    """Read a store written by save_zarr back into a labeled.Dataset (CF times are decoded)."""
+    import json
+    import os
+    import zlib
+    coords, data_vars = {}, {}
+    gattrs = json.load(open(os.path.join(path, ".zattrs"))) if os.path.isfile(os.path.join(path, ".zattrs")) else {}
+    cattrs = {}
+    for name in sorted(os.listdir(path)):
+        d = os.path.join(path, name)
+        if not os.path.isfile(os.path.join(d, ".zarray")):
+            continue
+        meta = json.load(open(os.path.join(d, ".zarray")))
+        attrs = json.load(open(os.path.join(d, ".zattrs")))
+        dims = tuple(attrs.pop("_ARRAY_DIMENSIONS", ()))
+        dt = np.dtype(meta["dtype"])
+        shape, chunks = meta["shape"], meta["chunks"]
+        if not shape:
+            arr = np.frombuffer(zlib.decompress(open(os.path.join(d, "0"), "rb").read()), dt).reshape(())
+        else:
+            parts = []
+            for c in range(-(-shape[0] // chunks[0]) if shape[0] else 0):
+                key = ".".join([str(c)] + ["0"] * (len(shape) - 1))
+                parts.append(np.frombuffer(zlib.decompress(open(os.path.join(d, key), "rb").read()), dt).reshape(chunks))
+            arr = np.concatenate(parts)[:shape[0]] if parts else np.zeros(shape, dt)
+        if str(attrs.get("units", "")).startswith("seconds since 1970-01-01"):
+            fillv = attrs.pop("_FillValue", None)
+            t = _EPOCH + arr.astype("timedelta64[s]")
+            if fillv is not None:
+                t = np.where(arr == fillv, np.datetime64("NaT"), t)
+            arr = t
+            attrs.pop("units", None)
+            attrs.pop("calendar", None)
+        if len(dims) <= 1 and (dims == (name,) or dims == ()):
+            coords[name] = arr
+            if attrs:
+                cattrs[name] = attrs
+        else:
+            data_vars[name] = labeled.DataArray(arr, dims, attrs=attrs, name=name)
+    out = labeled.Dataset(coords=coords, attrs=gattrs)
+    out.coord_attrs.update(cattrs)
+    for k, v in data_vars.items():
+        out[k] = v
+    return out
