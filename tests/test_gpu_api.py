@@ -129,3 +129,64 @@ def test_intermediate_and_maxpad_api(api, oisst):
     ocean = ~np.isnan(oisst["sst"]).all(0)
     assert np.array_equal(c1["thresh"].values.reshape(366, -1),
                           oth.reshape(366, 8, 4)[:, ocean.any(1)][:, :, ocean.any(0)].reshape(366, -1), equal_nan=True)
+
+
+def test_plan_limits_surface_as_xmhw_exception(api):
+    """A window the climatology plans cannot express (wider than a year) leaves threshold() as the
+    reference's exception type, not as a raw internal error."""
+    xmhw, labeled = api
+    from xmhw_b200.exception import XmhwException
+    t = np.arange(np.datetime64("2001-01-01"), np.datetime64("2004-01-01"))[:36 * 30:30]      # 36 monthly-ish steps
+    da = labeled.DataArray(np.random.default_rng(0).normal(15, 1, (36, 2, 2)).astype(np.float32),
+                           ("time", "lat", "lon"), {"time": t, "lat": np.arange(2.0), "lon": np.arange(2.0)})
+    with pytest.raises(XmhwException):
+        xmhw.threshold(da, tstep=True, windowHalfWidth=7, smoothPercentileWidth=3)
+
+
+def test_attributes_anynans_coldspells_through_pipeline(api, oisst):
+    """The public functions run through the pipelined host path (core.host_pipeline): CF attributes of
+    annotate_ds, anynans dropping cells BEFORE the gap interpolation like the reference (xmhw.py:138 vs
+    :159-160), coldSpells sign handling."""
+    xmhw, labeled = api
+    from oracle import xmhw_oracle as O
+    sst = oisst["sst"].copy()
+    sst[50, 2, 1] = np.nan                                   # one missing day in an ocean cell
+    da = labeled.DataArray(sst, ("time", "lat", "lon"), {"time": oisst["time"], "lat": oisst["lat"], "lon": oisst["lon"]},
+                           attrs={"units": "degree_C"})
+    da.coord_attrs = {"lat": {"units": "degrees_north"}}
+    clim = xmhw.threshold(da, anynans=True, maxPadLength=3)
+    assert clim["thresh"].attrs["units"] == "degree_C" and clim.coord_attrs["lat"] == {"units": "degrees_north"}
+    assert clim.attrs["source"].endswith("github.com/coecms/xmhw")
+    doy = O.add_doy(oisst["time"])
+    flat = sst.reshape(len(doy), -1)
+    keep = ~np.isnan(flat).any(0)
+    assert keep.sum() < (~np.isnan(flat).all(0)).sum()       # the cell with the single NaN is dropped
+    oth, _ = O.threshold(np.where(keep[None], flat, np.nan), doy, 366)
+    got = clim["thresh"].values
+    exp = oth.reshape(366, 8, 4)[:, keep.reshape(8, 4).any(1)][:, :, keep.reshape(8, 4).any(0)]
+    assert np.array_equal(got, exp, equal_nan=True)
+    cold = xmhw.threshold(da, coldSpells=True, pctile=90)
+    oth_c, _ = O.threshold(-flat, doy, 366)
+    ocean = ~np.isnan(flat).all(0)
+    exp_c = oth_c.reshape(366, 8, 4)[:, ocean.reshape(8, 4).any(1)][:, :, ocean.reshape(8, 4).any(0)]
+    assert np.array_equal(cold["thresh"].values, exp_c, equal_nan=True)
+    mhw = xmhw.detect(da, cold["thresh"], cold["seas"], coldSpells=True, compact=True)
+    assert (mhw["intensity_max"].values < 0).all()           # flip_cold: intensities negated back (features.py:298-315)
+    assert mhw["intensity_max"].attrs["long_name"].startswith("MHW maximum (peak) intensity")
+
+
+def test_real_xarray_dataarray_when_available(api, oisst):
+    """A real xarray.DataArray goes in and real xarray Datasets come out (skipped where xarray is absent)."""
+    xr = pytest.importorskip("xarray")
+    xmhw, labeled = api
+    da = xr.DataArray(oisst["sst"], dims=("time", "lat", "lon"),
+                      coords={"time": oisst["time"], "lat": oisst["lat"], "lon": oisst["lon"]}, attrs={"units": "degC"})
+    da["lat"].attrs["units"] = "degrees_north"
+    clim = xmhw.threshold(da)
+    assert isinstance(clim, xr.Dataset) and clim["thresh"].dims == ("doy", "lat", "lon")
+    assert clim["lat"].attrs["units"] == "degrees_north" and clim["doy"].attrs["long_name"] == "Day of the year"
+    mhw = xmhw.detect(da, clim["thresh"], clim["seas"])
+    assert isinstance(mhw, xr.Dataset) and "events" in mhw.dims
+    ref = xmhw.threshold(labeled.DataArray(oisst["sst"], ("time", "lat", "lon"),
+                                           {"time": oisst["time"], "lat": oisst["lat"], "lon": oisst["lon"]}))
+    assert np.array_equal(clim["thresh"].values, ref["thresh"].values, equal_nan=True)

@@ -96,12 +96,12 @@ class DevicePlan2:
     exc_rows: object            # device int32: window rows of the exceptional doys (CSR by host.exc_off)
 
 
-# The two-stack top-K sweep is chosen when its plan fits AND the top-K capacity is small (high
-# percentiles: pctile 99 needs 5 of 337 keys): there its merges are nearly free.  At pctile 90
-# (36 keys) it measured 65 ms against 55 ms of the general sorted-list sweep on the global grid
-# (profiles/ncu_r02_sweep2_*.txt: one warp per scheduler because the unit slots fill shared memory),
-# so the general sweep stays the default there.
-TOPK_AUTO_MAX_KP = 16
+# Measured on B200 (global 0.25 deg grid, 30 years): the two-stack top-K sweep takes 65 ms at pctile 90
+# (36-key arrays) and 47 ms at pctile 99 (8-key arrays) against 55 / 37 ms of the general sorted-list
+# sweep (profiles/ncu_r02_sweep2_*.txt: its unit slots fill shared memory, so one warp per scheduler
+# issues ~2900 instructions per doy at 0.3 IPC).  The general sweep therefore stays the default for
+# every capacity; the top-K sweep is selectable (XMHW_B200_SWEEP=topk) and fully parity-tested.
+TOPK_AUTO_MAX_KP = 0
 
 
 def sweep_mode():

@@ -75,7 +75,7 @@ def _pad_steps(maxPadLength, time):
     if not maxPadLength:
         return 0
     n = maxPadLength
-    if not isinstance(n, (int, float, np.integer, np.floating)):
+    if isinstance(n, np.timedelta64) or not isinstance(n, (int, float, np.integer, np.floating)):
         t = np.asarray(time)
         if not np.issubdtype(t.dtype, np.datetime64) or len(t) < 2:
             raise XmhwException("a timedelta-like maxPadLength needs a datetime time axis")
@@ -174,14 +174,16 @@ def threshold(temp, tdim="time", climatologyPeriod=[None, None], pctile=90, wind
         th_h = th_h.reshape((ndoy,) + grid_shape)
         se_h = se_h.reshape((ndoy,) + grid_shape)
         for ax, k in enumerate(keep):
-            th_h = np.take(th_h, k, axis=ax + 1)
-            se_h = np.take(se_h, k, axis=ax + 1)
+            if len(k) != grid_shape[ax]:                    # (no copy of the 6 GB arrays when nothing vanishes)
+                th_h = np.take(th_h, k, axis=ax + 1)
+                se_h = np.take(se_h, k, axis=ax + 1)
         out_coords = {"doy": doy_coord}
         for d, k in zip(other, keep):
             c = coords[d][k]
             srt = np.argsort(c, kind="stable")              # unstack returns sorted coordinate values
             ax = other.index(d) + 1
-            th_h, se_h = np.take(th_h, srt, axis=ax), np.take(se_h, srt, axis=ax)
+            if not np.array_equal(srt, np.arange(len(srt))):
+                th_h, se_h = np.take(th_h, srt, axis=ax), np.take(se_h, srt, axis=ax)
             out_coords[d] = c[srt]
         dims = ("doy",) + tuple(other)
     else:
@@ -230,6 +232,10 @@ def _clim_to_grid(arr, other, grid_coords, grid_shape, ndoy, name):
         raise XmhwException(f"{name} dimensions {o} do not match the series dimensions {list(other)}")
     data = np.transpose(data, [dims.index("doy")] + [dims.index(d) for d in o])
     doyc = _coord(arr, "doy")
+    # fast path: the climatology already sits on the series' full grid (same coordinate vectors, all doys)
+    if data.shape == (ndoy,) + tuple(grid_shape) and (doyc is None or np.array_equal(doyc, np.arange(1, ndoy + 1))) \
+            and all(_coord(arr, d) is None or np.array_equal(_coord(arr, d), grid_coords[d]) for d in other):
+        return np.ascontiguousarray(data).reshape(ndoy, -1)
     full = np.full((ndoy,) + tuple(grid_shape), np.nan)
     drow = (np.asarray(doyc, np.int64) - 1) if doyc is not None else np.arange(data.shape[0])
     index = [drow]
