@@ -150,7 +150,7 @@ def test_attributes_anynans_coldspells_through_pipeline(api, oisst):
     xmhw, labeled = api
     from oracle import xmhw_oracle as O
     sst = oisst["sst"].copy()
-    sst[50, 2, 1] = np.nan                                   # one missing day in an ocean cell
+    sst[50, 1, 2] = np.nan                                   # one missing day in an ocean cell
     da = labeled.DataArray(sst, ("time", "lat", "lon"), {"time": oisst["time"], "lat": oisst["lat"], "lon": oisst["lon"]},
                            attrs={"units": "degree_C"})
     da.coord_attrs = {"lat": {"units": "degrees_north"}}
