@@ -186,6 +186,23 @@ int xmhw_events_gather(const int32_t* stage, int32_t cap_per_cell, const int32_t
                        const int64_t* offsets, int64_t ngrid, int64_t cap, int32_t* ev_i32,
                        void* stream);
 
+/* Fused detect: ONE time-major pass over the series replaces xmhw_exceed_mask_f32 + xmhw_events_count_stage
+ * + xmhw_events_gather + xmhw_event_stats_cm_f32 (identify.py:367-479, :273-325, features.py:22-295; the loop
+ * xmhw.py:440-454).  A block owns 32 adjacent cells for the whole time axis: threshold compare against
+ * float32 round-down thresholds held in shared memory, per-cell run rules, and the statistics of every
+ * event while its rows are still L2-resident.  Records are appended in completion order to the staging
+ * table stage_i32 [XMHW_EI_COUNT + 1][stage_cap] (extra last row: ordinal of the event in its cell) and
+ * stage_f64 [XMHW_EF_COUNT][stage_cap]; counts [ngrid] and nvalid [ngrid] are written, counter[0] = number
+ * of staged records, counter[1] != 0 when stage_cap was too small (the caller then uses the kernel chain).
+ * After xmhw_exclusive_scan_i32 of counts, xmhw_events_scatter places the records at offsets[cell] + ordinal
+ * in the (cell, start) ordered table.  clim_cm: xmhw_clim_cellmajor_f64.                                  */
+int xmhw_detect_fused_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy, int32_t ndoy,
+                          const double* thresh, const double* clim_cm, int32_t min_duration, int32_t join_gaps,
+                          int32_t max_gap, int32_t* counts, int32_t* nvalid, int32_t* stage_i32, double* stage_f64,
+                          int64_t stage_cap, int32_t* counter, void* stream);
+int xmhw_events_scatter(const int32_t* stage_i32, const double* stage_f64, int64_t stage_cap, int64_t nstaged,
+                        const int64_t* offsets, int64_t cap, int32_t* ev_i32, double* ev_f64, void* stream);
+
 /* features.py:22-295 mhw_df + agg_df + properties + onset_decline for nev events.
  * doy [T] i32 (1-based labels); thresh, seas [ndoy][ngrid] f64;
  * ev_i32 [XMHW_EI_COUNT][cap], ev_f64 [XMHW_EF_COUNT][cap].                       */

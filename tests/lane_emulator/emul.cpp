@@ -129,6 +129,24 @@ int emul_find_events(const uint8_t* b, int T, int min_dur, int join, int max_gap
   return em.n;
 }
 
+// same with eager emission after every word (the fused detect kernel's use of RunFinder)
+int emul_find_events_eager(const uint8_t* b, int T, int min_dur, int join, int max_gap, int32_t* starts, int32_t* ends,
+                           int32_t* emitted_at) {
+  RunFinder rf(min_dur, join, max_gap);
+  VecEmit em{starts, ends, 0};
+  int done = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    uint32_t bits = 0;
+    for (int i = 0; i < 32 && t0 + i < T; ++i) bits |= (uint32_t)(b[t0 + i] != 0) << i;
+    rf.feed(bits, t0, em);
+    rf.flush_pending(t0 + 32 < T ? t0 + 32 : T, em);
+    for (; done < em.n; ++done) emitted_at[done] = t0 + 32 < T ? t0 + 32 : T;
+  }
+  rf.finish(T, em);
+  for (; done < em.n; ++done) emitted_at[done] = T;
+  return em.n;
+}
+
 void emul_event_stats(const float* col, const double* th, const double* se, const int32_t* doy, int64_t ngrid,
                       int T, int s, int e, int32_t* oi, double* of) {
   event_stats(col, th, se, doy, ngrid, T, s, e, oi, of, 1);

@@ -204,6 +204,7 @@ def test_event_staging_overflow_falls_back_to_exact_fill(core, monkeypatch):
     """The one-pass event finder parks a bounded number of events per cell; a cell with more
     must take the exact two-pass path and give the same table."""
     from xmhw_b200 import synth
+    monkeypatch.setenv("XMHW_B200_DETECT", "chain")
     time = synth.daily_time(1982, 2011)
     doy = synth.doy366(time)
     ts = torch.from_numpy(synth.synth_sst(len(time), 96, synth.season_table(time))).cuda()
@@ -218,6 +219,44 @@ def test_event_staging_overflow_falls_back_to_exact_fill(core, monkeypatch):
     assert "xmhw_events_fill" in names and "xmhw_events_gather" not in names
     for f in a:
         assert np.array_equal(a[f], b[f], equal_nan=True), f
+
+
+def test_fused_detect_equals_kernel_chain(core, monkeypatch):
+    """The fused time-major detect pass (xmhw_detect_fused_f32 + xmhw_events_scatter) and the kernel chain
+    (exceedance mask -> staged run finding -> gather -> statistics) give the identical table, bit for bit,
+    for several option sets incl. land, NaNs, a ragged last warp and an event that ends the series; a
+    staging table that is too small makes the fused path fall back to the chain."""
+    from xmhw_b200 import synth
+    time = synth.daily_time(1990, 2004)
+    doy = synth.doy366(time)
+    T, ngrid = len(time), 1000
+    land = synth.land_mask(10, 100).ravel()
+    ts_h = synth.synth_sst(T, ngrid, synth.season_table(time), land=land, nan_ppm=3000)
+    ts_h[-40:, 7] += 6.0                                   # an event running into the end of the series
+    ts_h[:30, 9] += 6.0                                    # and one from the very first step (index 0 never counts)
+    ts = torch.from_numpy(ts_h).cuda()
+    th, se = core.threshold_arrays(ts, doy, 366)
+    for minD, join, maxG in ((5, True, 2), (1, True, 0), (3, False, 1), (7, True, 5)):
+        monkeypatch.setenv("XMHW_B200_DETECT", "fused")
+        core.TRACE = []
+        a = core.detect_arrays(ts, doy, 366, th, se, minD, join, maxG)
+        names = [n for n, _, _ in core.TRACE]
+        core.TRACE = None
+        assert "xmhw_detect_fused_f32" in names and "xmhw_exceed_mask_f32" not in names
+        monkeypatch.setenv("XMHW_B200_DETECT", "chain")
+        b = core.detect_arrays(ts, doy, 366, th, se, minD, join, maxG)
+        assert a.n == b.n and a.n > 1000
+        assert torch.equal(a.offsets, b.offsets) and torch.equal(a.nvalid, b.nvalid)
+        assert torch.equal(a.i32[:, :a.n], b.i32[:, :b.n])
+        assert np.array_equal(a.f64[:, :a.n].cpu().numpy().view(np.int64), b.f64[:, :b.n].cpu().numpy().view(np.int64))
+    monkeypatch.setenv("XMHW_B200_DETECT", "fused")
+    monkeypatch.setattr(core, "FUSED_EVENTS_PER_YEAR", 0.01)
+    core.TRACE = []
+    c = core.detect_arrays(ts, doy, 366, th, se, 7, True, 5)
+    names = [n for n, _, _ in core.TRACE]
+    core.TRACE = None
+    assert "xmhw_detect_fused_f32" in names and "xmhw_event_stats_cm_f32" in names and c.n == b.n
+    assert torch.equal(c.i32[:, :c.n], b.i32[:, :b.n])
 
 
 def test_event_stats_layouts_and_two_pass_fill_agree(core):

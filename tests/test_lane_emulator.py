@@ -253,6 +253,14 @@ def test_run_finder_fuzz(em):
         n = lib.emul_find_events(_vp(b), T, minD, join, maxG, _vp(s), _vp(e))
         so, eo = O.find_events(b.astype(bool), minD, bool(join), maxG)
         assert n == len(so) and np.array_equal(s[:n], so) and np.array_equal(e[:n], eo)
+        # eager emission (fused detect kernel): identical events, each emitted no later than
+        # maxGap + 32 steps after the word in which it became final
+        s2 = np.zeros(T + 1, np.int32)
+        e2 = np.zeros(T + 1, np.int32)
+        at = np.zeros(T + 1, np.int32)
+        n2 = lib.emul_find_events_eager(_vp(b), T, minD, join, maxG, _vp(s2), _vp(e2), _vp(at))
+        assert n2 == n and np.array_equal(s2[:n], so) and np.array_equal(e2[:n], eo)
+        assert np.all(at[:n] > eo) or T in at[:n]                  # never before the event has ended
 
 
 def test_event_stats_vs_reference_tables(em, ref_cases):

@@ -294,6 +294,10 @@ def detect_arrays(ts, doy, ndoy, thresh, seas, minDuration=5, joinGaps=True, max
     if maxGap >= minDuration:
         raise ValueError("Maximum gap between mhw events should be smaller than event minimum duration")
     dev = ts.device
+    if detect_mode() == "fused":
+        ev = _detect_fused(ts, doy, ndoy, thresh, seas, minDuration, joinGaps, maxGap)
+        if ev is not None:
+            return ev
     with torch.cuda.device(dev):
         st = _stream()
         ptr, tidx, doy32 = _doy_tables(doy, ndoy, dev)
@@ -335,6 +339,56 @@ def detect_arrays(ts, doy, ndoy, thresh, seas, minDuration=5, joinGaps=True, max
             _call("xmhw_clim_cellmajor_f64", _ptr(thresh), _ptr(seas), ndoy, ngrid, _ptr(clim_cm), st)
             _call("xmhw_event_stats_cm_f32", _ptr(ts), T, ngrid, _ptr(doy32), ndoy, _ptr(clim_cm), nev, cap,
                                               _ptr(ev_i32), _ptr(ev_f64), st)
+    return EventTable(ev_i32, ev_f64, nev, offsets, nvalid, T, ngrid)
+
+
+def detect_mode():
+    """XMHW_B200_DETECT: "fused" (default: one time-major pass, xmhw_detect_fused_f32) or "chain"
+    (exceedance mask -> staged run finding -> gather -> per-event statistics)."""
+    import os
+    return os.environ.get("XMHW_B200_DETECT", "fused")
+
+
+# staging capacity of the fused pass in events per cell and year (real SST: ~2-3); an overflow falls
+# back to the kernel chain, which sizes its table exactly
+FUSED_EVENTS_PER_YEAR = 3.5
+
+
+def _detect_fused(ts, doy, ndoy, thresh, seas, minDuration, joinGaps, maxGap):
+    """detect_arrays by the fused time-major pass; None when its staging table overflowed."""
+    T, ngrid = ts.shape
+    dev = ts.device
+    with torch.cuda.device(dev):
+        st = _stream()
+        _, _, doy32 = _doy_tables(doy, ndoy, dev)
+        clim_cm = torch.empty((ngrid, ndoy, 2), dtype=torch.float64, device=dev)
+        _call("xmhw_clim_cellmajor_f64", _ptr(thresh), _ptr(seas), ndoy, ngrid, _ptr(clim_cm), st)
+        years = max(1.0, T / max(ndoy, 1))
+        scap = int(ngrid * years * FUSED_EVENTS_PER_YEAR) + 4096
+        stage_i = torch.empty((EI_COUNT + 1, scap), dtype=torch.int32, device=dev)
+        stage_f = torch.empty((EF_COUNT, scap), dtype=torch.float64, device=dev)
+        counts = torch.zeros(ngrid, dtype=torch.int32, device=dev)
+        nvalid = torch.zeros(ngrid, dtype=torch.int32, device=dev)
+        offsets = torch.empty(ngrid + 2, dtype=torch.int64, device=dev)     # [ngrid + 1] = staged count | overflow flag
+        counter = offsets[ngrid + 1:].view(torch.int32)
+        _call("xmhw_detect_fused_f32", _ptr(ts), T, ngrid, _ptr(doy32), ndoy, _ptr(thresh), _ptr(clim_cm),
+              int(minDuration), int(bool(joinGaps)), int(maxGap), _ptr(counts), _ptr(nvalid), _ptr(stage_i),
+              _ptr(stage_f), scap, _ptr(counter), st)
+        del clim_cm
+        scratch = torch.empty(ngrid // 1024 + 2, dtype=torch.int64, device=dev)
+        _call("xmhw_exclusive_scan_i32", _ptr(counts), ngrid, _ptr(offsets), _ptr(scratch), st)
+        tail = offsets[ngrid:].cpu()           # the one host sync: event total + (staged count, overflow flag)
+        nev = int(tail[0])
+        staged, overflowed = int(tail[1]) & 0xffffffff, (int(tail[1]) >> 32) != 0
+        if overflowed or staged != nev:
+            return None
+        offsets = offsets[:ngrid + 1]
+        cap = max(nev, 1)
+        ev_i32 = torch.empty((EI_COUNT, cap), dtype=torch.int32, device=dev)
+        ev_f64 = torch.empty((EF_COUNT, cap), dtype=torch.float64, device=dev)
+        if nev:
+            _call("xmhw_events_scatter", _ptr(stage_i), _ptr(stage_f), scap, nev, _ptr(offsets), cap, _ptr(ev_i32),
+                  _ptr(ev_f64), st)
     return EventTable(ev_i32, ev_f64, nev, offsets, nvalid, T, ngrid)
 
 

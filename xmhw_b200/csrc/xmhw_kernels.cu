@@ -591,6 +591,143 @@ __global__ void __launch_bounds__(EVT_WARPS * 32) events_gather_kernel(
 }
 
 // ---------------------------------------------------------------------------
+// K3f  fused detect: ONE time-major pass over the series does the threshold compare, the run
+// rules and the event statistics (identify.py:367-479, :273-325, features.py:22-295).
+//
+// A block owns 32 adjacent cells (lane = cell) for the whole time axis; its DF_WARPS warps take
+// consecutive 32-step words of a chunk, so every lane builds the exceedance bits of ITS OWN cell
+// from coalesced 128-byte row loads -- no mask array, no bit transpose.  The float32 round-down
+// thresholds of the 32 cells (ts > thresh in float64 == ts > round_down_f32(thresh)) sit in shared
+// memory for all doys.  Warp 0 then feeds the words of the chunk, in time order, to the per-cell
+// run finder, which emits an event as soon as no later run can join it; events queue up in shared
+// memory and, a block-full at a time, every thread computes one event's statistics while the rows
+// it needs are still L2-resident (read a few hundred steps ago by this very block), so the sparse
+// 4-bytes-per-32-byte-sector reads of the statistics hit L2 instead of DRAM.  Records go to a
+// staging table in completion order together with (cell, ordinal in cell); after the scan of the
+// per-cell counts events_scatter_kernel moves them to their place in the (cell, start) ordered table.
+// ---------------------------------------------------------------------------
+struct ClimCellMajor {
+  const double2* cm;       // this cell's [ndoy] {thresh, seas} pairs
+  __device__ __forceinline__ void get(int d, double& t, double& s) const {
+    const double2 v = __ldg(cm + d);
+    t = v.x; s = v.y;
+  }
+};
+
+constexpr int DF_WARPS = 8;
+constexpr int DF_QFLUSH = 32 * DF_WARPS;          // run the statistics when this many events wait
+
+struct QueueEmit {
+  int4* q; int* q_n; int lane; int k;
+  __device__ __forceinline__ void operator()(int s, int e) {
+    const int i = atomicAdd(q_n, 1);
+    q[i] = make_int4(lane, s, e, k);
+    ++k;
+  }
+};
+
+__global__ void __launch_bounds__(DF_WARPS * 32) detect_fused_kernel(
+    const float* __restrict__ ts, int64_t T, int64_t ngrid, const int32_t* __restrict__ doy, int ndoy,
+    const double* __restrict__ thresh, const double2* __restrict__ cm, int min_dur, int join, int max_gap,
+    int32_t* __restrict__ counts, int32_t* __restrict__ nvalid, int32_t* __restrict__ stage_i,
+    double* __restrict__ stage_f, int64_t scap, int32_t* __restrict__ counter /* [0] staged, [1] overflow */) {
+  extern __shared__ float df_smem[];
+  float* thrs = df_smem;                                            // [ndoy][32]
+  uint32_t* words = reinterpret_cast<uint32_t*>(thrs + (size_t)ndoy * 32);   // [DF_WARPS][32]
+  int* sh = reinterpret_cast<int*>(words + DF_WARPS * 32);          // [0] queue length, [1] staging base, [2..33] valid counts
+  int4* queue = reinterpret_cast<int4*>(sh + 36);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t cell = (int64_t)blockIdx.x * 32 + lane;
+  const bool ok = cell < ngrid;
+  const float* col = ts + (ok ? cell : 0);
+  const float inf = __int_as_float(0x7f800000);
+  for (int d = warp; d < ndoy; d += DF_WARPS) {
+    const double th = ok ? thresh[(int64_t)d * ngrid + cell] : qnan();
+    thrs[d * 32 + lane] = (th == th) ? __double2float_rd(th) : inf;   // NaN threshold / out-of-grid lane: nothing exceeds
+  }
+  if (threadIdx.x < 36) sh[threadIdx.x] = 0;
+  __syncthreads();
+  RunFinder rf(min_dur, join, max_gap);
+  QueueEmit em{queue, sh, lane, 0};
+  int cnt = 0;
+  const uint32_t ng32 = (uint32_t)ngrid;
+
+  auto stats_phase = [&]() {
+    // every thread one queued event; records go to the staging table at a block-wide atomic base
+    const int nq = sh[0];
+    if (threadIdx.x == 0) sh[1] = atomicAdd(counter, nq);
+    __syncthreads();
+    const int64_t base = sh[1];
+    for (int i = threadIdx.x; i < nq; i += DF_WARPS * 32) {
+      const int4 ev = queue[i];
+      const int64_t pos = base + i;
+      if (pos >= scap) { atomicOr(counter + 1, 1); continue; }
+      const int64_t c = (int64_t)blockIdx.x * 32 + ev.x;
+      ClimCellMajor clim{cm + c * ndoy};
+      event_stats<8, ClimCellMajor>(ts + c, clim, doy, ngrid, (int)T, ev.y, ev.z, stage_i + pos, stage_f + pos, scap);
+      stage_i[(size_t)EI_CELL * scap + pos] = (int32_t)c;
+      stage_i[(size_t)EI_COUNT * scap + pos] = ev.w;                  // ordinal of the event within its cell
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sh[0] = 0;
+    __syncthreads();
+  };
+
+  for (int64_t t0 = 0; t0 < T; t0 += 32 * DF_WARPS) {
+    const int64_t tw = t0 + 32 * warp;                               // this warp's word
+    uint32_t bits = 0u;
+    if (tw < T) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int64_t t = tw + i < T ? tw + i : T - 1;               // clamped: loads stay unconditional
+        v[i] = __ldg(col + (uint64_t)t * ng32);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool in = tw + i < T;
+        const int d = __ldg(doy + (in ? tw + i : T - 1)) - 1;
+        const float thr = thrs[d * 32 + lane];
+        bits |= (uint32_t)(in && ok && v[i] > thr) << i;
+        cnt += in && ok && v[i] == v[i];
+      }
+    }
+    words[warp * 32 + lane] = bits;
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll 1
+      for (int w = 0; w < DF_WARPS; ++w)
+        if (t0 + 32 * w < T) rf.feed(words[w * 32 + lane], (int)(t0 + 32 * w), em);
+      const int64_t t_end = t0 + 32 * DF_WARPS < T ? t0 + 32 * DF_WARPS : T;
+      if (t_end < T) rf.flush_pending((int)t_end, em);
+      else rf.finish((int)T, em);
+    }
+    __syncthreads();
+    if (sh[0] >= DF_QFLUSH || t0 + 32 * DF_WARPS >= T) stats_phase();
+  }
+  if (cnt) atomicAdd(sh + 2 + lane, cnt);
+  __syncthreads();
+  if (warp == 0 && ok) {
+    counts[cell] = em.k;
+    nvalid[cell] = sh[2 + lane];
+  }
+}
+
+// staged records -> the (cell, start) ordered event table: position = offsets[cell] + ordinal
+__global__ void __launch_bounds__(256) events_scatter_kernel(const int32_t* __restrict__ stage_i,
+                                                             const double* __restrict__ stage_f, int64_t scap,
+                                                             int64_t nstaged, const int64_t* __restrict__ offsets,
+                                                             int64_t cap, int32_t* __restrict__ ei, double* __restrict__ ef) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nstaged) return;
+  const int64_t pos = offsets[stage_i[(size_t)EI_CELL * scap + j]] + stage_i[(size_t)EI_COUNT * scap + j];
+#pragma unroll
+  for (int k = 0; k < EI_COUNT; ++k) ei[(size_t)k * cap + pos] = stage_i[(size_t)k * scap + j];
+#pragma unroll
+  for (int k = 0; k < EF_COUNT; ++k) ef[(size_t)k * cap + pos] = stage_f[(size_t)k * scap + j];
+}
+
+// ---------------------------------------------------------------------------
 // exclusive scan int32 -> int64 (three small kernels; n <= a few million)
 // ---------------------------------------------------------------------------
 constexpr int SCAN_ITEMS = 1024;
@@ -684,14 +821,6 @@ __global__ void __launch_bounds__(256) clim_cellmajor_kernel(const double* __res
     if (d < ndoy && c < ngrid) cm[c * ndoy + d] = make_double2(tt[tx][cl], tsn[tx][cl]);
   }
 }
-
-struct ClimCellMajor {
-  const double2* cm;       // this cell's [ndoy] {thresh, seas} pairs
-  __device__ __forceinline__ void get(int d, double& t, double& s) const {
-    const double2 v = __ldg(cm + d);
-    t = v.x; s = v.y;
-  }
-};
 
 template <int BATCH, int MINB>
 __global__ void __launch_bounds__(128, MINB) event_stats_cm_kernel(const float* __restrict__ ts, int64_t T, int64_t ngrid,
@@ -1198,6 +1327,43 @@ int xmhw_events_gather(const int32_t* stage, int32_t cap_per_cell, const int32_t
   const int64_t ncg = (ngrid + 31) / 32;
   events_gather_kernel<<<(unsigned)((ncg + EVT_WARPS - 1) / EVT_WARPS), EVT_WARPS * 32, 0, (cudaStream_t)stream>>>(
       stage, cap_per_cell, counts, offsets, ngrid, cap, ev_i32);
+  return cuda_status();
+}
+
+int xmhw_detect_fused_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* doy, int32_t ndoy,
+                          const double* thresh, const double* clim_cm, int32_t min_duration, int32_t join_gaps,
+                          int32_t max_gap, int32_t* counts, int32_t* nvalid, int32_t* stage_i32, double* stage_f64,
+                          int64_t stage_cap, int32_t* counter, void* stream) {
+  if (!ts || !doy || !thresh || !clim_cm || !counts || !nvalid || !stage_i32 || !stage_f64 || !counter || T <= 0 ||
+      ngrid <= 0 || ndoy <= 0 || min_duration < 1 || max_gap < 0 || stage_cap <= 0 || ((uintptr_t)clim_cm & 15) ||
+      ngrid > 0xffffffffll || T > 0x7fffffffll)
+    return XMHW_E_ARG;
+  // queue: what waits below the flush level plus what one chunk can emit (per lane at most one event
+  // per min_duration + 1 steps, + 2 for the chunk edges)
+  const int per_lane = (32 * DF_WARPS) / (min_duration + 1) + 2;
+  const size_t qcap = (size_t)DF_QFLUSH + 32u * per_lane;
+  const size_t smem = (size_t)ndoy * 32 * 4 + DF_WARPS * 32 * 4 + 36 * 4 + qcap * sizeof(int4) + 16;
+  if (smem > 227 * 1024) return XMHW_E_SMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(counter, 0, 2 * sizeof(int32_t), st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(detect_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t ncg = (ngrid + 31) / 32;
+  detect_fused_kernel<<<(unsigned)ncg, DF_WARPS * 32, smem, st>>>(ts, T, ngrid, doy, ndoy, thresh,
+                                                                  (const double2*)clim_cm, min_duration, join_gaps, max_gap,
+                                                                  counts, nvalid, stage_i32, stage_f64, stage_cap, counter);
+  return cuda_status();
+}
+
+int xmhw_events_scatter(const int32_t* stage_i32, const double* stage_f64, int64_t stage_cap, int64_t nstaged,
+                        const int64_t* offsets, int64_t cap, int32_t* ev_i32, double* ev_f64, void* stream) {
+  if (!stage_i32 || !stage_f64 || !offsets || !ev_i32 || !ev_f64 || stage_cap <= 0 || nstaged < 0 || nstaged > stage_cap ||
+      cap < nstaged)
+    return XMHW_E_ARG;
+  if (nstaged == 0) return 0;
+  events_scatter_kernel<<<(unsigned)((nstaged + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      stage_i32, stage_f64, stage_cap, nstaged, offsets, cap, ev_i32, ev_f64);
   return cuda_status();
 }
 

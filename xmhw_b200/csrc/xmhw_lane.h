@@ -735,6 +735,15 @@ struct RunFinder {
     if (run_start >= 0) { close(run_start, T - 1, emit); run_start = -1; }
     if (ps >= 0) { emit(ps, pe); ps = -1; }
   }
+  // Eager emission (fused detect kernel): after everything before time t_end was fed, the pending
+  // event is final as soon as no later qualified run can still join it -- the next run starts at
+  // run_start (a run in progress) or at t_end at the earliest.  Same events, same order as with
+  // finish() alone; only the moment of emission moves forward.
+  template <class Emit> XMHW_HD void flush_pending(int t_end, Emit& emit) {
+    if (ps < 0) return;
+    const int nxt = run_start >= 0 ? run_start : t_end;
+    if (!join || nxt - pe - 1 > max_gap) { emit(ps, pe); ps = -1; }
+  }
 };
 
 // ---------------------------------------------------------------------------
