@@ -20,8 +20,19 @@ def _free_port():
     return p
 
 
+def _table(ev, ngrid):
+    """oracle event dict -> a core.EventTable on CPU tensors (what multi.event_checksum reads)"""
+    import torch
+    from xmhw_b200 import core
+    n = len(ev["cell"])
+    i32 = torch.from_numpy(np.stack([np.asarray(ev[f], np.int32) for f in core.EI_FIELDS]).reshape(core.EI_COUNT, n))
+    f64 = torch.from_numpy(np.stack([np.asarray(ev[f], np.float64) for f in core.EF_FIELDS]).reshape(core.EF_COUNT, n))
+    return core.EventTable(i32, f64, n, None, None, 0, ngrid)
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
+    import torch
     import torch.distributed as dist
     from oracle import xmhw_oracle as O
     from xmhw_b200 import shard, synth
@@ -35,8 +46,15 @@ def _worker(rank, world, port, q):
     a, b = ranges[rank]
     ts = synth.synth_sst(len(tm), b - a, synth.season_table(tm), land=land[a:b], cell0=a)   # own shard only
     th, se = O.threshold(ts, doy, 366)
-    ev = shard.globalize(O.detect(ts, doy, th, se), a)
-    got = shard.gather_results({"range": (a, b), "thresh": th, "events": ev}, dst=0)
+    loc = O.detect(ts, doy, th, se)
+    ev = shard.globalize(loc, a)
+    # the product's partition-independent checksums (xmhw_b200.multi), summed over the ranks with gloo
+    from xmhw_b200 import multi
+    sums = {"events": len(loc["cell"]), "table": multi.event_checksum(_table(loc, b - a), a),
+            "clim": multi.clim_checksum(torch.from_numpy(th), torch.from_numpy(se))}
+    sums = multi.combine_checksums(sums)
+    got = shard.gather_results({"range": (a, b), "thresh": th, "events": ev, "sums": sums,
+                                "rank_range": multi.rank_range(~land.astype(bool), rank, world)}, dst=0)
     if rank == 0:
         q.put(got)
     dist.barrier()
@@ -71,6 +89,13 @@ def test_two_rank_sharding_and_gather():
     allev = shard.concat_tables([g["events"] for g in got])
     for k in ev:
         assert np.array_equal(allev[k], ev[k], equal_nan=True), k
+    # checksums: both ranks hold the same sums, equal to the one-process checksums of the whole grid
+    import torch
+    from xmhw_b200 import multi
+    whole = {"events": len(ev["cell"]), "table": multi.event_checksum(_table(ev, land.size), 0),
+             "clim": multi.clim_checksum(torch.from_numpy(th), torch.from_numpy(se))}
+    assert got[0]["sums"] == got[1]["sums"] == whole
+    assert [g["rank_range"] for g in got] == [g["range"] for g in got]
 
 
 def test_balanced_ranges_properties():
