@@ -236,6 +236,7 @@ def test_fused_detect_equals_kernel_chain(core, monkeypatch):
     ts_h[:30, 9] += 6.0                                    # and one from the very first step (index 0 never counts)
     ts = torch.from_numpy(ts_h).cuda()
     th, se = core.threshold_arrays(ts, doy, 366)
+    monkeypatch.setattr(core, "FUSED_EVENTS_PER_YEAR", 60.0)        # minDuration 1 yields ~25 events per cell-year
     for minD, join, maxG in ((5, True, 2), (1, True, 0), (3, False, 1), (7, True, 5)):
         monkeypatch.setenv("XMHW_B200_DETECT", "fused")
         core.TRACE = []

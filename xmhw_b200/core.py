@@ -343,10 +343,15 @@ def detect_arrays(ts, doy, ndoy, thresh, seas, minDuration=5, joinGaps=True, max
 
 
 def detect_mode():
-    """XMHW_B200_DETECT: "fused" (default: one time-major pass, xmhw_detect_fused_f32) or "chain"
-    (exceedance mask -> staged run finding -> gather -> per-event statistics)."""
+    """XMHW_B200_DETECT: "chain" (default: exceedance mask -> staged run finding -> gather -> per-event
+    statistics) or "fused" (one time-major pass, xmhw_detect_fused_f32).  Measured on B200 at the global
+    0.25 deg grid: chain 27.9 ms, fused 80.8 + 13.9 ms (profiles/ncu_r02f_detect_fused_quarter.txt): with the
+    thresholds of 32 cells in shared memory only two blocks fit an SM and the per-cell run rules of a
+    block are one warp's serial work, so the other warps wait at the block barrier (57 % of the stall
+    samples); the chain's kernels already issue ~2 instructions per cycle, i.e. the work is as much
+    issue-bound as memory-bound and a fused pass cannot drop below their sum by much."""
     import os
-    return os.environ.get("XMHW_B200_DETECT", "fused")
+    return os.environ.get("XMHW_B200_DETECT", "chain")
 
 
 # staging capacity of the fused pass in events per cell and year (real SST: ~2-3); an overflow falls
