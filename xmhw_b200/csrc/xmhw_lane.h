@@ -191,6 +191,7 @@ template <int N> XMHW_HD void sort_desc(uint32_t* k);
 template <> XMHW_HD void sort_desc<8>(uint32_t* k) { XMHW_SORTNET_8 }
 template <> XMHW_HD void sort_desc<16>(uint32_t* k) { XMHW_SORTNET_16 }
 template <> XMHW_HD void sort_desc<24>(uint32_t* k) { XMHW_SORTNET_24 }
+template <> XMHW_HD void sort_desc<30>(uint32_t* k) { XMHW_SORTNET_30 }
 template <> XMHW_HD void sort_desc<32>(uint32_t* k) { XMHW_SORTNET_32 }
 template <> XMHW_HD void sort_desc<40>(uint32_t* k) { XMHW_SORTNET_40 }
 template <> XMHW_HD void sort_desc<48>(uint32_t* k) { XMHW_SORTNET_48 }
@@ -312,6 +313,9 @@ struct Sweeper {
   uint32_t pivot;        // cut value (key of the smallest sample above the cut)
   float pv[MAXN];        // prefetched rows of the next instance to load (MAXN = 32 or 48 keys per list)
   int total_enter;
+  int pend_off, pend_size;   // the list whose rows sit in (or are on their way to) the prefetch registers
+  Vec pend_rows_v;           // its row indices
+  Vec cur_use; int cur_m; uint32_t cur_plo, cur_phi;    // enter_phase(s) -> walk_phase(s)
   int nzero;             // steps without any sample (per-cell doy compaction of the smoothing)
   Vec rec_next, use_next;   // step record / list bases of the next step (prefetched)
 
@@ -336,14 +340,18 @@ struct Sweeper {
   // issue the loads of the list whose time rows are the first `size` entries of rv
   XMHW_HD void prefetch_rows(const Vec& rv, int size) {
     // unconditional loads (entries past `size` read row 0 and are masked in consume), so the
-    // compiler keeps all of them in flight instead of waiting on each predicated result
-    const uint32_t ng32 = (uint32_t)ngrid;      // row offset as one 32x32->64 multiply (ngrid < 2^32)
+    // compiler keeps all of them in flight instead of waiting on each predicated result.
+    // Byte offsets: row * (4 ngrid) added to the column pointer is ONE 32x32+64 multiply-add per row.
+    const uint32_t ng4 = (uint32_t)ngrid * 4u;      // ngrid < 2^30 (checked by the launcher)
+    const char* const cb = reinterpret_cast<const char*>(col);
     if (MAXN == 32 || size <= 32) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(uint32_t)env.vget(rv, i) * ng32);
+      for (int i = 0; i < 32; ++i)
+        pv[i] = XMHW_LDG(reinterpret_cast<const float*>(cb + (uint64_t)(uint32_t)env.vget(rv, i) * ng4));
     } else {
 #pragma unroll
-      for (int i = 0; i < MAXN; ++i) pv[i] = XMHW_LDG(col + (uint64_t)(uint32_t)env.vget(rv, i) * ng32);
+      for (int i = 0; i < MAXN; ++i)
+        pv[i] = XMHW_LDG(reinterpret_cast<const float*>(cb + (uint64_t)(uint32_t)env.vget(rv, i) * ng4));
     }
   }
 
@@ -367,8 +375,8 @@ struct Sweeper {
     return lo;
   }
 
-  // keys of the prefetched instance -> sorted block in the pool
-  template <int N>
+  // keys of the prefetched instance -> sorted block in the pool (EXACT: the list has exactly N rows)
+  template <int N, bool EXACT = false>
   XMHW_HD void consume(int base, int sbase, int size, int keep, int& len, int& ptr) {
     // all-land shortcut: a warp whose 32 cells have no valid sample in this list skips the key
     // conversion, sums and sort (ocean warps pay one compare + vote for the test)
@@ -391,13 +399,17 @@ struct Sweeper {
     uint32_t k[N];
     len = 0;
     double sum = 0.0;
+    // Lanes past the grid edge read cell 0 and compute on it: nothing of theirs is ever stored
+    // (lanes share no data), so validity is just "inside the list and not NaN".  An invalid sample
+    // enters the f64 sum as +0.0f (exact) instead of being skipped by a select on the f64 halves.
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const float v = pv[i];
       const uint32_t b = f32_bits(v);
-      const bool valid = (i < size) && ok && (v == v);
+      const bool valid = (EXACT || i < size) && (v == v);
       k[i] = valid ? (b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u)) : 0u;
-      if (valid) { ++len; sum = sum + (double)v; }
+      len += valid ? 1 : 0;
+      sum = sum + (double)(valid ? v : 0.0f);
     }
     ptr = 0;
     uint32_t cinc = 0xffffffffu, cexc = 0u;
@@ -410,7 +422,14 @@ struct Sweeper {
         if (i < keep) srow[i * 32] = k[i];                  // top `keep` keys: shared memory
         if (i >= keep && i < size) grow[i * 32] = k[i];     // sorted remainder: global scratch
       }
-      partition_sorted<N>(k, pivot, ptr, cinc, cexc);
+      if (N == 30) {                 // the halving search wants a power of two: two 0 keys (below every pivot) appended
+        uint32_t k32[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) k32[i] = i < N ? k[i] : 0u;
+        partition_sorted<32>(k32, pivot, ptr, cinc, cexc);
+      } else {
+        partition_sorted<N>(k, pivot, ptr, cinc, cexc);
+      }
     }
     scratch[(size_t)(sbase + SCR_SUM) * 32 + lane] = f64_lo(sum);
     scratch[(size_t)(sbase + SCR_SUM + 1) * 32 + lane] = f64_hi(sum);
@@ -438,6 +457,7 @@ struct Sweeper {
     const bool loaded = (e >> 30) != 0;
     if (loaded) {
       if (size <= 8) consume<8>(base, sbase, size, keep, len, ptr);
+      else if (size == 30) consume<30, true>(base, sbase, size, keep, len, ptr);      // 30-year series: the common list
       else if (MAXN == 32 || size <= 32) consume<32>(base, sbase, size, keep, len, ptr);
       else if (size <= 40) consume<(MAXN > 32 ? 40 : 32)>(base, sbase, size, keep, len, ptr);
       else consume<(MAXN > 32 ? 48 : 32)>(base, sbase, size, keep, len, ptr);
@@ -468,7 +488,9 @@ struct Sweeper {
                          (XMHW_LDG(p.step_rec + STEP_COUNTS) >> 16) & 0x7f, lane);
     int off0, size0;
     next_load(0, off0, size0);
-    if (size0 > 0) prefetch_rows(env.vload(p.rows + off0, size0, lane), size0);
+    pend_off = off0; pend_size = size0;
+    pend_rows_v = env.vload(p.rows + off0, size0, lane);
+    prefetch_rows(pend_rows_v, size0);
   }
 
   // One pass over the lists in use: the two smallest keys above the cut (i1 <= i2, lists
@@ -496,7 +518,23 @@ struct Sweeper {
     }
   }
 
+  // A sweep step = enter_phase(s) (lists leave / enter; consumes the prefetch registers), the ONE
+  // unconditional prefetch of the list that is pending afterwards, then walk_phase(s) (selection +
+  // output).  Measured variants of where the prefetch sits (B200, global grid, profiles/
+  // kernel_ms_r02_general_sweep_variants.txt): inside the conditional entry loop 54.6 ms (round 1: ptxas
+  // resolves the 32-register phi with copies right behind the loads, 14 % of the stall samples wait
+  // there); one unconditional site after the entries 53.2 ms (this); at the end of the step 54.1 ms;
+  // loop rotated so that the registers are written and read in one iteration 54.1 ms (code grows, the
+  // instruction-fetch stalls eat the gain).
   XMHW_HD void step(int s, double& thresh, double& seas) {
+    enter_phase(s);
+    prefetch_pending();
+    walk_phase(s, thresh, seas);
+  }
+
+  XMHW_HD void prefetch_pending() { prefetch_rows(pend_rows_v, pend_size); }
+
+  XMHW_HD void enter_phase(int s) {
     const Vec rec = rec_next;
     const Vec usev = use_next;
     const uint32_t w0 = (uint32_t)env.vget(rec, STEP_COUNTS);
@@ -519,14 +557,20 @@ struct Sweeper {
       leave_list(ovf ? XMHW_LDG(p.leave + l0 + j) : env.vget(rec, (STEP_LEAVE + j) & 31), slo, shi);
       wsum = wsum - f64_from(slo, shi);
     }
-    // row indices of the list that will be prefetched after this step's first entering load:
-    // requested now so that they are here when the prefetch is issued (no dependent-load wait)
-    int early_size = -1;
-    Vec early_rows = rec;
-    if (!ovf && n_enter > 0) {
-      early_size = env.vget(rec, STEP_NEXT_LOAD + 1);
-      if (early_size > 0) early_rows = env.vload(p.rows + env.vget(rec, STEP_NEXT_LOAD), early_size, lane);
+    // The list that will sit in the prefetch registers AFTER this step: the one named by the last
+    // loaded entry of the step, or (no load this step) the one already pending.  Its row indices
+    // are requested now; its loads are issued by prefetch_pending(), unconditionally (a step without a
+    // load simply re-reads the pending list: L2 hits).
+    int jl = -1;
+    if (!ovf) {
+      for (int j = 0; j < n_enter; ++j)
+        if (env.vget(rec, (STEP_ENTER + 3 * j) & 31) >> 30) jl = j;
+      if (jl >= 0) {
+        pend_off = env.vget(rec, (STEP_NEXT_LOAD + 2 * jl) & 31);
+        pend_size = env.vget(rec, (STEP_NEXT_LOAD + 2 * jl + 1) & 31);
+      }
     }
+    if (!ovf) pend_rows_v = env.vload(p.rows + pend_off, pend_size, lane);
 #pragma unroll 1
     for (int j = 0; j < n_enter; ++j) {
       int e, base, size, keep, sbase, next_off = 0, next_size = -1;
@@ -543,17 +587,23 @@ struct Sweeper {
         next_off = env.vget(rec, (STEP_NEXT_LOAD + 2 * j) & 31);
         next_size = env.vget(rec, (STEP_NEXT_LOAD + 2 * j + 1) & 31);
       }
-      if (enter_list(e, base, size, keep, sbase)) {       // loaded: prefetch the next list to load
-        Vec rv = early_rows;
-        int rsize = early_size;
-        if (j != 0 || early_size < 0) {                   // not the one requested at the top of the step
-          if (next_size < 0) next_load(eoff + j + 1, next_off, next_size);
-          rsize = next_size;
-          if (rsize > 0) rv = env.vload(p.rows + next_off, rsize, lane);
-        }
-        if (rsize > 0) prefetch_rows(rv, rsize);
+      if (enter_list(e, base, size, keep, sbase) && (ovf || j != jl)) {
+        // loaded, and another list of THIS step still has to be loaded (first step; the split
+        // leap / non-leap lists around Feb 29): fetch it right away
+        if (next_size < 0) next_load(eoff + j + 1, next_off, next_size);
+        if (ovf) { pend_off = next_off; pend_size = next_size; }
+        if (next_size > 0) prefetch_rows(env.vload(p.rows + next_off, next_size, lane), next_size);
       }
     }
+    if (ovf) pend_rows_v = env.vload(p.rows + pend_off, pend_size, lane);
+    cur_use = usev; cur_m = m; cur_plo = plo; cur_phi = phi;
+  }
+
+  XMHW_HD void walk_phase(int s, double& thresh, double& seas) {
+    (void)s;
+    const Vec usev = cur_use;
+    const int m = cur_m;
+    const uint32_t plo = cur_plo, phi = cur_phi;
     // stage the base rows of the lists in use (padded to a multiple of 4 with the null list)
     const int m4 = (m + 3) & ~3;
     uint32_t* ub = pool + p.pool_rows * 32;

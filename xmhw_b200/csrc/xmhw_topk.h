@@ -77,7 +77,6 @@ template <> XMHW_HD void bitonic_valley_desc<24>(uint32_t (&k)[24]) { XMHW_BITON
 template <> XMHW_HD void bitonic_valley_desc<36>(uint32_t (&k)[36]) { XMHW_BITONIC_36 }
 template <> XMHW_HD void bitonic_valley_desc<48>(uint32_t (&k)[48]) { XMHW_BITONIC_48 }
 
-template <> XMHW_HD void sort_desc<30>(uint32_t* k) { XMHW_SORTNET_30 }
 
 // A (KP keys, descending) := the KP largest of A u L (N keys, descending), descending.
 // max(A[i], L[KP-1-i]) is the top KP as a valley; the pruned bitonic merger sorts it.
