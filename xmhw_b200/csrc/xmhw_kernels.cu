@@ -59,30 +59,38 @@ __global__ void __launch_bounds__(32, MINB) clim_sweep_kernel(
     int32_t* __restrict__ nempty, uint32_t* __restrict__ scratch) {
   extern __shared__ uint32_t pool[];
   const int lane = threadIdx.x;
-  // PERSISTENT blocks: the grid is the number of warps the device holds at once, each block walks the
-  // 32-cell groups blockIdx.x, + gridDim.x, ...  Its scratch rows are reused from group to group, so
-  // the near region (gridDim.x * scratch_rows rows, tens of MB) is rewritten in place inside L2 instead
-  // of being written back once per group.
-  uint32_t* const near_rows = scratch + (size_t)blockIdx.x * p.scratch_rows * 32;
-  uint32_t* const far_rows = scratch + ((size_t)gridDim.x + (size_t)blockIdx.x * (p.scratch_split >> 8)) * p.scratch_rows * 32;
+  // PERSISTENT blocks: the grid is the number of warps the device holds at once; a block takes its next
+  // 32-cell group from a global ticket counter (all-land groups cost almost nothing, a static split
+  // would leave a third of the blocks idle at the end).  Its scratch rows are reused from group to
+  // group, so the near region (gridDim.x * scratch_rows rows, tens of MB) is rewritten in place inside
+  // L2 instead of being written back once per group.  Word 0 of the scratch is the ticket counter
+  // (zeroed by the launcher), the rows start one row later.
+  uint32_t* const rows0 = scratch + 32;
+  uint32_t* const near_rows = rows0 + (size_t)blockIdx.x * p.scratch_rows * 32;
+  uint32_t* const far_rows = rows0 + ((size_t)gridDim.x + (size_t)blockIdx.x * (p.scratch_split >> 8)) * p.scratch_rows * 32;
   const int64_t ncg = (ngrid + 31) / 32;
   WarpEnv env;
-  for (int64_t g = blockIdx.x; g < ncg; g += gridDim.x) {
+  int64_t g = blockIdx.x;
+  while (g < ncg) {
     const int64_t cell = g * 32 + lane;
     const bool ok = cell < ngrid;
     const float* col = ts + (ok ? cell : 0);
-    Sweeper<WarpEnv, MAXN> sw(env, p, pool, near_rows, far_rows, lane, col, ngrid, ok);
-    sw.init();
-    for (int s = 0; s < p.nsteps; ++s) {
-      double a, b;
-      sw.step(s, a, b);
-      if (ok) {
-        thr[(int64_t)s * ngrid + cell] = a;
-        seas[(int64_t)s * ngrid + cell] = b;
+    {
+      Sweeper<WarpEnv, MAXN> sw(env, p, pool, near_rows, far_rows, lane, col, ngrid, ok);
+      sw.init();
+      for (int s = 0; s < p.nsteps; ++s) {
+        double a, b;
+        sw.step(s, a, b);
+        if (ok) {
+          thr[(int64_t)s * ngrid + cell] = a;
+          seas[(int64_t)s * ngrid + cell] = b;
+        }
       }
+      if (ok) nempty[cell] = sw.nzero;
     }
-    if (ok) nempty[cell] = sw.nzero;
-    __syncwarp();
+    unsigned ticket = 0;
+    if (lane == 0) ticket = atomicAdd(scratch, 1u);
+    g = (int64_t)gridDim.x + __shfl_sync(0xffffffffu, ticket, 0);
   }
 }
 
@@ -1223,7 +1231,7 @@ int64_t xmhw_clim_sweep_scratch_bytes(const xmhw_clim_plan* plan, int64_t ngrid)
   SweepLaunch L;
   if (sweep_launch_shape(plan, ngrid, &L) != 0) return -1;
   const int64_t far_mul = plan->scratch_split >> 8;
-  return (int64_t)L.blocks * plan->scratch_rows * (1 + far_mul) * 128 + 128;
+  return (int64_t)L.blocks * plan->scratch_rows * (1 + far_mul) * 128 + 256;      // + ticket row + slack
 }
 
 int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan* plan,
@@ -1244,8 +1252,9 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
   // read ~10 steps later and every pop of the walk waits for DRAM.  Development knob
   // XMHW_B200_SWEEP_L2 = 0 disables the window.  A device without the feature just runs without it.
   static const int l2_on = getenv("XMHW_B200_SWEEP_L2") ? atoi(getenv("XMHW_B200_SWEEP_L2")) : 1;
-  const size_t near_bytes = (size_t)L.blocks * plan->scratch_rows * 128;
+  const size_t near_bytes = (size_t)L.blocks * plan->scratch_rows * 128 + 128;      // ticket row + near rows
   bool window = false;
+  if (cudaMemsetAsync(scratch, 0, 128, st) != cudaSuccess) return cuda_status();
   if (l2_on && near_bytes > 0) {
     int dev = 0, max_persist = 0, max_window = 0;
     cudaGetDevice(&dev);

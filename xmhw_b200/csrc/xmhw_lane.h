@@ -387,7 +387,9 @@ struct Sweeper {
   }
 
   // keys of the prefetched instance -> sorted block in the pool (EXACT: the list has exactly N rows)
-  template <int N, bool EXACT = false>
+  // FARFROM > 0 (needs EXACT): the caller checked keep + near_keys <= FARFROM, so the keys from rank
+  // FARFROM on all go to the far region -- plain stores, no placement tests.
+  template <int N, bool EXACT = false, int FARFROM = 0>
   XMHW_HD void consume(int base, int sbase, int size, int keep, int& len, int& ptr) {
     // all-land shortcut: a warp whose 32 cells have no valid sample in this list skips the key
     // conversion, sums and sort (ocean warps pay one compare + vote for the test)
@@ -433,6 +435,7 @@ struct Sweeper {
       const int nend = keep + near_keys < size ? keep + near_keys : size;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
+        if (FARFROM > 0 && i >= FARFROM) { frow[i * 32] = k[i]; continue; }
         if (i < keep) srow[i * 32] = k[i];                  // top `keep` keys: shared memory
         if (i >= keep && i < nend) grow[i * 32] = k[i];     // the next near_keys: near global scratch (L2)
         if (i >= nend && i < size) frow[i * 32] = k[i];     // sorted remainder: far global scratch
@@ -472,7 +475,8 @@ struct Sweeper {
     const bool loaded = (e >> 30) != 0;
     if (loaded) {
       if (size <= 8) consume<8>(base, sbase, size, keep, len, ptr);
-      else if (size == 30) consume<30, true>(base, sbase, size, keep, len, ptr);      // 30-year series: the common list
+      else if (size == 30 && keep + near_keys <= 16) consume<30, true, 16>(base, sbase, size, keep, len, ptr);   // 30-year series: the common list
+      else if (size == 30) consume<30, true>(base, sbase, size, keep, len, ptr);
       else if (MAXN == 32 || size <= 32) consume<32>(base, sbase, size, keep, len, ptr);
       else if (size <= 40) consume<(MAXN > 32 ? 40 : 32)>(base, sbase, size, keep, len, ptr);
       else consume<(MAXN > 32 ? 48 : 32)>(base, sbase, size, keep, len, ptr);
