@@ -38,7 +38,7 @@ extern "C" {
 #define XMHW_E_PLAN  (-2)   /* inconsistent climatology plan               */
 #define XMHW_E_SMEM  (-3)   /* plan needs more shared memory than one SM has */
 
-#define XMHW_ABI_VERSION 3
+#define XMHW_ABI_VERSION 2
 
 /* event table columns (struct-of-arrays, column c of event i at [c * cap + i]) */
 enum xmhw_event_i32 {
@@ -72,8 +72,8 @@ typedef struct xmhw_clim_plan {
   int32_t pool_rows;            /* shared-memory rows (128 B) per 32-cell warp  */
   int32_t nmax;                 /* q tables have nmax + 1 entries               */
   int32_t max_size;             /* largest list, <= 32                          */
-  int32_t scratch_rows;         /* NEAR global scratch rows (128 B) per resident warp */
-  int32_t scratch_split;        /* near_keys | far_mul << 8: far rows = scratch_rows * far_mul */
+  int32_t scratch_rows;         /* global scratch rows (128 B) per 32-cell warp  */
+  int32_t reserved_;
   const int32_t* inst_base;     /* [ninst]                                      */
   const int32_t* inst_size;     /* [ninst] time rows of the list (1..32)         */
   const int32_t* inst_keep;     /* [ninst] key rows held in shared memory        */
@@ -111,8 +111,7 @@ typedef struct xmhw_clim_plan2 {
   int32_t nslots;               /* unit slots per 32-cell warp, <= 32              */
   int32_t n_init;               /* atoms pushed before the first step              */
   int32_t cap;                  /* key rows per slot                               */
-  int32_t reuse_delay;          /* steps between a slot's pop and its reuse; >= 2 selects the sorter / merger
-                                   warp-pair kernel (two warps per 32 cells share the slots)              */
+  int32_t reserved_;
   double q;                     /* quantile in [0,1] (numpy 'linear': (n-1) q)     */
   uint32_t rec[XMHW_SC_MAX_STEPS][XMHW_SC_REC_WORDS];   /* step records            */
   uint32_t flip[XMHW_SC_MAX_FLIP];                      /* flip entries            */
@@ -127,11 +126,8 @@ const char* xmhw_strerror(int code);
  * Feb-29 rule and smoothing) for every grid cell: the general sorted-list sweep (any calendar,
  * any quantile).  ts [T][ngrid] f32 -> thresh_raw, seas_raw [nsteps][ngrid] f64 (NaN = no
  * sample), nempty [ngrid] i32 = number of doys without any sample.
- * scratch: caller-owned workspace of xmhw_clim_sweep_scratch_bytes(plan, ngrid) bytes (< 0: bad
- * plan): the sorted list tails of the warps resident on the device -- the kernel's blocks are
- * persistent, so the size depends on the device, not on ngrid.  Its first part (list sums + the keys
- * the cut visits) is pinned in L2 for the launch with an access-policy window.          */
-int64_t xmhw_clim_sweep_scratch_bytes(const xmhw_clim_plan* plan, int64_t ngrid);
+ * scratch: caller-owned workspace of ceil(ngrid/32) * plan->scratch_rows * 128 bytes
+ * (sorted list tails; stays L2-resident while a warp needs it).                       */
 int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan* plan,
                         double* thresh_raw, double* seas_raw, int32_t* nempty, uint32_t* scratch, void* stream);
 

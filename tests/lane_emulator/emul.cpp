@@ -27,11 +27,10 @@ template <int MAXN>
 static void sweep_cells(const float* ts, int64_t ngrid, const ClimPlan* plan, double* thr, double* seas) {
   std::vector<uint32_t> pool((size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 32);
   std::vector<uint32_t> scratch((size_t)(plan->scratch_rows + 1) * 32);
-  std::vector<uint32_t> far((size_t)(plan->scratch_rows * (plan->scratch_split >> 8) + 1) * 32);
   HostEnv env;
   for (int64_t cell = 0; cell < ngrid; ++cell) {
     const int lane = (int)(cell & 31);
-    Sweeper<HostEnv, MAXN> sw(env, *plan, pool.data(), scratch.data(), far.data(), lane, ts + cell, ngrid, true);
+    Sweeper<HostEnv, MAXN> sw(env, *plan, pool.data(), scratch.data(), lane, ts + cell, ngrid, true);
     sw.init();
     for (int s = 0; s < plan->nsteps; ++s) {
       double a, b;
@@ -62,32 +61,6 @@ static void sweep2_cells(const float* ts, int64_t ngrid, const ClimPlan2* plan, 
   }
 }
 
-template <int KP, int MAXN>
-static void sweep2_pair_cells(const float* ts, int64_t ngrid, const ClimPlan2* plan, double* thr, double* seas,
-                              int32_t* nzero) {
-  // the sorter / merger pair executed in the order the block barrier allows: sorter(g + 1), then merger(g)
-  std::vector<uint32_t> pool((size_t)(plan->nslots * plan->slot_rows + PAIR_MAILBOX_ROWS) * 32);
-  HostEnv env;
-  const int G = pair_groups(*plan);
-  for (int64_t cell = 0; cell < ngrid; ++cell) {
-    const int lane = (int)(cell & 31);
-    TopkSorter<HostEnv, MAXN> so(env, *plan, pool.data(), lane, ts + cell, ngrid);
-    TopkMerger<HostEnv, KP, MAXN> me(env, *plan, pool.data(), lane);
-    so.start();
-    so.group(0);
-    for (int g = 0; g < G; ++g) {
-      if (g + 1 < G) so.group(g + 1);
-      double a, b;
-      int row;
-      if (me.group(g, a, b, row)) {
-        thr[(int64_t)row * ngrid + cell] = a;
-        seas[(int64_t)row * ngrid + cell] = b;
-      }
-    }
-    nzero[cell] = me.nzero;
-  }
-}
-
 template <int KP>
 static void direct_cells(const float* ts, int64_t ngrid, const int32_t* rows, int nrows, double q, double* thr,
                          double* seas, int32_t* nzero) {
@@ -115,21 +88,6 @@ int emul_clim_sweep2(const float* ts, int64_t T, int64_t ngrid, const ClimPlan2*
     case 24: if (big) sweep2_cells<24, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<24, 32>(ts, ngrid, plan, thr, seas, nzero); break;
     case 36: if (big) sweep2_cells<36, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<36, 32>(ts, ngrid, plan, thr, seas, nzero); break;
     case 48: if (big) sweep2_cells<48, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<48, 32>(ts, ngrid, plan, thr, seas, nzero); break;
-    default: return -1;
-  }
-  return 0;
-}
-
-int emul_clim_sweep2_pair(const float* ts, int64_t T, int64_t ngrid, const ClimPlan2* plan, double* thr, double* seas,
-                          int32_t* nzero) {
-  (void)T;
-  const bool big = plan->max_size > 32;
-  switch (plan->kp) {
-    case 8: if (big) sweep2_pair_cells<8, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_pair_cells<8, 32>(ts, ngrid, plan, thr, seas, nzero); break;
-    case 16: if (big) sweep2_pair_cells<16, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_pair_cells<16, 32>(ts, ngrid, plan, thr, seas, nzero); break;
-    case 24: if (big) sweep2_pair_cells<24, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_pair_cells<24, 32>(ts, ngrid, plan, thr, seas, nzero); break;
-    case 36: if (big) sweep2_pair_cells<36, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_pair_cells<36, 32>(ts, ngrid, plan, thr, seas, nzero); break;
-    case 48: if (big) sweep2_pair_cells<48, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_pair_cells<48, 32>(ts, ngrid, plan, thr, seas, nzero); break;
     default: return -1;
   }
   return 0;

@@ -27,9 +27,9 @@ def _vp(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def sweep(em, ts, doy, ndoy, w, q, keep=None, near_keys=None):
+def sweep(em, ts, doy, ndoy, w, q, keep=None):
     lib, cabi = em
-    hp = P.build_clim_plan(doy, ndoy, w, q, keep=keep, near_keys=near_keys)
+    hp = P.build_clim_plan(doy, ndoy, w, q, keep=keep)
     s, keep = cabi.numpy_plan_struct(hp)
     ts = np.ascontiguousarray(ts, np.float32)
     T, ng = ts.shape
@@ -63,24 +63,18 @@ def test_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct, keep):
         ts[100:300, 3] = np.nan
         ts[:, 5] = np.nan
         ts[700:, 7] = np.nan
-    # near_keys: list keys behind `keep` that go to the near scratch region; small values push the
-    # cut into the far region (keep 3 -> 2 near keys, keep 1 -> 1), the default keeps it near
-    near = {16: None, 3: 2, 1: 1}[keep]
-    hp, thr, se = sweep(em, ts, doy, 366, w, pct / 100.0, keep=keep, near_keys=near)
+    hp, thr, se = sweep(em, ts, doy, 366, w, pct / 100.0, keep=keep)
     oth, ose = O.threshold(ts, doy, 366, pctile=pct, windowHalfWidth=w, smoothPercentile=False, tstep=True)
     assert bit_equal(thr, oth)
     assert np.nanmax(np.abs(se - ose), initial=0) <= 1e-12
     assert hp.rows_loaded < len(doy) * 1.1 and hp.max_size <= 48
-    if near is not None and hp.max_size > keep + near:
-        assert hp.far_mul >= 1 and hp.far_mul * (2 + near) >= hp.max_size - keep - near
 
 
-def sweep2(em, ts, doy, ndoy, w, q, pair=False):
-    """two-stack top-K sweep (csrc/xmhw_topk.h) + the direct selection of the exceptional doys;
-    pair: the sorter / merger warp-pair form of the same sweep (plan with slot reuse delayed by 2 steps)"""
+def sweep2(em, ts, doy, ndoy, w, q):
+    """two-stack top-K sweep (csrc/xmhw_topk.h) + the direct selection of the exceptional doys"""
     from xmhw_b200 import plan2 as P2
     lib, cabi = em
-    hp = P2.build_clim_plan2(doy, ndoy, w, q, reuse_delay=2 if pair else 0)
+    hp = P2.build_clim_plan2(doy, ndoy, w, q)
     if hp is None:
         return None, None, None, None
     s = cabi.plan2_struct(hp)
@@ -89,8 +83,7 @@ def sweep2(em, ts, doy, ndoy, w, q, pair=False):
     thr = np.full((ndoy, ng), np.nan)
     se = np.full((ndoy, ng), np.nan)
     nz = np.zeros(ng, np.int32)
-    fn = lib.emul_clim_sweep2_pair if pair else lib.emul_clim_sweep2
-    assert fn(_vp(ts), C.c_int64(T), C.c_int64(ng), C.byref(s), _vp(thr), _vp(se), _vp(nz)) == 0
+    assert lib.emul_clim_sweep2(_vp(ts), C.c_int64(T), C.c_int64(ng), C.byref(s), _vp(thr), _vp(se), _vp(nz)) == 0
     for k, d in enumerate(hp.exc_doy):
         rows = np.ascontiguousarray(hp.exc_rows[hp.exc_off[k]:hp.exc_off[k + 1]], np.int32)
         off = (int(d) - 1) * ng * 8
@@ -107,9 +100,8 @@ CASES2 = CASES + [
 ]
 
 
-@pytest.mark.parametrize("pair", [False, True], ids=["one_warp", "warp_pair"])
 @pytest.mark.parametrize("name,years,ncell,nan_ppm,w,pct", CASES2, ids=[c[0] for c in CASES2])
-def test_topk_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct, pair):
+def test_topk_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct):
     """The two-stack top-K sweep is bit-equal to the oracle wherever its plan accepts the calendar;
     the cases it declines (huge K, very wide windows) are the general sweep's (test above)."""
     tm = S.daily_time(*years)
@@ -119,7 +111,7 @@ def test_topk_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct, pair
         ts[100:300, 3] = np.nan
         ts[:, 5] = np.nan
         ts[700:, 7] = np.nan
-    hp, thr, se, nz = sweep2(em, ts, doy, 366, w, pct / 100.0, pair=pair)
+    hp, thr, se, nz = sweep2(em, ts, doy, 366, w, pct / 100.0)
     if name in ("70yr_two_pieces", "w15_p10"):
         assert hp is None
         return
@@ -128,7 +120,7 @@ def test_topk_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct, pair
     assert bit_equal(thr, oth)
     assert np.nanmax(np.abs(se - ose), initial=0) <= 1e-12
     assert np.array_equal(nz + (366 - hp.nsteps - len(hp.exc_doy)), np.isnan(oth).sum(axis=0))     # + absent labels
-    if name == "30yr" and not pair:
+    if name == "30yr":
         assert hp.kp == 36 and list(hp.exc_doy) == [60] and hp.pool_rows <= 444 and len(hp.pat) <= 8      # 4 warps per SM
 
 

@@ -30,7 +30,7 @@ _f64p = C.POINTER(C.c_double)
 class ClimPlanStruct(C.Structure):
     """Mirror of `xmhw_clim_plan` (include/xmhw_b200.h)."""
     _fields_ = [("nsteps", C.c_int32), ("pool_rows", C.c_int32), ("nmax", C.c_int32),
-                ("max_size", C.c_int32), ("scratch_rows", C.c_int32), ("scratch_split", C.c_int32),
+                ("max_size", C.c_int32), ("scratch_rows", C.c_int32), ("reserved_", C.c_int32),
                 ("inst_base", C.c_void_p), ("inst_size", C.c_void_p), ("inst_keep", C.c_void_p),
                 ("inst_sbase", C.c_void_p),
                 ("inst_row_off", C.c_void_p),
@@ -48,7 +48,7 @@ class ClimPlan2Struct(C.Structure):
     """Mirror of `xmhw_clim_plan2` (include/xmhw_b200.h): the two-stack top-K sweep, one plain host
     struct that the library copies into the kernel's launch parameters."""
     _fields_ = [("nsteps", C.c_int32), ("kp", C.c_int32), ("max_size", C.c_int32), ("slot_rows", C.c_int32),
-                ("nslots", C.c_int32), ("n_init", C.c_int32), ("cap", C.c_int32), ("reuse_delay", C.c_int32),
+                ("nslots", C.c_int32), ("n_init", C.c_int32), ("cap", C.c_int32), ("reserved_", C.c_int32),
                 ("q", C.c_double),
                 ("rec", C.c_uint32 * SC_REC_WORDS * SC_MAX_STEPS), ("flip", C.c_uint32 * SC_MAX_FLIP),
                 ("pat", C.c_int32 * SC_PAT_LEN * SC_MAX_PAT), ("init", C.c_uint32 * 2 * SC_MAX_INIT)]
@@ -71,7 +71,6 @@ PLAN_ARRAYS = ("inst_base", "inst_size", "inst_keep", "inst_sbase", "inst_row_of
 _SIGNATURES = {
     "xmhw_abi_version": (C.c_int, []),
     "xmhw_strerror": (C.c_char_p, [C.c_int]),
-    "xmhw_clim_sweep_scratch_bytes": (C.c_int64, [C.POINTER(ClimPlanStruct), C.c_int64]),
     "xmhw_clim_sweep_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlanStruct),
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_clim_sweep2_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlan2Struct),
@@ -141,7 +140,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 3
+ABI_VERSION = 2
 if lib.xmhw_abi_version() != ABI_VERSION:
     raise ImportError("xmhw_b200: ABI version mismatch in %s" % LIB_PATH)
 
@@ -163,7 +162,6 @@ def plan_struct(host_plan, pointers):
     s.nmax, s.max_size = host_plan.nmax, host_plan.max_size
     s.q = float(host_plan.q)
     s.scratch_rows = int(host_plan.scratch_rows)
-    s.scratch_split = int(host_plan.near_keys) | (int(host_plan.far_mul) << 8)
     for name in PLAN_ARRAYS:
         setattr(s, name, pointers[name])
     return s
@@ -172,7 +170,7 @@ def plan_struct(host_plan, pointers):
 def plan2_struct(host_plan):
     """Build a ClimPlan2Struct (host memory) from a plan2.ClimPlan2Host."""
     s = ClimPlan2Struct()
-    for f in ("nsteps", "kp", "max_size", "slot_rows", "nslots", "n_init", "cap", "reuse_delay"):
+    for f in ("nsteps", "kp", "max_size", "slot_rows", "nslots", "n_init", "cap"):
         setattr(s, f, int(getattr(host_plan, f)))
     s.q = float(host_plan.q)
 

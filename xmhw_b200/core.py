@@ -71,8 +71,7 @@ class DevicePlan:
 def device_plan(doy, ndoy, w, q, device):
     """Build (or fetch from cache) the climatology sweep plan on `device`."""
     doy = np.ascontiguousarray(doy, dtype=np.int64)
-    key = (hashlib.sha1(doy.tobytes()).hexdigest(), int(ndoy), int(w), float(q), str(device), _plan.default_keep(), _plan.default_pool_rows(),
-           _plan.default_near_keys())
+    key = (hashlib.sha1(doy.tobytes()).hexdigest(), int(ndoy), int(w), float(q), str(device), _plan.default_keep(), _plan.default_pool_rows())
     hit = _plan_cache.get(key)
     if hit is not None:
         return hit
@@ -116,13 +115,10 @@ def device_plan2(doy, ndoy, w, q, device):
     """Plan of the two-stack top-K sweep on `device`, or None when the calendar / quantile needs
     the general sweep (plan2.build_clim_plan2 returns None)."""
     doy = np.ascontiguousarray(doy, dtype=np.int64)
-    import os
-    # development knob: XMHW_B200_SWEEP2_PAIR=1 runs the top-K sweep as sorter / merger warp pairs
-    delay = 2 if os.environ.get("XMHW_B200_SWEEP2_PAIR", "0") == "1" else 0
-    key = ("topk", hashlib.sha1(doy.tobytes()).hexdigest(), int(ndoy), int(w), float(q), str(device), delay)
+    key = ("topk", hashlib.sha1(doy.tobytes()).hexdigest(), int(ndoy), int(w), float(q), str(device))
     if key in _plan_cache:
         return _plan_cache[key]
-    host = _plan2.build_clim_plan2(doy, ndoy, w, q, reuse_delay=delay)
+    host = _plan2.build_clim_plan2(doy, ndoy, w, q)
     dp = None
     if host is not None:
         dp = DevicePlan2(host, _cabi.plan2_struct(host),
@@ -134,20 +130,6 @@ def device_plan2(doy, ndoy, w, q, device):
 
 
 _csr_cache = {}
-_scratch_cache = {}
-
-
-def _sweep_scratch(nbytes, device):
-    """Workspace of the general sweep for the CURRENT stream of `device`: kept between calls so that its
-    address (the L2 access-policy window of the launch) and its L2-resident lines are reused."""
-    key = (str(device), int(torch.cuda.current_stream(device).cuda_stream))
-    t = _scratch_cache.get(key)
-    if t is None or t.numel() * 4 < nbytes:
-        t = None
-        _scratch_cache.pop(key, None)
-        t = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=device)
-        _scratch_cache[key] = t
-    return t
 
 
 def _doy_tables(doy, ndoy, device):
@@ -232,10 +214,7 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
             dp = device_plan(doy, ndoy, windowHalfWidth, q, ts.device)
             raw_t = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
             raw_s = torch.empty((ndoy, ngrid), dtype=torch.float64, device=ts.device)
-            nbytes = int(_cabi.lib.xmhw_clim_sweep_scratch_bytes(dp.struct, ngrid))
-            if nbytes < 0:
-                raise _cabi.XmhwCudaError("xmhw_clim_sweep_scratch_bytes: the plan does not fit this device")
-            scratch = _sweep_scratch(nbytes, ts.device)
+            scratch = torch.empty(max(1, ncg * dp.host.scratch_rows * 32), dtype=torch.int32, device=ts.device)
             _call("xmhw_clim_sweep_f32", _ptr(ts), T, ngrid, dp.struct, _ptr(raw_t), _ptr(raw_s), _ptr(nempty),
                   _ptr(scratch), st)
         W = int(smoothPercentileWidth) if smoothPercentile else 1

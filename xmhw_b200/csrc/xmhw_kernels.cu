@@ -59,39 +59,21 @@ __global__ void __launch_bounds__(32, MINB) clim_sweep_kernel(
     int32_t* __restrict__ nempty, uint32_t* __restrict__ scratch) {
   extern __shared__ uint32_t pool[];
   const int lane = threadIdx.x;
-  // PERSISTENT blocks: the grid is the number of warps the device holds at once; a block takes its next
-  // 32-cell group from a global ticket counter (all-land groups cost almost nothing, a static split
-  // would leave a third of the blocks idle at the end).  Its scratch rows are reused from group to
-  // group, so the near region (gridDim.x * scratch_rows rows, tens of MB) is rewritten in place inside
-  // L2 instead of being written back once per group.  Word 0 of the scratch is the ticket counter
-  // (zeroed by the launcher), the rows start one row later.
-  uint32_t* const rows0 = scratch + 32;
-  uint32_t* const near_rows = rows0 + (size_t)blockIdx.x * p.scratch_rows * 32;
-  uint32_t* const far_rows = rows0 + ((size_t)gridDim.x + (size_t)blockIdx.x * (p.scratch_split >> 8)) * p.scratch_rows * 32;
-  const int64_t ncg = (ngrid + 31) / 32;
+  const int64_t cell = (int64_t)blockIdx.x * 32 + lane;
+  const bool ok = cell < ngrid;
+  const float* col = ts + (ok ? cell : 0);
   WarpEnv env;
-  int64_t g = blockIdx.x;
-  while (g < ncg) {
-    const int64_t cell = g * 32 + lane;
-    const bool ok = cell < ngrid;
-    const float* col = ts + (ok ? cell : 0);
-    {
-      Sweeper<WarpEnv, MAXN> sw(env, p, pool, near_rows, far_rows, lane, col, ngrid, ok);
-      sw.init();
-      for (int s = 0; s < p.nsteps; ++s) {
-        double a, b;
-        sw.step(s, a, b);
-        if (ok) {
-          thr[(int64_t)s * ngrid + cell] = a;
-          seas[(int64_t)s * ngrid + cell] = b;
-        }
-      }
-      if (ok) nempty[cell] = sw.nzero;
+  Sweeper<WarpEnv, MAXN> sw(env, p, pool, scratch + (size_t)blockIdx.x * p.scratch_rows * 32, lane, col, ngrid, ok);
+  sw.init();
+  for (int s = 0; s < p.nsteps; ++s) {
+    double a, b;
+    sw.step(s, a, b);
+    if (ok) {
+      thr[(int64_t)s * ngrid + cell] = a;
+      seas[(int64_t)s * ngrid + cell] = b;
     }
-    unsigned ticket = 0;
-    if (lane == 0) ticket = atomicAdd(scratch, 1u);
-    g = (int64_t)gridDim.x + __shfl_sync(0xffffffffu, ticket, 0);
   }
+  if (ok) nempty[cell] = sw.nzero;
 }
 
 // ---------------------------------------------------------------------------
@@ -123,45 +105,6 @@ __global__ void __launch_bounds__(32 * WPB, MINB) clim_sweep2_kernel(
     if (WPB > 1) __syncthreads();
   }
   if (ok) nempty[cell] = sw.nzero;
-}
-
-// K1''  the same sweep by sorter / merger warp PAIRS (xmhw_topk.h): block = 2 warps = 32 cells, warp 0
-// sorts the atoms of push group g + 1 while warp 1 merges / flips / queries group g; one barrier per group.
-template <int KP, int MAXN>
-__global__ void __launch_bounds__(64) clim_sweep2_pair_kernel(
-    const __grid_constant__ ClimPlan2 p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr,
-    double* __restrict__ seas, int32_t* __restrict__ nempty) {
-  extern __shared__ uint32_t pool[];
-  const int lane = threadIdx.x & 31;
-  const bool merger = threadIdx.x >= 32;
-  const int64_t cell = (int64_t)blockIdx.x * 32 + lane;
-  const bool ok = cell < ngrid;
-  const float* col = ts + (ok ? cell : 0);
-  WarpEnv env;
-  const int G = pair_groups(p);
-  if (!merger) {
-    TopkSorter<WarpEnv, MAXN> so(env, p, pool, lane, col, ngrid);
-    so.start();
-    so.group(0);
-    __syncthreads();
-    for (int g = 0; g < G; ++g) {
-      if (g + 1 < G) so.group(g + 1);
-      __syncthreads();
-    }
-  } else {
-    TopkMerger<WarpEnv, KP, MAXN> me(env, p, pool, lane);
-    __syncthreads();
-    for (int g = 0; g < G; ++g) {
-      double a, b;
-      int row;
-      if (me.group(g, a, b, row) && ok) {
-        thr[(int64_t)row * ngrid + cell] = a;
-        seas[(int64_t)row * ngrid + cell] = b;
-      }
-      __syncthreads();
-    }
-    if (ok) nempty[cell] = me.nzero;
-  }
 }
 
 // doys whose window is not a range of the atom order (doy 60): direct selection, one thread = one cell
@@ -1163,55 +1106,6 @@ inline int cuda_status() {
 
 }  // namespace
 
-// launch shape of the general sweep: (blocks per SM asked for, kernel variant) -> resident blocks of the device
-namespace {
-struct SweepLaunch {
-  int variant;        // index into the XMHW_SWEEP_VARIANTS list below
-  int blocks;         // persistent grid = resident 1-warp blocks of the whole device
-  size_t smem;
-};
-int sweep_minb() {
-  static const int minb = getenv("XMHW_B200_SWEEP_MINB") ? atoi(getenv("XMHW_B200_SWEEP_MINB")) : 16;   // development knob
-  return minb;
-}
-template <int N, int B>
-cudaError_t sweep_occupancy(size_t smem, int* per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(clim_sweep_kernel<N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, clim_sweep_kernel<N, B>, 32, smem);
-}
-int sweep_launch_shape(const xmhw_clim_plan* plan, int64_t ngrid, SweepLaunch* out) {
-  if (plan->nsteps <= 0 || plan->pool_rows <= 0 || plan->max_size > 48 || plan->nmax <= 0) return XMHW_E_PLAN;
-  size_t smem = (size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 128;
-  static const int smem_pad = getenv("XMHW_B200_SWEEP_SMEM_PAD") ? atoi(getenv("XMHW_B200_SWEEP_SMEM_PAD")) : 0;
-  smem += (size_t)smem_pad;       // development knob: lowers the resident warps per SM without touching the code
-  if (smem > 227 * 1024) return XMHW_E_SMEM;
-  const int minb = sweep_minb();
-  int variant, per_sm = 0;
-  cudaError_t e;
-  if (plan->max_size <= 32) {
-    if (minb >= 24) { variant = 0; e = sweep_occupancy<32, 24>(smem, &per_sm); }
-    else if (minb >= 20) { variant = 1; e = sweep_occupancy<32, 20>(smem, &per_sm); }
-    else if (minb >= 16) { variant = 2; e = sweep_occupancy<32, 16>(smem, &per_sm); }
-    else if (minb >= 14) { variant = 3; e = sweep_occupancy<32, 14>(smem, &per_sm); }
-    else { variant = 4; e = sweep_occupancy<32, 12>(smem, &per_sm); }
-  } else {
-    variant = 5; e = sweep_occupancy<48, 10>(smem, &per_sm);
-  }
-  if (e != cudaSuccess) return (int)e;
-  int dev = 0, sms = 0;
-  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
-  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
-  if (per_sm <= 0 || sms <= 0) return XMHW_E_SMEM;
-  const int64_t ncg = (ngrid + 31) / 32;
-  const int64_t resident = (int64_t)per_sm * sms;
-  out->variant = variant;
-  out->blocks = (int)(ncg < resident ? ncg : resident);
-  out->smem = smem;
-  return 0;
-}
-}  // namespace
-
 extern "C" {
 
 int xmhw_abi_version(void) { return XMHW_ABI_VERSION; }
@@ -1226,76 +1120,36 @@ const char* xmhw_strerror(int code) {
   }
 }
 
-int64_t xmhw_clim_sweep_scratch_bytes(const xmhw_clim_plan* plan, int64_t ngrid) {
-  if (!plan || ngrid <= 0 || plan->scratch_rows < 0) return -1;
-  SweepLaunch L;
-  if (sweep_launch_shape(plan, ngrid, &L) != 0) return -1;
-  const int64_t far_mul = plan->scratch_split >> 8;
-  return (int64_t)L.blocks * plan->scratch_rows * (1 + far_mul) * 128 + 256;      // + ticket row + slack
-}
-
 int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan* plan,
                         double* thresh_raw, double* seas_raw, int32_t* nempty, uint32_t* scratch, void* stream) {
   if (!ts || !plan || !thresh_raw || !seas_raw || !nempty || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
   if (plan->scratch_rows < 0 || (plan->scratch_rows > 0 && !scratch)) return XMHW_E_ARG;
-  if ((plan->scratch_split & 0xff) <= 0) return XMHW_E_PLAN;
   if (ngrid > 0xffffffffll || T > 0x7fffffffll) return XMHW_E_ARG;
-  SweepLaunch L;
-  const int rc = sweep_launch_shape(plan, ngrid, &L);
-  if (rc != 0) return rc;
+  if (plan->nsteps <= 0 || plan->pool_rows <= 0 || plan->max_size > 48 || plan->nmax <= 0) return XMHW_E_PLAN;
+  size_t smem = (size_t)(plan->pool_rows + POOL_STAGE_ROWS) * 128;
+  static const int smem_pad = getenv("XMHW_B200_SWEEP_SMEM_PAD") ? atoi(getenv("XMHW_B200_SWEEP_SMEM_PAD")) : 0;
+  smem += (size_t)smem_pad;       // development knob: lowers the resident warps per SM without touching the code
+  if (smem > 227 * 1024) return XMHW_E_SMEM;
   ClimPlan p;
   memcpy(&p, plan, sizeof(p));
-  cudaStream_t st = (cudaStream_t)stream;
-  // The near scratch region (list sums + the keys the cut visits) is pinned in L2 for the launch: an
-  // access-policy window with the persisting property over exactly that region, inside an L2 set-aside
-  // of the same size.  Without it the 45 GB input stream evicts the rows between their write and their
-  // read ~10 steps later and every pop of the walk waits for DRAM.  Development knob
-  // XMHW_B200_SWEEP_L2 = 0 disables the window.  A device without the feature just runs without it.
-  static const int l2_on = getenv("XMHW_B200_SWEEP_L2") ? atoi(getenv("XMHW_B200_SWEEP_L2")) : 1;
-  const size_t near_bytes = (size_t)L.blocks * plan->scratch_rows * 128 + 128;      // ticket row + near rows
-  bool window = false;
-  if (cudaMemsetAsync(scratch, 0, 128, st) != cudaSuccess) return cuda_status();
-  if (l2_on && near_bytes > 0) {
-    int dev = 0, max_persist = 0, max_window = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-    if (max_persist > 0 && max_window > 0) {
-      static size_t set_aside[64] = {0};
-      const size_t want = near_bytes < (size_t)max_persist ? near_bytes : (size_t)max_persist;
-      if (dev < 64 && set_aside[dev] < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
-        set_aside[dev] = want;
-      cudaStreamAttrValue v;
-      memset(&v, 0, sizeof(v));
-      v.accessPolicyWindow.base_ptr = scratch;
-      v.accessPolicyWindow.num_bytes = near_bytes < (size_t)max_window ? near_bytes : (size_t)max_window;
-      const double hr = (double)want / (double)v.accessPolicyWindow.num_bytes;
-      v.accessPolicyWindow.hitRatio = hr < 1.0 ? (float)hr : 1.0f;
-      v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess;
-    }
-    cudaGetLastError();           // the window is an optimisation: its errors do not fail the call
+  const int64_t ncg = (ngrid + 31) / 32;
+  cudaError_t e;
+  static const int minb = getenv("XMHW_B200_SWEEP_MINB") ? atoi(getenv("XMHW_B200_SWEEP_MINB")) : 16;   // development knob
+#define XMHW_SWEEP(N, B)                                                                                            \
+  {                                                                                                                 \
+    e = cudaFuncSetAttribute(clim_sweep_kernel<N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e != cudaSuccess) return (int)e;                                                                            \
+    clim_sweep_kernel<N, B><<<(unsigned)ncg, 32, smem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw,  \
+                                                                               nempty, scratch);                   \
   }
-#define XMHW_SWEEP(N, B)                                                                                       \
-  clim_sweep_kernel<N, B><<<(unsigned)L.blocks, 32, L.smem, st>>>(p, ts, ngrid, thresh_raw, seas_raw, nempty, scratch);
-  switch (L.variant) {
-    case 0: XMHW_SWEEP(32, 24) break;
-    case 1: XMHW_SWEEP(32, 20) break;
-    case 2: XMHW_SWEEP(32, 16) break;
-    case 3: XMHW_SWEEP(32, 14) break;
-    case 4: XMHW_SWEEP(32, 12) break;
-    default: XMHW_SWEEP(48, 10) break;
+  if (plan->max_size <= 32) {
+    if (minb >= 24) XMHW_SWEEP(32, 24) else if (minb >= 20) XMHW_SWEEP(32, 20) else if (minb >= 16) XMHW_SWEEP(32, 16)
+    else if (minb >= 14) XMHW_SWEEP(32, 14) else XMHW_SWEEP(32, 12)
+  } else {
+    XMHW_SWEEP(48, 10)
   }
 #undef XMHW_SWEEP
-  const int status = cuda_status();
-  if (window) {
-    cudaStreamAttrValue v;
-    memset(&v, 0, sizeof(v));
-    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);      // later launches: no window
-    cudaGetLastError();
-  }
-  return status;
+  return cuda_status();
 }
 
 int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan2* plan,
@@ -1329,27 +1183,6 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
 #define XMHW_SWEEP2(K, N)                                                                                            \
   { if (wpb == 4) XMHW_SWEEP2_W(K, N, 4) else if (wpb == 2) XMHW_SWEEP2_W(K, N, 2) else XMHW_SWEEP2_W(K, N, 1) }
   const bool big = plan->max_size > 32;
-  if (plan->reuse_delay >= 2) {          // sorter / merger warp pairs
-    const size_t psmem = smem1 + (size_t)PAIR_MAILBOX_ROWS * 128;
-    if (psmem > 227 * 1024) return XMHW_E_SMEM;
-#define XMHW_PAIR(K, N)                                                                                              \
-  {                                                                                                                  \
-    e = cudaFuncSetAttribute(clim_sweep2_pair_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem); \
-    if (e != cudaSuccess) return (int)e;                                                                             \
-    clim_sweep2_pair_kernel<K, N><<<(unsigned)ncg, 64, psmem, (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw,      \
-                                                                                      seas_raw, nempty);             \
-  }
-    switch (plan->kp) {
-      case 8: if (big) XMHW_PAIR(8, 48) else XMHW_PAIR(8, 32) break;
-      case 16: if (big) XMHW_PAIR(16, 48) else XMHW_PAIR(16, 32) break;
-      case 24: if (big) XMHW_PAIR(24, 48) else XMHW_PAIR(24, 32) break;
-      case 36: if (big) XMHW_PAIR(36, 48) else XMHW_PAIR(36, 32) break;
-      case 48: if (big) XMHW_PAIR(48, 48) else XMHW_PAIR(48, 32) break;
-      default: return XMHW_E_PLAN;
-    }
-#undef XMHW_PAIR
-    return cuda_status();
-  }
   switch (plan->kp) {
     case 8: if (big) XMHW_SWEEP2(8, 48) else XMHW_SWEEP2(8, 32) break;
     case 16: if (big) XMHW_SWEEP2(16, 48) else XMHW_SWEEP2(16, 32) break;

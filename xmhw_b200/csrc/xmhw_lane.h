@@ -16,7 +16,6 @@
 //   per-event statistics               xmhw/features.py:22-295
 #pragma once
 #include <stdint.h>
-#include <stddef.h>
 #include <math.h>
 #include <string.h>
 
@@ -127,9 +126,8 @@ struct ClimPlan {
   int32_t pool_rows;             // shared-memory rows (32 words each) per warp
   int32_t nmax;                  // max samples per window (size of q tables - 1)
   int32_t max_size;              // largest instance (<= 32)
-  int32_t scratch_rows;          // NEAR global scratch rows (32 words each) per warp; FAR: scratch_rows * far_mul
-  int32_t scratch_split;         // near_keys | far_mul << 8 (plan.py): key keep + j of a list lives in its near
-                                 // block for j < near_keys, else in far row sbase * far_mul + j - near_keys
+  int32_t scratch_rows;          // global scratch rows (32 words each) per warp
+  int32_t reserved_;
   const int32_t* inst_base;      // [ninst] first pool row of the instance block
   const int32_t* inst_size;      // [ninst] number of time rows (1..32)
   const int32_t* inst_keep;      // [ninst] key rows held in shared memory (1..size)
@@ -305,9 +303,7 @@ struct Sweeper {
   const Env& env;
   const ClimPlan& p;
   uint32_t* pool;
-  uint32_t* scratch;     // this warp's NEAR global scratch rows (list sums, the first sorted keys past `keep`)
-  uint32_t* far;         // this warp's FAR global scratch rows (the keys behind those)
-  const int near_keys, far_mul;
+  uint32_t* scratch;     // this warp's global scratch rows (sorted keys past `keep`)
   const int lane;
   const float* col;
   const int64_t ngrid;
@@ -323,10 +319,8 @@ struct Sweeper {
   int nzero;             // steps without any sample (per-cell doy compaction of the smoothing)
   Vec rec_next, use_next;   // step record / list bases of the next step (prefetched)
 
-  XMHW_HD Sweeper(const Env& e, const ClimPlan& pl, uint32_t* po, uint32_t* sc, uint32_t* fa, int ln, const float* c,
-                  int64_t ng, bool k)
-      : env(e), p(pl), pool(po), scratch(sc), far(fa), near_keys(pl.scratch_split & 0xff), far_mul(pl.scratch_split >> 8),
-        lane(ln), col(c), ngrid(ng), ok(k), C(0), n(0), wsum(0.0), pivot(0xffffffffu), nzero(0) {}
+  XMHW_HD Sweeper(const Env& e, const ClimPlan& pl, uint32_t* po, uint32_t* sc, int ln, const float* c, int64_t ng, bool k)
+      : env(e), p(pl), pool(po), scratch(sc), lane(ln), col(c), ngrid(ng), ok(k), C(0), n(0), wsum(0.0), pivot(0xffffffffu), nzero(0) {}
 
   XMHW_HD uint32_t& at(int row) { return pool[row * 32 + lane]; }
 
@@ -367,12 +361,7 @@ struct Sweeper {
     const bool in_pool = r < keep;
     // shared-memory read is unconditional (row clamped into the block); the scratch read is the rare path
     uint32_t k = at(base + POOL_KEYS + ((in_pool && need) ? r : 0));
-    if (need && !in_pool) {
-      const int j = r - keep, sb = meta_sbase(meta);
-      const uint32_t* const src = j < near_keys ? scratch + (size_t)(sb + SCR_KEYS + j) * 32
-                                                : far + (size_t)(sb * far_mul + j - near_keys) * 32;
-      k = src[lane];
-    }
+    if (need && !in_pool) k = scratch[(size_t)(meta_sbase(meta) + SCR_KEYS + r - keep) * 32 + lane];
     return need ? k : 0u;
   }
 
@@ -387,9 +376,7 @@ struct Sweeper {
   }
 
   // keys of the prefetched instance -> sorted block in the pool (EXACT: the list has exactly N rows)
-  // FARFROM > 0 (needs EXACT): the caller checked keep + near_keys <= FARFROM, so the keys from rank
-  // FARFROM on all go to the far region -- plain stores, no placement tests.
-  template <int N, bool EXACT = false, int FARFROM = 0>
+  template <int N, bool EXACT = false>
   XMHW_HD void consume(int base, int sbase, int size, int keep, int& len, int& ptr) {
     // all-land shortcut: a warp whose 32 cells have no valid sample in this list skips the key
     // conversion, sums and sort (ocean warps pay one compare + vote for the test)
@@ -429,16 +416,11 @@ struct Sweeper {
     if (env.any(len > 0)) {
       sort_desc<N>(k);
       uint32_t* const srow = pool + (base + POOL_KEYS) * 32 + lane;
-      // row i of the list relative to each region (the offsets may be negative: i >= keep, i >= keep + near_keys)
-      uint32_t* const grow = scratch + ((ptrdiff_t)(sbase + SCR_KEYS) - (ptrdiff_t)keep) * 32 + lane;
-      uint32_t* const frow = far + ((ptrdiff_t)sbase * far_mul - (ptrdiff_t)(keep + near_keys)) * 32 + lane;
-      const int nend = keep + near_keys < size ? keep + near_keys : size;
+      uint32_t* const grow = scratch + ((size_t)(sbase + SCR_KEYS) - (size_t)keep) * 32 + lane;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        if (FARFROM > 0 && i >= FARFROM) { frow[i * 32] = k[i]; continue; }
         if (i < keep) srow[i * 32] = k[i];                  // top `keep` keys: shared memory
-        if (i >= keep && i < nend) grow[i * 32] = k[i];     // the next near_keys: near global scratch (L2)
-        if (i >= nend && i < size) frow[i * 32] = k[i];     // sorted remainder: far global scratch
+        if (i >= keep && i < size) grow[i * 32] = k[i];     // sorted remainder: global scratch
       }
       if (N == 30) {                 // the halving search wants a power of two: two 0 keys (below every pivot) appended
         uint32_t k32[32];
@@ -475,8 +457,7 @@ struct Sweeper {
     const bool loaded = (e >> 30) != 0;
     if (loaded) {
       if (size <= 8) consume<8>(base, sbase, size, keep, len, ptr);
-      else if (size == 30 && keep + near_keys <= 16) consume<30, true, 16>(base, sbase, size, keep, len, ptr);   // 30-year series: the common list
-      else if (size == 30) consume<30, true>(base, sbase, size, keep, len, ptr);
+      else if (size == 30) consume<30, true>(base, sbase, size, keep, len, ptr);      // 30-year series: the common list
       else if (MAXN == 32 || size <= 32) consume<32>(base, sbase, size, keep, len, ptr);
       else if (size <= 40) consume<(MAXN > 32 ? 40 : 32)>(base, sbase, size, keep, len, ptr);
       else consume<(MAXN > 32 ? 48 : 32)>(base, sbase, size, keep, len, ptr);

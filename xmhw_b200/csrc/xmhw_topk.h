@@ -41,7 +41,7 @@ struct ClimPlan2 {
   int32_t nslots;        // slots (= units alive at once)
   int32_t n_init;        // atoms pushed before the first step
   int32_t cap;           // key rows per slot = max(kp, rows of the largest unit)
-  int32_t reuse_delay;
+  int32_t reserved_;
   double q;              // quantile in [0,1]; numpy 'linear': v = (n-1) q
   uint32_t rec[SC_MAX_STEPS][SC_REC_WORDS];   // step records (REC_*)
   uint32_t flip[SC_MAX_FLIP];                 // flip entries (FLIP_*)
@@ -317,282 +317,6 @@ struct TopkSweeper {
       thresh = qnan();
       seas = qnan();
     }
-  }
-};
-
-// ---------------------------------------------------------------------------
-// Sorter / merger warp PAIRS: the same sweep with the work of a step split over two warps that
-// share one pool (and the same 32 cells).  The sorter runs one push group ahead: it converts and
-// sorts the atoms of group g + 1 and parks them in their slots while the merger merges the atoms
-// of group g (read back from the stash), flips, queries and writes the doy's result; one block
-// barrier per group.  Groups: the initial fill in chunks of 3 atoms, then one group per sweep step.
-// The plan must have been built with reuse_delay = 2 (plan2.py): the sorter writes into the slot of
-// step s + 1's atom while the merger still reads the slots popped at step s.  The per-atom sample
-// count and f64 sum travel in a small double-buffered mailbox behind the pool.
-// ---------------------------------------------------------------------------
-enum { PAIR_MAILBOX_ROWS = 2 * 3 * 3 };     // [parity][atom of the group][len, sum lo, sum hi]
-
-XMHW_HD int pair_init_groups(const ClimPlan2& p) { return (p.n_init + 2) / 3; }
-XMHW_HD int pair_groups(const ClimPlan2& p) { return pair_init_groups(p) + p.nsteps; }
-
-// atoms of group g: descriptors d0[j], d1[j] and the descriptor of the atom that follows the group's last
-XMHW_HD int pair_group_atoms(const ClimPlan2& p, int g, uint32_t (&d0)[3], uint32_t (&d1)[3], uint32_t& n0, uint32_t& n1) {
-  const int gi = pair_init_groups(p);
-  int na;
-  if (g < gi) {
-    const int a0 = 3 * g;
-    na = p.n_init - a0 < 3 ? p.n_init - a0 : 3;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { d0[j] = j < na ? p.init[a0 + j][0] : 0u; d1[j] = j < na ? p.init[a0 + j][1] : 0u; }
-    n0 = p.init[a0 + na][0]; n1 = p.init[a0 + na][1];             // init has n_init + 1 entries
-  } else {
-    const uint32_t* const rec = p.rec[g - gi];
-    na = (int)((rec[0] >> 3) & 3u);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { d0[j] = j < na ? rec[REC_PUSH + 2 * j] : 0u; d1[j] = j < na ? rec[REC_PUSH + 2 * j + 1] : 0u; }
-    n0 = rec[REC_NEXT]; n1 = rec[REC_NEXT + 1];
-  }
-  return na;
-}
-
-template <class Env, int MAXN>
-struct TopkSorter {
-  const Env& env;
-  const ClimPlan2& p;
-  uint32_t* pool;
-  const int lane;
-  const float* col;
-  const int64_t ngrid;
-  float pv[MAXN];
-  uint32_t last0, last1;      // descriptor of the atom sitting in pv (0: none)
-
-  XMHW_HD TopkSorter(const Env& e, const ClimPlan2& pl, uint32_t* po, int ln, const float* c, int64_t ng)
-      : env(e), p(pl), pool(po), lane(ln), col(c), ngrid(ng), last0(0u), last1(0u) {}
-
-  XMHW_HD void prefetch(uint32_t d0, uint32_t d1) {
-    const uint32_t ng4 = (uint32_t)ngrid * 4u;
-    const int32_t* const pt = p.pat[d1 & 31u];
-    const char* const cb = reinterpret_cast<const char*>(col) + (uint64_t)(d0 & 0xffffffu) * ng4;
-#pragma unroll
-    for (int i = 0; i < MAXN; ++i) pv[i] = XMHW_LDG(reinterpret_cast<const float*>(cb + (uint64_t)(uint32_t)pt[i] * ng4));
-  }
-  XMHW_HD void start() { prefetch(p.init[0][0], p.init[0][1]); }
-
-  // atom in pv -> sorted keys in its slot, (len, sum) in the mailbox
-  XMHW_HD void sort_atom(uint32_t d0, uint32_t d1, int parity, int j) {
-    const int size = (int)((d0 >> 24) & 63u);
-    const bool ragged = ((d1 >> 17) & 1u) != 0u;
-    const int slot_base = (int)((d1 >> 5) & 31u) * p.slot_rows, off = (int)((d1 >> 10) & 127u);
-    uint32_t k[MAXN];
-    int len = 0;
-    double sum = 0.0;
-#pragma unroll
-    for (int i = 0; i < MAXN; ++i) {
-      const float v = pv[i];
-      const uint32_t b = f32_bits(v);
-      const bool valid = i < size && v == v;       // lanes past the grid edge compute on cell 0: never stored
-      k[i] = valid ? (b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u)) : 0u;
-      len += valid ? 1 : 0;
-      sum = sum + (double)(valid ? v : 0.0f);
-    }
-    if (env.any(len > 0)) sort_desc<MAXN>(k);
-    uint32_t* const srow = pool + (slot_base + 1 + off) * 32 + lane;
-    if (ragged) {
-#pragma unroll
-      for (int i = 0; i < MAXN; ++i)
-        if (i < size) srow[i * 32] = k[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < MAXN; ++i) srow[i * 32] = k[i];
-    }
-    uint32_t* const mb = pool + (p.nslots * p.slot_rows + (parity * 3 + j) * 3) * 32 + lane;
-    mb[0] = (uint32_t)len; mb[32] = f64_lo(sum); mb[64] = f64_hi(sum);
-  }
-
-  XMHW_HD void group(int g) {
-    uint32_t d0[3], d1[3], n0, n1;
-    const int na = pair_group_atoms(p, g, d0, d1, n0, n1);
-#pragma unroll 1
-    for (int j = 0; j < na; ++j) {
-      sort_atom(d0[j], d1[j], g & 1, j);
-      const uint32_t x0 = j + 1 < na ? d0[(j + 1) % 3] : n0, x1 = j + 1 < na ? d1[(j + 1) % 3] : n1;
-      if ((x0 >> 24) & 63u) prefetch(x0, x1);
-    }
-  }
-};
-
-template <class Env, int KP, int MAXN>
-struct TopkMerger {
-  const Env& env;
-  const ClimPlan2& p;
-  uint32_t* pool;
-  const int lane;
-  uint32_t A[KP];
-  int n, nzero;
-  double wsum;
-
-  XMHW_HD TopkMerger(const Env& e, const ClimPlan2& pl, uint32_t* po, int ln)
-      : env(e), p(pl), pool(po), lane(ln), n(0), nzero(0), wsum(0.0) {
-#pragma unroll
-    for (int i = 0; i < KP; ++i) A[i] = 0u;
-  }
-  XMHW_HD uint32_t& at(int row) { return pool[row * 32 + lane]; }
-
-  // a stashed atom (sorted keys in its slot) goes into the accumulator
-  XMHW_HD void merge_stashed(int slot_base, int off, int size, int flags, bool acc) {
-    uint32_t k[MAXN];
-    const uint32_t* const srow = pool + (slot_base + 1 + off) * 32 + lane;
-    if (flags & JOB_F_RAGGED) {
-#pragma unroll
-      for (int i = 0; i < MAXN; ++i) k[i] = i < size ? srow[i * 32] : 0u;
-    } else {
-#pragma unroll
-      for (int i = 0; i < MAXN; ++i) k[i] = srow[i * 32];
-    }
-    if (flags & JOB_F_COPY) {
-#pragma unroll
-      for (int i = 0; i < KP; ++i) A[i] = (acc && i < MAXN) ? k[i] : 0u;
-    } else if (acc) {
-      merge_topk<KP, MAXN>(A, k);
-    }
-  }
-  XMHW_HD void store_acc(int slot_base, bool alive) {
-    uint32_t* const srow = pool + (slot_base + 1) * 32 + lane;
-    if (alive) {
-#pragma unroll
-      for (int i = 0; i < KP; ++i) srow[i * 32] = A[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < KP; ++i) srow[i * 32] = 0u;
-    }
-  }
-  // push of atom j of the group: bookkeeping from the mailbox + merge of its stash
-  XMHW_HD void push(uint32_t d0, uint32_t d1, int parity, int j) {
-    const int size = (int)((d0 >> 24) & 63u);
-    const int flags = (int)(d0 >> 30) | (int)(((d1 >> 17) & 1u) * JOB_F_RAGGED);
-    const int slot_base = (int)((d1 >> 5) & 31u) * p.slot_rows, off = (int)((d1 >> 10) & 127u);
-    const uint32_t* const mb = pool + (p.nslots * p.slot_rows + (parity * 3 + j) * 3) * 32 + lane;
-    const int len = (int)mb[0];
-    const double sum = f64_from(mb[32], mb[64]);
-    uint32_t* const lrow = pool + slot_base * 32 + lane;
-    uint32_t* const sum_row = pool + (slot_base + 1 + p.cap) * 32 + lane;
-    if (flags & JOB_F_FIRST) {
-      lrow[0] = XMHW_GUARD | (uint32_t)len;
-      sum_row[0] = f64_lo(sum); sum_row[32] = f64_hi(sum);
-    } else {
-      lrow[0] = lrow[0] + (uint32_t)len;
-      const double s2 = f64_from(sum_row[0], sum_row[32]) + sum;
-      sum_row[0] = f64_lo(s2); sum_row[32] = f64_hi(s2);
-    }
-    n += len;
-    wsum = wsum + sum;
-    merge_stashed(slot_base, off, size, flags, env.any(len > 0));
-  }
-
-  // group g; returns true when it was a sweep step (thresh / seas / out_row are then set)
-  XMHW_HD bool group(int g, double& thresh, double& seas, int& out_row) {
-    uint32_t d0[3], d1[3], n0, n1;
-    const int na = pair_group_atoms(p, g, d0, d1, n0, n1);
-    const int gi = pair_init_groups(p);
-    if (g < gi) {
-#pragma unroll 1
-      for (int j = 0; j < na; ++j) push(d0[j % 3], d1[j % 3], g & 1, j);
-      return false;
-    }
-    const uint32_t* const rec = p.rec[g - gi];
-    const uint32_t w0 = rec[0];
-    const int n_pop = (int)(w0 & 7u), n_flip = (int)((w0 >> 6) & 63u);
-    const bool flip_late = ((w0 >> 5) & 1u) != 0u;
-    const int front_base = (int)((w0 >> 12) & 31u) * p.slot_rows;
-    out_row = (int)(w0 >> 17);
-    double psum = 0.0;
-    {
-      const uint32_t pw = rec[REC_POPS];
-      for (int j = 0; j < n_pop; ++j) {
-        const int sb = (int)((pw >> (5 * j)) & 31u) * p.slot_rows;
-        n -= (int)(at(sb) & 0xffu);
-        psum = psum + f64_from(at(sb + 1 + p.cap), at(sb + 2 + p.cap));
-      }
-    }
-    const int flip_off = (int)rec[REC_FLIP_OFF];
-    bool alive = true;
-    const int n_jobs = na + n_flip;
-#pragma unroll 1
-    for (int jb = 0; jb < n_jobs; ++jb) {
-      const bool is_push = flip_late ? jb < na : jb >= n_flip;
-      if (is_push) {
-        const int j = flip_late ? jb : jb - n_flip;
-        push(d0[j % 3], d1[j % 3], g & 1, j);
-        continue;
-      }
-      const int e = flip_late ? jb - na : jb;
-      if (e == 0) alive = env.any(n > 0);
-      const uint32_t f0 = p.flip[flip_off + e];
-      const int slot_base = (int)(f0 & 31u) * p.slot_rows, off = (int)((f0 >> 5) & 127u);
-      const int size = (int)((f0 >> 12) & 63u), flags = (int)((f0 >> 18) & 63u);
-      const int dst_base = (int)((f0 >> 24) & 31u) * p.slot_rows;
-      if (flags & JOB_F_CLEAR) {
-#pragma unroll
-        for (int i = 0; i < KP; ++i) A[i] = 0u;
-        continue;
-      }
-      if (flags & JOB_F_STOREP) { store_acc(dst_base, alive); continue; }
-      merge_stashed(slot_base, off, size, flags, alive);
-      if (flags & JOB_F_STORE) store_acc(slot_base, alive);
-    }
-    wsum = wsum - psum;
-    const bool live = n > 0;
-    nzero += live ? 0 : 1;
-    if (!env.any(live)) { thresh = qnan(); seas = qnan(); return true; }
-    if (env.any(!(wsum - wsum == 0.0))) {
-      uint32_t alive_slots = rec[REC_ALIVE];
-      double fresh = 0.0;
-      while (alive_slots) {
-        const int sb = ctz32(alive_slots) * p.slot_rows;
-        alive_slots &= alive_slots - 1u;
-        fresh = fresh + f64_from(at(sb + 1 + p.cap), at(sb + 2 + p.cap));
-      }
-      if (!(wsum - wsum == 0.0)) wsum = fresh;
-    }
-    int target = 1;
-    double gamma = 0.0;
-    if (live) {
-      const double nm1 = (double)(n - 1);
-      const double v = nm1 * p.q;
-      double fl = floor(v);
-      gamma = v - fl;
-      if (v >= nm1) { fl = nm1; gamma = 0.0; }
-      target = n - (int)fl;
-    }
-    // the query of TopkSweeper::step: loop over the warp's distinct ranks, warp-uniform rows
-    const uint32_t* const srow = pool + front_base * 32 + lane;
-    uint32_t r1 = 0u, r2 = 0u;
-    int todo = live ? (target < KP ? target : KP) : 0;
-    while (true) {
-      const int kk = env.max_all(todo);
-      if (kk == 0) break;
-      uint32_t q1 = 0u, q2 = 0u;
-      uint32_t am1 = 0xffffffffu, am2 = 0u;
-#pragma unroll
-      for (int i = 0; i <= KP; ++i) {
-        const int row = kk - i > 0 ? kk - i : 0;
-        const uint32_t sv = srow[row * 32];
-        q1 = umax32(q1, umin32(am1, sv));
-        if (i >= 1) q2 = umax32(q2, umin32(am2, sv));
-        am2 = am1;
-        am1 = i < KP ? A[i] : 0u;
-      }
-      if (todo == kk) { r1 = q1; r2 = q2; todo = 0; }
-    }
-    if (live) {
-      const uint32_t kb = target >= 2 ? r2 : r1;
-      thresh = lerp_q(key_f32(r1), key_f32(kb), gamma);
-      seas = wsum / (double)n;
-    } else {
-      thresh = qnan();
-      seas = qnan();
-    }
-    return true;
   }
 };
 

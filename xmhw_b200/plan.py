@@ -36,13 +36,6 @@ STAGE_ROWS = 2         # two rows after the pool: staged bases of the lists in u
 MAX_LISTS = 64
 LOAD_FLAG = 1 << 30
 MAX_GAP_STEPS = 2      # a class stays resident across holes of up to this many sweep steps
-NEAR_KEYS = 8          # scratch keys per list right behind `keep` that live in the NEAR (L2-persisting) region
-
-
-def default_near_keys():
-    """Keys per list in the near scratch region (development knob XMHW_B200_SWEEP_NEAR; >= 48: no far region)."""
-    import os
-    return int(os.environ.get("XMHW_B200_SWEEP_NEAR", str(NEAR_KEYS)))
 
 
 @dataclass
@@ -52,8 +45,6 @@ class ClimPlanHost:
     nmax: int
     max_size: int
     scratch_rows: int
-    near_keys: int          # keys per list behind `keep` in the near scratch block
-    far_mul: int            # far scratch row of (list at near row sbase, key keep + near_keys + j) = sbase * far_mul + j
     inst_base: np.ndarray
     inst_size: np.ndarray
     inst_keep: np.ndarray
@@ -110,12 +101,9 @@ def default_pool_rows():
     return int(os.environ.get("XMHW_B200_POOL_ROWS", "0"))
 
 
-def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None, near_keys=None):
+def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None):
     """doy: int array [T] of 1-based labels in 1..ndoy; w: window half width; q in [0,1]."""
     keep = default_keep() if keep is None else int(keep)
-    near_keys = default_near_keys() if near_keys is None else int(near_keys)
-    if not 1 <= near_keys <= 255:
-        raise ValueError("near_keys must be in 1..255")
     if not 1 <= keep <= MAX_LIST:
         raise ValueError("keep must be in 1..32")
     doy = np.asarray(doy, dtype=np.int64)
@@ -260,10 +248,7 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None, near_keys=None):
 
     if max_lists > MAX_LISTS:
         raise NotImplementedError("more than %d sorted lists per window (windowHalfWidth too large)" % MAX_LISTS)
-    # global scratch for the sorted keys past `keep` (same lifetime as the pool block).  NEAR block of a
-    # list: its f64 sum + the first near_keys of those keys (the ranks the cut visits: this region is small
-    # enough to stay in L2); the keys behind them go to the FAR region at row sbase * far_mul + j, which
-    # needs no allocator: near blocks are disjoint and a list with far keys owns a full near block.
+    # global scratch rows for the sorted keys past `keep` (same lifetime as the pool block)
     sfree = [(SCRATCH_HEAD, 1 << 30)]       # rows 0,1 = sum of the null list
     sbase = np.zeros(ninst, np.int32)
     scratch_rows = SCRATCH_HEAD
@@ -283,7 +268,7 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None, near_keys=None):
             if not e & LOAD_FLAG:
                 continue
             i = e & (LOAD_FLAG - 1)
-            n = SCRATCH_HEAD + min(near_keys, max(0, sizes_list[i] - keeps[i]))
+            n = SCRATCH_HEAD + max(0, sizes_list[i] - keeps[i])
             for k, (a, sz) in enumerate(sfree):
                 if sz >= n:
                     sfree[k] = (a + n, sz - n)
@@ -293,8 +278,6 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None, near_keys=None):
             srel[insts[i]["steps"][-1] + 1].append((int(sbase[i]), n))
     if scratch_rows >= (1 << 14):
         raise NotImplementedError("scratch too large for the pool meta word")
-    far_need = max(max(0, sizes_list[i] - keeps[i] - near_keys) for i in range(ninst))
-    far_mul = -(-far_need // (SCRATCH_HEAD + near_keys))
     sizes = np.array([len(it["rows"]) for it in insts], np.int32)
     row_off = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)
     rows = np.concatenate([it["rows"] for it in insts]).astype(np.int32)
@@ -340,7 +323,6 @@ def build_clim_plan(doy, ndoy, w, q, keep=None, max_rows=None, near_keys=None):
 
     return ClimPlanHost(
         nsteps=ndoy, pool_rows=int(pool_rows), nmax=int(nmax), max_size=int(sizes.max()), scratch_rows=int(scratch_rows),
-        near_keys=int(near_keys), far_mul=int(far_mul),
         inst_base=base, inst_size=sizes, inst_keep=np.asarray(keeps, np.int32), inst_sbase=sbase,
         inst_row_off=row_off, rows=rows,
         leave_off=arr(leave_off), leave=arr(leave), enter_off=arr(enter_off), enter=arr(enter),

@@ -55,7 +55,6 @@ class ClimPlan2Host:
     exc_rows: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
     n_merges: int = 0                      # diagnostics: top-K merges over the whole sweep
     n_flips: int = 0
-    reuse_delay: int = 0                   # steps between a slot's pop and its reuse (2: sorter / merger warp pairs)
 
     def smem_bytes(self):
         return self.pool_rows * 128
@@ -123,10 +122,8 @@ def _try_order(doy, ndoy, sigs, exc):
     return atoms, regular
 
 
-def build_clim_plan2(doy, ndoy, w, q, reuse_delay=0):
+def build_clim_plan2(doy, ndoy, w, q):
     """doy: int array [T] of 1-based labels in 1..ndoy; w: window half width; q in [0,1].
-    reuse_delay: a slot freed by a pop at step s is reused by pushes of step s + reuse_delay at the earliest
-    (0: same step; 2: what the sorter / merger warp pairs need, the sorter works one step ahead).
     Returns a ClimPlan2Host, or None when this calendar / quantile needs the general sweep."""
     doy = np.asarray(doy, dtype=np.int64)
     T = len(doy)
@@ -295,9 +292,8 @@ def build_clim_plan2(doy, ndoy, w, q, reuse_delay=0):
         u = int(unit_of[i])
         flags = 0
         if u not in slot_of_unit:
-            ready = [k for k, (sl_, avail) in enumerate(free_slots) if avail <= s]
-            if ready:
-                slot_of_unit[u] = free_slots.pop(ready[0])[0]
+            if free_slots:
+                slot_of_unit[u] = free_slots.pop(0)
             else:
                 slot_of_unit[u] = nslots
                 nslots += 1
@@ -319,8 +315,6 @@ def build_clim_plan2(doy, ndoy, w, q, reuse_delay=0):
         atom_desc[i] = r
         return r
 
-    cur_step = [0]
-
     def do_pop():
         nonlocal next_pop_unit
         u = next_pop_unit
@@ -332,7 +326,7 @@ def build_clim_plan2(doy, ndoy, w, q, reuse_delay=0):
         else:
             raise RuntimeError("pop order")
         sl = slot_of_unit.pop(u)
-        free_slots.append((sl, cur_step[0] + reuse_delay))
+        free_slots.append(sl)
         free_slots.sort()
         return sl
 
@@ -343,7 +337,6 @@ def build_clim_plan2(doy, ndoy, w, q, reuse_delay=0):
         for _ in range(n_init):
             do_push(0, None)
         for s in range(nsteps):
-            cur_step[0] = s
             pops = []
             stale = False
             while next_pop_unit < len(units) and b_arr[units[next_pop_unit][0]] < s:
@@ -422,4 +415,4 @@ def build_clim_plan2(doy, ndoy, w, q, reuse_delay=0):
         step_doy=np.asarray(regular, np.int32),
         exc_doy=np.asarray(exc_list, np.int32), exc_off=np.asarray(exc_off, np.int32),
         exc_rows=np.asarray(exc_rows if exc_rows else [0], np.int32),
-        n_merges=n_merges, n_flips=n_flips, reuse_delay=int(reuse_delay))
+        n_merges=n_merges, n_flips=n_flips)
