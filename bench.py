@@ -401,7 +401,7 @@ def run_ours(args):
                "the host (all ranks share its memory bandwidth) is the e2e limiter at N > 1"}
         api = None
         if world == 1 and not args.no_api:
-            api = api_e2e(host, doy, tm, wl, nlat, nlon, nocean_total, years)
+            api = api_e2e(host, doy, tm, wl, nlat, nlon, nocean_total, years, profile=args.api_profile)
         del host, out, res
         if api is not None:
             e2e["api"] = api
@@ -440,8 +440,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def api_e2e(host, doy, tm, wl, nlat, nlon, nocean, years):
-    """The drop-in public API on host arrays: xmhw.threshold + xmhw.detect(compact=True), wall clock."""
+def api_e2e(host, doy, tm, wl, nlat, nlon, nocean, years, profile=None):
+    """The drop-in public API on host arrays: xmhw.threshold + xmhw.detect(compact=True), wall clock.
+    profile: path of a cProfile listing of one extra (untimed) pass (development aid)."""
     if tm is None or wl.get("winter_blocks") or wl.get("threshold") or wl.get("detect"):
         return None
     import torch
@@ -464,6 +465,19 @@ def api_e2e(host, doy, tm, wl, nlat, nlon, nocean, years):
                "events": int(len(ev["index_start"].values)),
                "what": "xmhw_b200.xmhw.threshold + detect(compact=True) on host arrays (labeled.DataArray), wall clock"}
         del clim, ev
+    if profile:
+        import cProfile
+        import io
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        clim = api.threshold(da)
+        ev = api.detect(da, clim["thresh"], clim["seas"], compact=True)
+        pr.disable()
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(45)
+        open(profile, "w").write(buf.getvalue())
+        del clim, ev
     return out
 
 
@@ -481,6 +495,7 @@ def main():
     ap.add_argument("--checksum", action="store_true", help="recompute the result checksums in every step (default: first step)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-api", action="store_true")
+    ap.add_argument("--api-profile", default=None, help="write a cProfile listing of the public-API pass to this file")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: everything libraries write to file descriptor 1 goes to stderr

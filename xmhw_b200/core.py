@@ -465,7 +465,7 @@ def _pin(t):
 def host_pipeline(ts_host, doy, ndoy, do_threshold=True, do_detect=True, th_host=None, se_host=None,
                   pctile=90, windowHalfWidth=5, smoothPercentile=True, smoothPercentileWidth=31, feb29=True,
                   minDuration=5, joinGaps=True, maxGap=2, negate=False, max_pad=0, anynans=False,
-                  device="cuda", out=None, slabs=24):
+                  device="cuda", out=None, slabs=24, th_dev=None, se_dev=None, clim_on_device=False):
     """The hot path on a HOST series: `ts_host` float32 [T, ngrid] (pinned, or page-locked here for the
     call).  The grid is cut into `slabs` column blocks; the strided host->device copy of block i+1,
     the kernels of block i and the device->host copy of the results of block i-1 overlap on three
@@ -473,7 +473,10 @@ def host_pipeline(ts_host, doy, ndoy, do_threshold=True, do_detect=True, th_host
     adds is the tail after the last block's copy, so more, smaller blocks are better: 920 / 877 /
     866 ms with 8 / 16 / 24 blocks at config 3.
 
-    do_threshold   climatologies from the series (else `th_host` / `se_host` float64 [ndoy, ngrid] are uploaded per block)
+    do_threshold   climatologies from the series (else `th_host` / `se_host` float64 [ndoy, ngrid] are uploaded per
+                   block, or `th_dev` / `se_dev`, the same arrays already on the device, are sliced per block)
+    clim_on_device the climatologies stay on the device: the result holds `thresh_dev` / `seas_dev` [ndoy, ngrid]
+                   instead of the host copies (the public API drops land rows / columns there and copies once)
     do_detect      event table (needs climatologies from either source)
     negate, max_pad, anynans   the public functions' pre-steps on the device block: coldSpells sign flip
                    (xmhw.py:153-154, :412-413), maxPadLength gap interpolation (:159-160, :409-410), and
@@ -486,8 +489,9 @@ def host_pipeline(ts_host, doy, ndoy, do_threshold=True, do_detect=True, th_host
         ts_host = torch.from_numpy(ts_host)
     if ts_host.dtype != torch.float32 or ts_host.dim() != 2 or not ts_host.is_contiguous():
         raise TypeError("ts_host must be a contiguous float32 [T, ngrid] host tensor")
-    if not do_threshold and do_detect and (th_host is None or se_host is None):
-        raise ValueError("detect without threshold needs th_host and se_host")
+    clim_dev = th_dev is not None and se_dev is not None
+    if not do_threshold and do_detect and not clim_dev and (th_host is None or se_host is None):
+        raise ValueError("detect without threshold needs th_host and se_host (or th_dev and se_dev)")
     T, ngrid = ts_host.shape
     out = {} if out is None else out
     unpin = [_pin(ts_host)]
@@ -500,11 +504,16 @@ def host_pipeline(ts_host, doy, ndoy, do_threshold=True, do_detect=True, th_host
             return t
         return torch.empty(shape, dtype=dtype, pin_memory=True)
 
-    th_h = host_buf("thresh", (ndoy, ngrid), torch.float64) if do_threshold else None
-    se_h = host_buf("seas", (ndoy, ngrid), torch.float64) if do_threshold else None
+    to_host = do_threshold and not clim_on_device
+    th_h = host_buf("thresh", (ndoy, ngrid), torch.float64) if to_host else None
+    se_h = host_buf("seas", (ndoy, ngrid), torch.float64) if to_host else None
+    th_d = se_d = None
     nv_h = host_buf("nvalid", (ngrid,), torch.int32)
     ne_h = host_buf("nempty", (ngrid,), torch.int32) if do_threshold else None
-    if not do_threshold and do_detect:
+    if clim_dev:
+        if tuple(th_dev.shape) != (ndoy, ngrid) or tuple(se_dev.shape) != (ndoy, ngrid) or th_dev.dtype != torch.float64:
+            raise ValueError("th_dev / se_dev must be float64 [ndoy, ngrid]")
+    elif not do_threshold and do_detect:
         th_src = th_host if isinstance(th_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(th_host, np.float64))
         se_src = se_host if isinstance(se_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(se_host, np.float64))
         if th_src.shape != (ndoy, ngrid) or se_src.shape != (ndoy, ngrid):
@@ -522,7 +531,10 @@ def host_pipeline(ts_host, doy, ndoy, do_threshold=True, do_detect=True, th_host
             s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
             bufs = [torch.empty((T, w), dtype=torch.float32, device=dev) for _ in range(2)]
             cbufs = None
-            if not do_threshold and do_detect:
+            if do_threshold and clim_on_device:
+                th_d = torch.empty((ndoy, ngrid), dtype=torch.float64, device=dev)
+                se_d = torch.empty((ndoy, ngrid), dtype=torch.float64, device=dev)
+            if not do_threshold and do_detect and not clim_dev:
                 cbufs = [[torch.empty((ndoy, w), dtype=torch.float64, device=dev) for _ in range(2)] for _ in range(2)]
             s_in.wait_stream(main)          # the buffers were allocated on `main`
             s_out.wait_stream(main)
@@ -588,8 +600,13 @@ def host_pipeline(ts_host, doy, ndoy, do_threshold=True, do_detect=True, th_host
                 if do_threshold:
                     th, se, nempty = threshold_arrays(ts, doy, ndoy, pctile, windowHalfWidth, smoothPercentile,
                                                       smoothPercentileWidth, feb29, return_nempty=True)
+                elif clim_dev:
+                    th, se = th_dev[:, a:b].contiguous(), se_dev[:, a:b].contiguous()
                 else:
                     th, se = clim if clim is not None else (None, None)
+                if th_d is not None:
+                    th_d[:, a:b].copy_(th)
+                    se_d[:, a:b].copy_(se)
                 ev = None
                 if do_detect:
                     ev = detect_arrays(ts, doy, ndoy, th, se, minDuration, joinGaps, maxGap)
@@ -605,10 +622,11 @@ def host_pipeline(ts_host, doy, ndoy, do_threshold=True, do_detect=True, th_host
                     ev_parts = ev_parts_all[:]
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(done)
-                    if do_threshold:
+                    if to_host:
                         for src, dst in ((th, th_h), (se, se_h)):
                             check(lib.xmhw_copy2d_async(dst.data_ptr() + a * 8, ngrid * 8, _ptr(src), (b - a) * 8,
                                                         (b - a) * 8, ndoy, 1, s_out.cuda_stream), "xmhw_copy2d_async")
+                    if do_threshold:
                         ne_h[a:b].copy_(nempty, non_blocking=True)
                     nv_h[a:b].copy_(nvalid, non_blocking=True)
                     if stream_ev:
@@ -633,11 +651,16 @@ def host_pipeline(ts_host, doy, ndoy, do_threshold=True, do_detect=True, th_host
     finally:
         for u in unpin:
             u()
-    res = {"nvalid": nv_h, "n_events": nev, "h2d_bytes": T * ngrid * 4 + (0 if do_threshold or not do_detect else 2 * ndoy * ngrid * 8),
-           "d2h_bytes": (2 * ndoy * ngrid * 8 + ngrid * 4 if do_threshold else 0) + ngrid * 4
+    res = {"nvalid": nv_h, "n_events": nev,
+           "h2d_bytes": T * ngrid * 4 + (0 if do_threshold or not do_detect or clim_dev else 2 * ndoy * ngrid * 8),
+           "d2h_bytes": (2 * ndoy * ngrid * 8 if to_host else 0) + (ngrid * 4 if do_threshold else 0) + ngrid * 4
            + nev * (EI_COUNT * 4 + EF_COUNT * 8)}
     if do_threshold:
-        res.update(thresh=th_h, seas=se_h, nempty=ne_h)
+        res.update(nempty=ne_h)
+        if to_host:
+            res.update(thresh=th_h, seas=se_h)
+        else:
+            res.update(thresh_dev=th_d, seas_dev=se_d)
     if do_detect:
         res.update(ev_i32=ei_h[:, :nev], ev_f64=ef_h[:, :nev])
     return res

@@ -102,6 +102,27 @@ def _slabs(flat):
     return int(min(32, max(1, flat.nbytes >> 30)))
 
 
+def _to_host(t):
+    """Device tensor -> numpy array through ONE pinned buffer (the array keeps the buffer alive)."""
+    import torch
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy()
+
+
+def _take1(values, idx):
+    """values[idx] for a 1-D coordinate / time vector and a torch integer index of tens of millions of
+    entries: torch's index_select runs on all host cores (numpy's take on one)."""
+    import torch
+    v = np.ascontiguousarray(values)
+    if v.dtype.kind in "mM":
+        return torch.from_numpy(v.view(np.int64)).index_select(0, idx).numpy().view(v.dtype)
+    if v.dtype.kind in "iuf" and v.dtype.itemsize in (4, 8):
+        return torch.from_numpy(v).index_select(0, idx).numpy()
+    return v[idx.numpy()]
+
+
 def _wrap(ds, like):
     if labeled.is_xarray(like):
         try:
@@ -161,39 +182,42 @@ def threshold(temp, tdim="time", climatologyPeriod=[None, None], pctile=90, wind
         res = core.host_pipeline(torch.from_numpy(flat), doy, ndoy, do_threshold=True, do_detect=False,
                                  pctile=pctile, windowHalfWidth=windowHalfWidth, smoothPercentile=smoothPercentile,
                                  smoothPercentileWidth=smoothPercentileWidth, feb29=not tstep, negate=coldSpells,
-                                 max_pad=_pad_steps(maxPadLength, time), anynans=anynans, slabs=_slabs(flat))
+                                 max_pad=_pad_steps(maxPadLength, time), anynans=anynans, slabs=_slabs(flat),
+                                 clim_on_device=True)
     except NotImplementedError as exc:                       # a calendar / window the sweep plans cannot express
         raise XmhwException("threshold: %s" % exc)
     ocean = res["nvalid"].numpy() > 0
     if not point and not ocean.any():
         raise XmhwException("All points of grid are either land or NaN")   # identify.py:527-528
-    th_h, se_h = res["thresh"].numpy(), res["seas"].numpy()
+    # the climatologies are still on the device: rows / columns without ocean vanish and the coordinates
+    # get sorted THERE (unstack, xmhw.py:213-214), then one copy to the host -- no host pass over 6 GB arrays
+    th_d, se_d = res["thresh_dev"], res["seas_dev"]
     doy_coord = np.arange(1, ndoy + 1, dtype=np.int64)
     if not point:
         keep = _present(ocean.reshape(grid_shape))
-        th_h = th_h.reshape((ndoy,) + grid_shape)
-        se_h = se_h.reshape((ndoy,) + grid_shape)
-        for ax, k in enumerate(keep):
-            if len(k) != grid_shape[ax]:                    # (no copy of the 6 GB arrays when nothing vanishes)
-                th_h = np.take(th_h, k, axis=ax + 1)
-                se_h = np.take(se_h, k, axis=ax + 1)
+        th_d = th_d.view((ndoy,) + tuple(grid_shape))
+        se_d = se_d.view((ndoy,) + tuple(grid_shape))
         out_coords = {"doy": doy_coord}
-        for d, k in zip(other, keep):
+        for ax, (d, k) in enumerate(zip(other, keep)):
             c = coords[d][k]
             srt = np.argsort(c, kind="stable")              # unstack returns sorted coordinate values
-            ax = other.index(d) + 1
-            if not np.array_equal(srt, np.arange(len(srt))):
-                th_h, se_h = np.take(th_h, srt, axis=ax), np.take(se_h, srt, axis=ax)
+            idx = np.asarray(k)[srt]
+            if len(idx) != grid_shape[ax] or not np.array_equal(idx, np.arange(grid_shape[ax])):
+                idx_d = torch.from_numpy(np.ascontiguousarray(idx, np.int64)).to(th_d.device)
+                th_d, se_d = th_d.index_select(ax + 1, idx_d), se_d.index_select(ax + 1, idx_d)
             out_coords[d] = c[srt]
         dims = ("doy",) + tuple(other)
     else:
-        th_h, se_h = th_h[:, 0], se_h[:, 0]
+        th_d, se_d = th_d[:, 0], se_d[:, 0]
         out_coords, dims = {"doy": doy_coord}, ("doy",)
     # a doy without samples disappears from the reference's groupby output (identify.py:233)
-    present = ~np.isnan(th_h).all(axis=tuple(range(1, th_h.ndim))) if th_h.ndim > 1 else ~np.isnan(th_h)
+    present = (~torch.isnan(th_d).flatten(1).all(dim=1) if th_d.dim() > 1 else ~torch.isnan(th_d)).cpu().numpy()
     if not present.all():
-        th_h, se_h = th_h[present], se_h[present]
+        sel = torch.from_numpy(np.flatnonzero(present)).to(th_d.device)
+        th_d, se_d = th_d.index_select(0, sel), se_d.index_select(0, sel)
         out_coords["doy"] = doy_coord[present]
+    th_h, se_h = _to_host(th_d), _to_host(se_d)
+    del th_d, se_d, res
     out_coords["quantile"] = np.float64(pctile / 100.0)
     ds = labeled.Dataset(coords=out_coords)
     ds["thresh"] = labeled.DataArray(th_h, dims, name="threshold")      # xmhw.py:215-216
@@ -220,37 +244,57 @@ def threshold(temp, tdim="time", climatologyPeriod=[None, None], pctile=90, wind
     return _wrap(ds, temp)
 
 
-def _clim_to_grid(arr, other, grid_coords, grid_shape, ndoy, name):
-    """Bring a (doy, ...) climatology onto the full (doy, cell) grid of `temp` by coordinate
-    label (the reference matches cells positionally after land_check, xmhw.py:399-402)."""
+def _clim_to_grid(arr, other, grid_coords, grid_shape, ndoy, name, device):
+    """Bring a (doy, ...) climatology onto the full (doy, cell) grid of `temp` by coordinate label (the
+    reference matches cells positionally after land_check, xmhw.py:399-402).  The array is uploaded as it
+    is and spread over the full grid ON THE DEVICE (NaN where it has no value): float64 [ndoy, ncell]."""
+    import torch
+    from . import core
     dims = list(arr.dims)
     if "doy" not in dims:
         raise XmhwException(f"{name} must have a 'doy' dimension")
-    data = np.asarray(arr.values, np.float64)
     o = sorted(d for d in dims if d != "doy")
     if o != list(other):
         raise XmhwException(f"{name} dimensions {o} do not match the series dimensions {list(other)}")
-    data = np.transpose(data, [dims.index("doy")] + [dims.index(d) for d in o])
     doyc = _coord(arr, "doy")
-    # fast path: the climatology already sits on the series' full grid (same coordinate vectors, all doys)
-    if data.shape == (ndoy,) + tuple(grid_shape) and (doyc is None or np.array_equal(doyc, np.arange(1, ndoy + 1))) \
-            and all(_coord(arr, d) is None or np.array_equal(_coord(arr, d), grid_coords[d]) for d in other):
-        return np.ascontiguousarray(data).reshape(ndoy, -1)
-    full = np.full((ndoy,) + tuple(grid_shape), np.nan)
-    drow = (np.asarray(doyc, np.int64) - 1) if doyc is not None else np.arange(data.shape[0])
-    index = [drow]
+    # label -> position on the full grid, per axis (None: the axis already is the full one)
+    index = []
+    drow = (np.asarray(doyc, np.int64) - 1) if doyc is not None else None
+    if drow is not None and (drow.min(initial=0) < 0 or drow.max(initial=0) >= ndoy):
+        raise XmhwException(f"{name} has doy values outside 1..{ndoy}")
+    index.append(None if drow is None or np.array_equal(drow, np.arange(ndoy)) else drow)
     for d in other:
         c = _coord(arr, d)
-        if c is None:
-            index.append(np.arange(data.shape[len(index)]))
+        if c is None or np.array_equal(c, grid_coords[d]):
+            index.append(None)
             continue
         pos = {v: i for i, v in enumerate(grid_coords[d].tolist())}
         try:
             index.append(np.array([pos[v] for v in c.tolist()], np.int64))
         except KeyError:
             raise XmhwException(f"{name} has {d} values that are not on the series grid")
-    full[np.ix_(*index)] = data
-    return full.reshape(ndoy, -1)
+    host = torch.from_numpy(np.ascontiguousarray(np.asarray(arr.values, np.float64)))
+    unpin = core._pin(host)
+    try:
+        data = host.to(device, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+    finally:
+        unpin()
+    data = data.permute([dims.index("doy")] + [dims.index(d) for d in o])
+    full_shape = (ndoy,) + tuple(grid_shape)
+    for ax, ix in enumerate(index):
+        if ix is None:
+            if data.shape[ax] == full_shape[ax]:
+                continue
+            if data.shape[ax] > full_shape[ax]:
+                raise XmhwException(f"{name} is larger than the series grid along {(['doy'] + list(other))[ax]}")
+            ix = np.arange(data.shape[ax], dtype=np.int64)     # unlabeled and shorter: the leading positions
+        shape = list(data.shape)
+        shape[ax] = full_shape[ax]
+        wide = torch.full(shape, float("nan"), dtype=torch.float64, device=device)
+        wide.index_copy_(ax, torch.from_numpy(ix).to(device), data)
+        data = wide
+    return data.contiguous().view(ndoy, -1)
 
 
 def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, maxPadLength=None,
@@ -278,10 +322,11 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
     flat = np.ascontiguousarray(data.reshape(T, -1))
     if not point and _all_land(flat):
         raise XmhwException("All points of grid are either land or NaN")
-    th_full = _clim_to_grid(th, other, coords, grid_shape, ndoy, "th")
-    se_full = _clim_to_grid(se, other, coords, grid_shape, ndoy, "se")
     if not torch.cuda.is_available():
         raise RuntimeError("xmhw_b200 needs a CUDA device (there is no CPU path)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    thd = _clim_to_grid(th, other, coords, grid_shape, ndoy, "th", dev)
+    sed = _clim_to_grid(se, other, coords, grid_shape, ndoy, "se", dev)
     ts = None
     if intermediate:
         # the per-timestep dataset needs the whole series on the device at once (small grids only)
@@ -298,20 +343,23 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
             core.interp_gaps_(ts, _pad_steps(maxPadLength, time))
         if coldSpells:                                         # xmhw.py:412-413
             ts = -ts
-        thd, sed = torch.from_numpy(th_full).cuda(), torch.from_numpy(se_full).cuda()
         ev = core.detect_arrays(ts, doy, ndoy, thd, sed, minDuration, joinGaps, maxGap)
         ocean = nvalid.cpu().numpy() > 0
-        tab = ev.to_numpy()
+        ei_t, ef_t = ev.i32[:, :ev.n].cpu(), ev.f64[:, :ev.n].cpu()
     else:
-        # one pipelined pass over the host series; th / se are uploaded once, per column block
+        # one pipelined pass over the host series; th / se already sit on the device, sliced per column block
         res = core.host_pipeline(torch.from_numpy(flat), doy, ndoy, do_threshold=False, do_detect=True,
-                                 th_host=th_full, se_host=se_full, minDuration=minDuration, joinGaps=joinGaps,
+                                 th_dev=thd, se_dev=sed, minDuration=minDuration, joinGaps=joinGaps,
                                  maxGap=maxGap, negate=coldSpells, max_pad=_pad_steps(maxPadLength, time), anynans=anynans,
                                  slabs=_slabs(flat))
         ocean = res["nvalid"].numpy() > 0
-        ei, ef = res["ev_i32"].numpy(), res["ev_f64"].numpy()
-        tab = {f: ei[k].astype(np.int64) for k, f in enumerate(core.EI_FIELDS)}
-        tab.update({f: ef[k] for k, f in enumerate(core.EF_FIELDS)})
+        ei_t, ef_t = res["ev_i32"], res["ev_f64"]
+        del thd, sed
+    # event table columns: int32 [EI_COUNT, n] / float64 [EF_COUNT, n] host tensors; conversions and gathers
+    # of the (tens of millions of) rows go through torch, which uses all host cores
+    icol = {f: ei_t[k] for k, f in enumerate(core.EI_FIELDS)}
+    fcol = {f: ef_t[k] for k, f in enumerate(core.EF_FIELDS)}
+    tab = {f: icol[f].numpy() for f in ("cell", "index_start", "index_end", "index_peak", "category")}
     if not point and not ocean.any():
         raise XmhwException("All points of grid are either land or NaN")
     inter = None
@@ -319,17 +367,18 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
         inter = {k: v.cpu().numpy() for k, v in core.intermediate_arrays(ts, doy, ndoy, thd, sed, ev).items()}
         inter["ts"] = ts.cpu().numpy()
     n = len(tab["cell"])
-    cols = {"event": tab["index_start"].astype(np.float64)}
+    cols = {"event": icol["index_start"].to(torch.float64).numpy()}
     for f in ("index_start", "index_end", "index_peak", "duration", "category"):
-        cols[f] = tab[f].astype(np.float64)                    # integer-valued float64 in the reference
+        cols[f] = icol[f].to(torch.float64).numpy()            # integer-valued float64 in the reference
     cols["category"][tab["category"] < 0] = np.nan
     for f in ("duration_moderate", "duration_strong", "duration_severe", "duration_extreme"):
-        cols[f] = tab[f].astype(np.int64)
+        cols[f] = icol[f].to(torch.int64).numpy()
     for f in core.EF_FIELDS:
-        cols[f] = tab[f].astype(np.float32) if f in FLOAT32_VARIABLES else tab[f]
+        cols[f] = (fcol[f].to(torch.float32) if f in FLOAT32_VARIABLES else fcol[f]).numpy()
     time = np.asarray(time)
-    cols["time_start"], cols["time_end"] = time[tab["index_start"]], time[tab["index_end"]]
-    cols["time_peak"] = time[tab["index_peak"]]
+    cols["time_start"] = _take1(time, icol["index_start"])
+    cols["time_end"] = _take1(time, icol["index_end"])
+    cols["time_peak"] = _take1(time, icol["index_peak"])
     if coldSpells:                                             # xmhw.py:481-482
         cols = flip_cold(cols)
     params = f"MHW detected using: {minDuration} days of minimum duration"
@@ -348,14 +397,20 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
         params += """;
             any grid point with even only 1 NaN along time
             axis has been removed from calculation"""
-    cell_idx = np.unravel_index(tab["cell"], grid_shape) if not point else ()
+    cell_idx = ()
+    if not point:                                              # unravel_index on all host cores
+        rem, parts = icol["cell"].to(torch.int64), []
+        for size in reversed(grid_shape):
+            parts.append(torch.remainder(rem, size))
+            rem = torch.div(rem, size, rounding_mode="floor")
+        cell_idx = tuple(reversed(parts))
     if compact or point:
-        ds = labeled.Dataset(coords={"events": tab["index_start"] if point else np.arange(n)})
+        ds = labeled.Dataset(coords={"events": tab["index_start"].astype(np.int64) if point else np.arange(n)})
         dim = ("events",) if point else ("row",)
         if not point:
             ds.coords = {"row": np.arange(n)}
             for d, ix in zip(other, cell_idx):
-                ds[d] = labeled.DataArray(coords[d][ix], dim)
+                ds[d] = labeled.DataArray(_take1(coords[d], ix), dim)
         for v in EVENT_VARIABLES:
             ds[v] = labeled.DataArray(cols[v], dim)
     else:
@@ -374,7 +429,7 @@ def detect(temp, th, se, tdim="time", minDuration=5, joinGaps=True, maxGap=2, ma
             srt = np.argsort(c, kind="stable")
             inv = np.empty(len(coords[d]), np.int64)
             inv[k[srt]] = np.arange(len(k))
-            pos.append(inv[ix])
+            pos.append(inv[ix.numpy()])
             out_coords[d] = c[srt]
         ds = labeled.Dataset(coords=out_coords)
         dims = ("events",) + tuple(other)
