@@ -47,6 +47,9 @@ WORKLOADS = {
                              detect=dict(minDuration=3, maxGap=1)),              # BASELINE configs[3] (ii)
     "global010_30yr": dict(grid=(1800, 3600), years=(1982, 2011), land=0.33),     # BASELINE configs[4]: 284 GB, chunked
     "global025_quarter": dict(grid=(180, 1440), years=(1982, 2011), land=0.33),   # development timing
+    "quarter_w1": dict(grid=(180, 1440), years=(1982, 2011), land=0.33, threshold=dict(windowHalfWidth=1)),   # development:
+    "quarter_w2": dict(grid=(180, 1440), years=(1982, 2011), land=0.33, threshold=dict(windowHalfWidth=2)),   # narrower windows =
+    "quarter_w3": dict(grid=(180, 1440), years=(1982, 2011), land=0.33, threshold=dict(windowHalfWidth=3)),   # smaller pools, more warps/SM
     "small": dict(grid=(32, 64), years=(2001, 2010), land=0.2),
 }
 METRIC = "cell-years/s, threshold+detect, global 0.25deg 30-yr SST"

@@ -56,6 +56,50 @@ def test_add_doy_and_calendar(oisst):
     assert identify.get_calendar(t5, {"calendar": "360"}) == 360      # identify.py:125-126
 
 
+class _CfDate:
+    """What xarray hands over for a non-standard calendar: cftime-like objects (year, month, day,
+    dayofyr, calendar) in an object array -- cftime itself is not part of this image."""
+
+    def __init__(self, year, month, day, dayofyr, calendar):
+        self.year, self.month, self.day, self.dayofyr, self.calendar = year, month, day, dayofyr, calendar
+
+
+def _cf_axis(calendar, years):
+    mlen = {"noleap": [31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31], "all_leap": [31, 29, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31],
+            "360_day": [30] * 12}[calendar]
+    out = []
+    for y in years:
+        n = 0
+        for m, ml in enumerate(mlen, 1):
+            for d in range(1, ml + 1):
+                n += 1
+                out.append(_CfDate(y, m, d, n, calendar))
+    return np.array(out, dtype=object)
+
+
+def test_add_doy_cftime_calendars():
+    """Non-Gregorian time axes (identify.py:57-79, :82-134): `is_leap_year` follows the calendar of the
+    time objects, not the year number -- 2000 is not a leap year on a noleap axis."""
+    t = _cf_axis("noleap", [1999, 2000, 2001])
+    assert identify.get_calendar(t) == 365
+    doy, ndoy = identify.add_doy(t)
+    assert ndoy == 366 and len(doy) == 3 * 365
+    one = np.concatenate([np.arange(1, 60), np.arange(61, 367)])          # label 60 (Feb 29) never occurs
+    assert np.array_equal(doy, np.tile(one, 3))
+    doy, ndoy = identify.add_doy(t, keep_tstep=True)
+    assert ndoy == 365 and np.array_equal(doy, np.tile(np.arange(1, 366), 3))
+    t = _cf_axis("all_leap", [2001, 2002])
+    assert identify.get_calendar(t) == 366
+    doy, ndoy = identify.add_doy(t)
+    assert np.array_equal(doy, np.tile(np.arange(1, 367), 2))             # every year has its Feb 29
+    t = _cf_axis("360_day", [2001, 2002])
+    assert identify.get_calendar(t) == 360                                 # threshold() then forces tstep (xmhw.py:142-144)
+    doy, ndoy = identify.add_doy(t, keep_tstep=True)
+    assert ndoy == 360 and np.array_equal(doy, np.tile(np.arange(1, 361), 2))
+    doy, _ = identify.add_doy(t)                                           # detect() with tstep=False (xmhw.py:404):
+    assert doy[58] == 59 and doy[60] == 62                                 # dayofyr + 1 from March on, no leap years
+
+
 def test_synth_is_deterministic_and_shardable():
     tm = synth.daily_time(2001, 2002)
     sea = synth.season_table(tm)

@@ -190,3 +190,32 @@ def test_real_xarray_dataarray_when_available(api, oisst):
     ref = xmhw.threshold(labeled.DataArray(oisst["sst"], ("time", "lat", "lon"),
                                            {"time": oisst["time"], "lat": oisst["lat"], "lon": oisst["lon"]}))
     assert np.array_equal(clim["thresh"].values, ref["thresh"].values, equal_nan=True)
+
+
+def test_noleap_cftime_axis_through_api(api):
+    """A noleap (365-day) model calendar as xarray decodes it (cftime-like objects): label 60 never occurs,
+    so the climatology has 365 doys (identify.py:233: the empty group vanishes); events equal the oracle's
+    on the same labels.  With tstep=True the 365 steps are the labels themselves."""
+    xmhw, labeled = api
+    from oracle import xmhw_oracle as O
+    from tests.test_api_cpu import _cf_axis
+    from xmhw_b200 import identify, synth
+    t = _cf_axis("noleap", list(range(2001, 2011)))
+    ts = synth.synth_sst(len(t), 12, synth.season_table(len(t)), nan_ppm=3000).reshape(len(t), 3, 4)
+    da = labeled.DataArray(ts, ("time", "lat", "lon"), {"time": t, "lat": np.arange(3.0), "lon": np.arange(4.0)})
+    clim = xmhw.threshold(da)
+    assert clim["thresh"].shape == (365, 3, 4) and 60 not in clim["thresh"].coords["doy"].tolist()
+    doy, ndoy = identify.add_doy(t)
+    flat = ts.reshape(len(t), -1)
+    oth, ose = O.threshold(flat, doy, ndoy)
+    present = ~np.isnan(oth).all(1)
+    assert present.sum() == 365
+    assert np.array_equal(clim["thresh"].values.reshape(365, -1), oth[present])
+    ev = xmhw.detect(da, clim["thresh"], clim["seas"], compact=True)
+    exp = O.detect(flat, doy, oth, ose)
+    assert len(exp["cell"]) > 20 and np.array_equal(ev["index_start"].values, exp["index_start"].astype(np.float64))
+    assert ev["time_start"].values[0] is t[int(exp["index_start"][0])]        # cftime objects pass through
+    clim_t = xmhw.threshold(da, tstep=True)
+    assert clim_t["thresh"].shape == (365, 3, 4)
+    oth_t, _ = O.threshold(flat, np.tile(np.arange(1, 366), 10), 365, tstep=True)
+    assert np.array_equal(clim_t["thresh"].values.reshape(365, -1), oth_t)

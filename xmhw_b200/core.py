@@ -96,16 +96,22 @@ class DevicePlan2:
     exc_rows: object            # device int32: window rows of the exceptional doys (CSR by host.exc_off)
 
 
-# Measured on B200 (global 0.25 deg grid, 30 years): the two-stack top-K sweep takes 65 ms at pctile 90
-# (36-key arrays) and 47 ms at pctile 99 (8-key arrays) against 55 / 37 ms of the general sorted-list
-# sweep (profiles/ncu_r02_sweep2_*.txt: its unit slots fill shared memory, so one warp per scheduler
-# issues ~2900 instructions per doy at 0.3 IPC).  The general sweep therefore stays the default for
-# every capacity; the top-K sweep is selectable (XMHW_B200_SWEEP=topk) and fully parity-tested.
-TOPK_AUTO_MAX_KP = 0
+# Which sweep "auto" picks.  Measured on B200 (30-year daily series, profiles/kernel_ms_r02o_sweep_occupancy.txt):
+# the two-stack top-K sweep is bound by the warps its unit slots leave room for.  Default window
+# (windowHalfWidth 5: 11 slots x 40 rows = 55 KB per warp, 4 warps per SM): 65 ms against 52 ms of the
+# general sorted-list sweep on the global grid (pctile 99: 47 against 37).  Narrow windows
+# (windowHalfWidth <= 2: <= 25 KB per warp, >= 8 warps per SM): 8.2 against 9.6 ms and 6.6 against 7.6 ms on
+# the quarter grid -- there the top-K sweep wins, so "auto" takes it when at least TOPK_AUTO_MIN_WARPS of
+# its warps fit one SM, and the general sweep otherwise.
+TOPK_AUTO_MIN_WARPS = 8
+
+
+def _topk_warps_per_sm(host_plan):
+    return (227 * 1024) // (host_plan.pool_rows * 128 + 256)
 
 
 def sweep_mode():
-    """XMHW_B200_SWEEP: "auto" (default, see TOPK_AUTO_MAX_KP), "topk" (the two-stack top-K sweep
+    """XMHW_B200_SWEEP: "auto" (default, see TOPK_AUTO_MIN_WARPS), "topk" (the two-stack top-K sweep
     whenever the calendar fits) or "general" (always the sorted-list sweep of plan.py)."""
     import os
     return os.environ.get("XMHW_B200_SWEEP", "auto")
@@ -194,7 +200,7 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
         nempty = torch.empty(ngrid, dtype=torch.int32, device=ts.device)
         mode = sweep_mode()
         dp2 = device_plan2(doy, ndoy, windowHalfWidth, q, ts.device) if mode in ("topk", "auto") else None
-        if dp2 is not None and mode == "auto" and dp2.host.kp > TOPK_AUTO_MAX_KP:
+        if dp2 is not None and mode == "auto" and _topk_warps_per_sm(dp2.host) < TOPK_AUTO_MIN_WARPS:
             dp2 = None
         if dp2 is not None:
             # two-stack top-K sweep; rows of the doys it does not cover (absent labels) stay NaN

@@ -44,11 +44,27 @@ def _ymd(time_values):
     return years, months, dayofyear
 
 
-def add_doy(time_values, keep_tstep=False):
+def _is_leap(years, calendar):
+    """`t.dt.is_leap_year` of the reference (identify.py:73) for the calendar of the time axis: cftime
+    calendars without leap years never have one, all_leap always, julian every fourth year."""
+    if calendar in ("noleap", "365_day", "360_day"):
+        return np.zeros(len(years), bool)
+    if calendar in ("all_leap", "366_day"):
+        return np.ones(len(years), bool)
+    if calendar == "julian":
+        return years % 4 == 0
+    return (years % 4 == 0) & ((years % 100 != 0) | (years % 400 == 0))
+
+
+def add_doy(time_values, keep_tstep=False, calendar=None):
     """identify.py:28-79: 1-based day-of-year labels on a 366-day calendar (Feb 29 = 60
     exists only in leap years), or 1..steps-per-year tiled when keep_tstep.
+    `calendar`: CF calendar name; default = the `.calendar` of the time objects (cftime), else standard.
     Returns (doy int64[T], ndoy)."""
     years, months, dayofyear = _ymd(time_values)
+    if calendar is None:
+        t = np.asarray(time_values).ravel()
+        calendar = getattr(t[0], "calendar", "standard") if len(t) else "standard"
     T = len(years)
     if keep_tstep:
         uy = np.unique(years)
@@ -58,7 +74,7 @@ def add_doy(time_values, keep_tstep=False):
             raise XmhwException("To use original timestep as climatology base unit, "
                                 "timeseries has to have complete years")
         return np.tile(np.arange(1, steps + 1, dtype=np.int64), T // steps), steps
-    leap = (years % 4 == 0) & ((years % 100 != 0) | (years % 400 == 0))
+    leap = _is_leap(years, calendar)
     return dayofyear + ((~leap) & (months >= 3)).astype(np.int64), 366  # identify.py:73-76
 
 
