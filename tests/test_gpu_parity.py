@@ -150,13 +150,15 @@ def test_config4_skipna99_winter_blocks(core):
     assert_events_match(ev.to_numpy(), exp, _float_fields())
 
 
-@pytest.mark.parametrize("mode", ["topk", "general"])
+@pytest.mark.parametrize("mode", ["topk", "topk_tmem", "general"])
 def test_both_sweeps_forced(core, monkeypatch, mode):
     """The two climatology sweeps (two-stack top-K, csrc/xmhw_topk.h; general sorted lists, csrc/xmhw_lane.h)
     forced on the same 30-year series incl. land, NaNs and a ragged last warp: bit-equal to the oracle
     and therefore to each other (the default picks one by the top-K capacity)."""
     from xmhw_b200 import synth
-    monkeypatch.setenv("XMHW_B200_SWEEP", mode)
+    monkeypatch.setenv("XMHW_B200_SWEEP", mode.split("_")[0])
+    if mode == "topk_tmem":            # 8 warps per SM, the unit slots beyond shared memory in tensor memory
+        monkeypatch.setenv("XMHW_B200_SWEEP2_TMEM", "1")
     time = synth.daily_time(1982, 2011)
     doy = synth.doy366(time)
     ncell = 200
@@ -167,7 +169,7 @@ def test_both_sweeps_forced(core, monkeypatch, mode):
     _clim_check(core, ts_h, doy, 366)
     names = [n for n, _, _ in core.TRACE]
     core.TRACE = None
-    assert ("xmhw_clim_sweep2_f32" in names) == (mode == "topk")
+    assert ("xmhw_clim_sweep2_f32" in names) == mode.startswith("topk")
     _clim_check(core, ts_h, doy, 366, pctile=75, windowHalfWidth=2, smoothPercentileWidth=5)
 
 

@@ -107,6 +107,160 @@ __global__ void __launch_bounds__(32 * WPB, MINB) clim_sweep2_kernel(
   if (ok) nempty[cell] = sw.nzero;
 }
 
+// ---------------------------------------------------------------------------
+// K1t  the top-K sweep with half of every warp's unit slots in TENSOR MEMORY.
+// The sweep is bound by the warps its slots leave room for (55 KB per warp at the default window: four
+// warps fill the 227 KB of shared memory, one per scheduler).  The slot rows are only ever addressed
+// warp-uniformly (row = same for all lanes, word = lane), which is exactly the 32-lane x 32-bit shape of
+// tcgen05.ld / st: a TMEM column is a pool row.  A block = 8 warps = the whole SM: warps w and w + 4 own
+// the TMEM lane quarter w % 4, 256 columns each; the first `smem_slots` slots of a warp stay in shared
+// memory, the others are TMEM columns.  No tensor-core instruction is involved -- TMEM is used as 256 KB
+// of extra lane-private storage, doubling the resident warps of this kernel.
+// ---------------------------------------------------------------------------
+#include "tmem_gen.h"
+
+template <int N> __device__ __forceinline__ void tm_ld_block(uint32_t taddr, uint32_t* k) {
+  if constexpr (N >= 32) { tm_ld32(taddr, k); tm_ld_block<N - 32>(taddr + 32, k + 32); }
+  else if constexpr (N >= 16) { tm_ld16(taddr, k); tm_ld_block<N - 16>(taddr + 16, k + 16); }
+  else if constexpr (N >= 8) { tm_ld8(taddr, k); tm_ld_block<N - 8>(taddr + 8, k + 8); }
+  else if constexpr (N >= 4) { tm_ld4(taddr, k); tm_ld_block<N - 4>(taddr + 4, k + 4); }
+  else if constexpr (N >= 2) { tm_ld2(taddr, k); tm_ld_block<N - 2>(taddr + 2, k + 2); }
+  else if constexpr (N >= 1) { tm_ld1(taddr, k); }
+}
+template <int N> __device__ __forceinline__ void tm_st_block(uint32_t taddr, const uint32_t* k) {
+  if constexpr (N >= 32) { tm_st32(taddr, k); tm_st_block<N - 32>(taddr + 32, k + 32); }
+  else if constexpr (N >= 16) { tm_st16(taddr, k); tm_st_block<N - 16>(taddr + 16, k + 16); }
+  else if constexpr (N >= 8) { tm_st8(taddr, k); tm_st_block<N - 8>(taddr + 8, k + 8); }
+  else if constexpr (N >= 4) { tm_st4(taddr, k); tm_st_block<N - 4>(taddr + 4, k + 4); }
+  else if constexpr (N >= 2) { tm_st2(taddr, k); tm_st_block<N - 2>(taddr + 2, k + 2); }
+  else if constexpr (N >= 1) { tm_st1(taddr, k); }
+}
+template <int N> __device__ __forceinline__ void tm_gather(const uint32_t* a, uint32_t* k);
+template <> __device__ __forceinline__ void tm_gather<9>(const uint32_t* a, uint32_t* k) { tm_gather9(a, k); }
+template <> __device__ __forceinline__ void tm_gather<17>(const uint32_t* a, uint32_t* k) { tm_gather17(a, k); }
+template <> __device__ __forceinline__ void tm_gather<25>(const uint32_t* a, uint32_t* k) { tm_gather25(a, k); }
+template <> __device__ __forceinline__ void tm_gather<37>(const uint32_t* a, uint32_t* k) { tm_gather37(a, k); }
+template <> __device__ __forceinline__ void tm_gather<49>(const uint32_t* a, uint32_t* k) { tm_gather49(a, k); }
+
+// rows [0, split) of the warp's pool: shared memory; rows >= split: TMEM column tcol + (row - split).
+// A slot never straddles the split (it is a multiple of the slot size), so a block access is one or the other.
+struct SplitPool {
+  uint32_t* p;           // shared-memory row 0, this lane's word
+  int split;
+  uint32_t tcol;         // TMEM address (lane quarter << 16 | column) of row `split`
+  static constexpr bool kGather = true;
+  __device__ __forceinline__ uint32_t ld(int row) const {
+    if (row < split) return p[row * 32];
+    uint32_t v;
+    tm_ld1(tcol + (uint32_t)(row - split), &v);
+    return v;
+  }
+  __device__ __forceinline__ void st(int row, uint32_t v) const {
+    if (row < split) { p[row * 32] = v; return; }
+    tm_st1(tcol + (uint32_t)(row - split), &v);
+  }
+  template <int N> __device__ __forceinline__ void ld_block(int row0, uint32_t (&k)[N]) const {
+    if (row0 < split) {
+      const uint32_t* const r = p + row0 * 32;
+#pragma unroll
+      for (int i = 0; i < N; ++i) k[i] = r[i * 32];
+    } else {
+      tm_ld_block<N>(tcol + (uint32_t)(row0 - split), k);
+    }
+  }
+  template <int N> __device__ __forceinline__ void ld_block_n(int row0, int size, uint32_t (&k)[N]) const {
+    if (row0 < split) {
+      const uint32_t* const r = p + row0 * 32;
+#pragma unroll
+      for (int i = 0; i < N; ++i) k[i] = i < size ? r[i * 32] : 0u;
+    } else {                                   // rare (atoms that share a slot): column by column
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        k[i] = 0u;
+        if (i < size) tm_ld1(tcol + (uint32_t)(row0 - split + i), &k[i]);
+      }
+    }
+  }
+  template <int N> __device__ __forceinline__ void st_block(int row0, const uint32_t (&k)[N]) const {
+    if (row0 < split) {
+      uint32_t* const r = p + row0 * 32;
+#pragma unroll
+      for (int i = 0; i < N; ++i) r[i * 32] = k[i];
+    } else {
+      tm_st_block<N>(tcol + (uint32_t)(row0 - split), k);
+    }
+  }
+  template <int N> __device__ __forceinline__ void st_block_n(int row0, int size, const uint32_t (&k)[N]) const {
+    if (row0 < split) {
+      uint32_t* const r = p + row0 * 32;
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (i < size) r[i * 32] = k[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (i < size) tm_st1(tcol + (uint32_t)(row0 - split + i), &k[i]);
+    }
+  }
+  template <int N> __device__ __forceinline__ void ld_front(int base, int kk, uint32_t (&sv)[N]) const {
+    if (base < split) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) sv[i] = p[(base + (kk - i > 0 ? kk - i : 0)) * 32];
+    } else {
+      uint32_t a[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) a[i] = tcol + (uint32_t)(base - split + (kk - i > 0 ? kk - i : 0));
+      tm_gather<N>(a, sv);
+    }
+  }
+};
+
+enum { TM_WARPS = 8, TM_COLS_PER_WARP = 256 };
+
+template <int KP, int MAXN>
+__global__ void __launch_bounds__(32 * TM_WARPS, 1) clim_sweep2_tm_kernel(
+    const __grid_constant__ ClimPlan2 p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr,
+    double* __restrict__ seas, int32_t* __restrict__ nempty, int smem_slots) {
+  extern __shared__ uint32_t pool[];
+  __shared__ uint32_t tm_base;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (wib == 0) {               // the block owns all 512 columns of its SM (one block per SM: launch bounds + shared memory)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(&tm_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tm_base;
+  const int64_t cell = ((int64_t)blockIdx.x * TM_WARPS + wib) * 32 + lane;
+  const bool ok = cell < ngrid;
+  const float* col = ts + (ok ? cell : 0);
+  const int split = smem_slots * p.slot_rows;
+  SplitPool pl;
+  pl.p = pool + (size_t)wib * split * 32 + lane;
+  pl.split = split;
+  pl.tcol = tbase + ((uint32_t)((wib & 3) * 32) << 16) + (uint32_t)((wib >> 2) * TM_COLS_PER_WARP);
+  WarpEnv env;
+  {
+    TopkSweeperP<WarpEnv, SplitPool, KP, MAXN> sw(env, p, pl, col, ngrid, ok);
+    for (int s = -1; s < p.nsteps; ++s) {          // s = -1: initial fill of the first window
+      double a, b;
+      int row;
+      sw.step(s, a, b, row);
+      if (ok && s >= 0) {
+        thr[(int64_t)row * ngrid + cell] = a;
+        seas[(int64_t)row * ngrid + cell] = b;
+      }
+      __syncthreads();                             // lockstep: the 8 warps stream the same code
+    }
+    if (ok) nempty[cell] = sw.nzero;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (wib == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
+}
+
 // doys whose window is not a range of the atom order (doy 60): direct selection, one thread = one cell
 template <int KP>
 __global__ void __launch_bounds__(128) clim_direct_kernel(const float* __restrict__ ts, int64_t ngrid,
@@ -1183,6 +1337,33 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
 #define XMHW_SWEEP2(K, N)                                                                                            \
   { if (wpb == 4) XMHW_SWEEP2_W(K, N, 4) else if (wpb == 2) XMHW_SWEEP2_W(K, N, 2) else XMHW_SWEEP2_W(K, N, 1) }
   const bool big = plan->max_size > 32;
+  // XMHW_B200_SWEEP2_TMEM=1: 8 warps per SM, the slots that do not fit shared memory live in tensor memory
+  const int tm_on = getenv("XMHW_B200_SWEEP2_TMEM") ? atoi(getenv("XMHW_B200_SWEEP2_TMEM")) : 0;      // read per call
+  if (tm_on) {
+    const int max_smem_slots = (int)((227 * 1024 - 1024) / ((size_t)TM_WARPS * plan->slot_rows * 128));
+    const int min_smem_slots = plan->nslots - TM_COLS_PER_WARP / plan->slot_rows;
+    if (min_smem_slots <= max_smem_slots) {
+      const int smem_slots = min_smem_slots > 0 ? min_smem_slots : 0;
+      const size_t tsmem = (size_t)TM_WARPS * smem_slots * plan->slot_rows * 128;
+#define XMHW_TM(K, N)                                                                                                 \
+  {                                                                                                                   \
+    e = cudaFuncSetAttribute(clim_sweep2_tm_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);    \
+    if (e != cudaSuccess) return (int)e;                                                                              \
+    clim_sweep2_tm_kernel<K, N><<<(unsigned)((ncg + TM_WARPS - 1) / TM_WARPS), 32 * TM_WARPS, tsmem,                  \
+                                  (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw, nempty, smem_slots);    \
+  }
+      switch (plan->kp) {
+        case 8: if (big) XMHW_TM(8, 48) else XMHW_TM(8, 32) break;
+        case 16: if (big) XMHW_TM(16, 48) else XMHW_TM(16, 32) break;
+        case 24: if (big) XMHW_TM(24, 48) else XMHW_TM(24, 32) break;
+        case 36: if (big) XMHW_TM(36, 48) else XMHW_TM(36, 32) break;
+        case 48: if (big) XMHW_TM(48, 48) else XMHW_TM(48, 32) break;
+        default: return XMHW_E_PLAN;
+      }
+#undef XMHW_TM
+      return cuda_status();
+    }
+  }
   switch (plan->kp) {
     case 8: if (big) XMHW_SWEEP2(8, 48) else XMHW_SWEEP2(8, 32) break;
     case 16: if (big) XMHW_SWEEP2(16, 48) else XMHW_SWEEP2(16, 32) break;

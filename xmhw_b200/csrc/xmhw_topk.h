@@ -90,12 +90,49 @@ XMHW_HD void merge_topk(uint32_t (&A)[KP], const uint32_t (&L)[N]) {
   bitonic_valley_desc<KP>(A);
 }
 
-template <class Env, int KP, int MAXN>
-struct TopkSweeper {
+// Where a warp's unit slots live.  Every access of the sweep names a WARP-UNIFORM row (the lane only selects
+// the word of the row), so a pool may be any memory with "row of 32 lane-private words" addressing:
+// PlainPool = shared memory on the device / plain memory in the host emulator; the CUDA file adds a pool whose
+// upper rows are columns of tensor memory (tcgen05.ld / st, 32 lanes x 32 bit shape).
+struct PlainPool {
+  uint32_t* p;           // row 0, this lane's word
+  static constexpr bool kGather = false;      // query: load each front row right where it is used
+  XMHW_HD PlainPool(uint32_t* base, int lane) : p(base + lane) {}
+  XMHW_HD uint32_t ld(int row) const { return p[row * 32]; }
+  XMHW_HD void st(int row, uint32_t v) const { p[row * 32] = v; }
+  template <int N> XMHW_HD void ld_block(int row0, uint32_t (&k)[N]) const {
+    const uint32_t* const r = p + row0 * 32;
+#pragma unroll
+    for (int i = 0; i < N; ++i) k[i] = r[i * 32];
+  }
+  template <int N> XMHW_HD void ld_block_n(int row0, int size, uint32_t (&k)[N]) const {     // rows past `size`: 0
+    const uint32_t* const r = p + row0 * 32;
+#pragma unroll
+    for (int i = 0; i < N; ++i) k[i] = i < size ? r[i * 32] : 0u;
+  }
+  template <int N> XMHW_HD void st_block(int row0, const uint32_t (&k)[N]) const {
+    uint32_t* const r = p + row0 * 32;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i * 32] = k[i];
+  }
+  template <int N> XMHW_HD void st_block_n(int row0, int size, const uint32_t (&k)[N]) const { // only the first `size` rows
+    uint32_t* const r = p + row0 * 32;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (i < size) r[i * 32] = k[i];
+  }
+  // front rows of the query: sv[i] = row max(kk - i, 0) of the slot at `base`
+  template <int N> XMHW_HD void ld_front(int base, int kk, uint32_t (&sv)[N]) const {
+#pragma unroll
+    for (int i = 0; i < N; ++i) sv[i] = p[(base + (kk - i > 0 ? kk - i : 0)) * 32];
+  }
+};
+
+template <class Env, class Pool, int KP, int MAXN>
+struct TopkSweeperP {
   const Env& env;
   const ClimPlan2& p;
-  uint32_t* pool;        // this warp's shared-memory rows (32 words each; word = lane)
-  const int lane;
+  Pool pool;             // this warp's unit-slot rows (32 words each; word = lane)
   const float* col;
   const int64_t ngrid;
   const bool ok;
@@ -105,13 +142,13 @@ struct TopkSweeper {
   int nzero;             // steps without any sample (feeds the per-cell compaction of the smoothing)
   double wsum;           // f64 sum of the window (+ pushed unit sums, - popped)
 
-  XMHW_HD TopkSweeper(const Env& e, const ClimPlan2& pl, uint32_t* po, int ln, const float* c, int64_t ng, bool k)
-      : env(e), p(pl), pool(po), lane(ln), col(c), ngrid(ng), ok(k), n(0), nzero(0), wsum(0.0) {
+  XMHW_HD TopkSweeperP(const Env& e, const ClimPlan2& pl, const Pool& po, const float* c, int64_t ng, bool k)
+      : env(e), p(pl), pool(po), col(c), ngrid(ng), ok(k), n(0), nzero(0), wsum(0.0) {
 #pragma unroll
     for (int i = 0; i < KP; ++i) A[i] = 0u;
   }
 
-  XMHW_HD uint32_t& at(int row) { return pool[row * 32 + lane]; }
+  XMHW_HD uint32_t at(int row) const { return pool.ld(row); }
 
   // issue the loads of the atom (d0, d1): row i = first row + pattern[i]
   XMHW_HD void prefetch(uint32_t d0, uint32_t d1) {
@@ -132,7 +169,7 @@ struct TopkSweeper {
   XMHW_HD void job(bool push, int size, int flags, int slot_base, int off, bool alive) {
     uint32_t k[N];
     bool acc = alive;
-    uint32_t* const srow = pool + (slot_base + 1 + off) * 32 + lane;
+    const int srow = slot_base + 1 + off;          // first key row of the atom in its slot
     if (push) {
       int len = 0;
       double sum = 0.0;
@@ -146,32 +183,23 @@ struct TopkSweeper {
       }
       acc = env.any(len > 0);
       if (acc) sort_desc<N>(k);
-      if (flags & JOB_F_RAGGED) {
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-          if (i < size) srow[i * 32] = k[i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < N; ++i) srow[i * 32] = k[i];
-      }
-      uint32_t* const lrow = pool + slot_base * 32 + lane;
-      uint32_t* const sum_row = pool + (slot_base + 1 + p.cap) * 32 + lane;
+      if (flags & JOB_F_RAGGED) pool.template st_block_n<N>(srow, size, k);
+      else pool.template st_block<N>(srow, k);
+      const int lrow = slot_base, sum_row = slot_base + 1 + p.cap;
       if (flags & JOB_F_FIRST) {
-        lrow[0] = XMHW_GUARD | (uint32_t)len;
-        sum_row[0] = f64_lo(sum); sum_row[32] = f64_hi(sum);
+        pool.st(lrow, XMHW_GUARD | (uint32_t)len);
+        pool.st(sum_row, f64_lo(sum)); pool.st(sum_row + 1, f64_hi(sum));
       } else {
-        lrow[0] = lrow[0] + (uint32_t)len;
-        const double s2 = f64_from(sum_row[0], sum_row[32]) + sum;
-        sum_row[0] = f64_lo(s2); sum_row[32] = f64_hi(s2);
+        pool.st(lrow, pool.ld(lrow) + (uint32_t)len);
+        const double s2 = f64_from(pool.ld(sum_row), pool.ld(sum_row + 1)) + sum;
+        pool.st(sum_row, f64_lo(s2)); pool.st(sum_row + 1, f64_hi(s2));
       }
       n += len;
       wsum = wsum + sum;
     } else if (flags & JOB_F_RAGGED) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) k[i] = i < size ? srow[i * 32] : 0u;
+      pool.template ld_block_n<N>(srow, size, k);
     } else {
-#pragma unroll
-      for (int i = 0; i < N; ++i) k[i] = srow[i * 32];
+      pool.template ld_block<N>(srow, k);
     }
     if (flags & JOB_F_COPY) {
 #pragma unroll
@@ -182,13 +210,13 @@ struct TopkSweeper {
   }
 
   XMHW_HD void store_acc(int slot_base, bool alive) {
-    uint32_t* const srow = pool + (slot_base + 1) * 32 + lane;
     if (alive) {
-#pragma unroll
-      for (int i = 0; i < KP; ++i) srow[i * 32] = A[i];
+      pool.template st_block<KP>(slot_base + 1, A);
     } else {
+      uint32_t z[KP];
 #pragma unroll
-      for (int i = 0; i < KP; ++i) srow[i * 32] = 0u;
+      for (int i = 0; i < KP; ++i) z[i] = 0u;
+      pool.template st_block<KP>(slot_base + 1, z);
     }
   }
 
@@ -290,7 +318,6 @@ struct TopkSweeper {
     // serves R(k) with A[i-1] and R(k-1) with A[i-2].  The rank k = target differs between lanes
     // only where samples are missing, so the warp loops over its DISTINCT ranks: inside the loop
     // every shared-memory row index is warp-uniform (no per-lane addressing).
-    const uint32_t* const srow = pool + front_base * 32 + lane;
     uint32_t r1 = 0u, r2 = 0u;
     int todo = live ? (target < KP ? target : KP) : 0;         // 0: nothing (left) to compute for this lane
     while (true) {
@@ -298,14 +325,26 @@ struct TopkSweeper {
       if (kk == 0) break;
       uint32_t q1 = 0u, q2 = 0u;
       uint32_t am1 = 0xffffffffu, am2 = 0u;                    // A[i-1], A[i-2]
+      if (Pool::kGather) {                                     // all front rows first (one wait), then the scan
+        uint32_t sv[KP + 1];
+        pool.template ld_front<KP + 1>(front_base, kk, sv);
 #pragma unroll
-      for (int i = 0; i <= KP; ++i) {
-        const int row = kk - i > 0 ? kk - i : 0;               // warp-uniform; past the guard: dominated terms
-        const uint32_t sv = srow[row * 32];
-        q1 = umax32(q1, umin32(am1, sv));
-        if (i >= 1) q2 = umax32(q2, umin32(am2, sv));
-        am2 = am1;
-        am1 = i < KP ? A[i] : 0u;
+        for (int i = 0; i <= KP; ++i) {
+          q1 = umax32(q1, umin32(am1, sv[i]));
+          if (i >= 1) q2 = umax32(q2, umin32(am2, sv[i]));
+          am2 = am1;
+          am1 = i < KP ? A[i] : 0u;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i <= KP; ++i) {
+          const int row = kk - i > 0 ? kk - i : 0;             // warp-uniform; past the guard: dominated terms
+          const uint32_t sv = pool.ld(front_base + row);
+          q1 = umax32(q1, umin32(am1, sv));
+          if (i >= 1) q2 = umax32(q2, umin32(am2, sv));
+          am2 = am1;
+          am1 = i < KP ? A[i] : 0u;
+        }
       }
       if (todo == kk) { r1 = q1; r2 = q2; todo = 0; }
     }
@@ -318,6 +357,13 @@ struct TopkSweeper {
       seas = qnan();
     }
   }
+};
+
+// the sweep on a plain (shared / host) memory pool
+template <class Env, int KP, int MAXN>
+struct TopkSweeper : TopkSweeperP<Env, PlainPool, KP, MAXN> {
+  XMHW_HD TopkSweeper(const Env& e, const ClimPlan2& pl, uint32_t* po, int ln, const float* c, int64_t ng, bool k)
+      : TopkSweeperP<Env, PlainPool, KP, MAXN>(e, pl, PlainPool(po, ln), c, ng, k) {}
 };
 
 // ---------------------------------------------------------------------------
