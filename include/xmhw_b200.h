@@ -38,7 +38,7 @@ extern "C" {
 #define XMHW_E_PLAN  (-2)   /* inconsistent climatology plan               */
 #define XMHW_E_SMEM  (-3)   /* plan needs more shared memory than one SM has */
 
-#define XMHW_ABI_VERSION 2
+#define XMHW_ABI_VERSION 3
 
 /* event table columns (struct-of-arrays, column c of event i at [c * cap + i]) */
 enum xmhw_event_i32 {
@@ -137,9 +137,14 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
  * nempty [ngrid] i32 = number of those doys without any sample.  `plan` is a HOST pointer.
  * The few doys the plan excludes (doy 60 of the 366-day calendar: its window holds leap years
  * only) are computed by xmhw_clim_direct_f32 from their row list: rows [nrows] i32 time indices,
- * thresh_row / seas_row = that doy's row of the raw arrays, nempty += 1 where it has no sample. */
+ * thresh_row / seas_row = that doy's row of the raw arrays, nempty += 1 where it has no sample.
+ * group_order: NULL, or a device permutation [ceil(ngrid/32)] i32 of the 32-cell groups = the order the
+ * warps take them in (results do not depend on it).  The warps of a block advance in lockstep, so a block
+ * whose groups have equal work wastes nothing: callers put the groups that look like land (all NaN in a
+ * probe row) last.  With XMHW_B200_SWEEP2_TMEM=1 in the environment the kernel keeps the unit slots that do
+ * not fit shared memory in tensor memory (8 warps per SM instead of 4 at the default window).          */
 int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan2* plan,
-                         double* thresh_raw, double* seas_raw, int32_t* nempty, void* stream);
+                         double* thresh_raw, double* seas_raw, int32_t* nempty, const int32_t* group_order, void* stream);
 int xmhw_clim_direct_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* rows, int32_t nrows, int32_t kp,
                          double q, double* thresh_row, double* seas_row, int32_t* nempty, void* stream);
 

@@ -34,6 +34,6 @@ def test_argument_errors_without_gpu():
     """Null pointers / bad sizes are rejected before any CUDA call."""
     from xmhw_b200 import _cabi
     assert _cabi.lib.xmhw_clim_finish_f64(None, None, 366, 10, 1, 31, None, None) == -1
-    assert _cabi.lib.xmhw_clim_sweep2_f32(None, 10, 10, None, None, None, None, None) == -1
+    assert _cabi.lib.xmhw_clim_sweep2_f32(None, 10, 10, None, None, None, None, None, None) == -1
     assert _cabi.lib.xmhw_events_count(None, 10, 10, 5, 1, 2, None, None) == -1
     assert _cabi.lib.xmhw_exclusive_scan_i32(None, 0, None, None, None) == -1

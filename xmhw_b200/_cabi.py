@@ -74,7 +74,7 @@ _SIGNATURES = {
     "xmhw_clim_sweep_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlanStruct),
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_clim_sweep2_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlan2Struct),
-                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_clim_direct_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_clim_finish_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
@@ -140,7 +140,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 2
+ABI_VERSION = 3
 if lib.xmhw_abi_version() != ABI_VERSION:
     raise ImportError("xmhw_b200: ABI version mismatch in %s" % LIB_PATH)
 

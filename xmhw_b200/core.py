@@ -106,6 +106,19 @@ class DevicePlan2:
 TOPK_AUTO_MIN_WARPS = 8
 
 
+def _group_order(ts):
+    """Processing order of the 32-cell groups for the lockstep top-K sweep: groups that look like land (all 32
+    cells NaN in three probe rows) last, so a block's warps carry equal work.  Any permutation is correct;
+    this one only costs three row reads."""
+    T, ngrid = ts.shape
+    ncg = (ngrid + 31) // 32
+    probe = torch.isnan(ts[0]) & torch.isnan(ts[T // 2]) & torch.isnan(ts[T - 1])
+    if ncg * 32 != ngrid:
+        probe = torch.cat([probe, torch.ones(ncg * 32 - ngrid, dtype=torch.bool, device=ts.device)])
+    land = probe.view(ncg, 32).all(dim=1)
+    return torch.argsort(land.to(torch.uint8), stable=True).to(torch.int32)
+
+
 def _topk_warps_per_sm(host_plan):
     return (227 * 1024) // (host_plan.pool_rows * 128 + 256)
 
@@ -209,7 +222,10 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
             alloc = torch.empty if full else (lambda *a, **k: torch.full(*a, float("nan"), **k))
             raw_t = alloc((ndoy, ngrid), dtype=torch.float64, device=ts.device)
             raw_s = alloc((ndoy, ngrid), dtype=torch.float64, device=ts.device)
-            _call("xmhw_clim_sweep2_f32", _ptr(ts), T, ngrid, dp2.struct, _ptr(raw_t), _ptr(raw_s), _ptr(nempty), st)
+            import os
+            order = _group_order(ts) if os.environ.get("XMHW_B200_SWEEP2_ORDER", "1") != "0" else None
+            _call("xmhw_clim_sweep2_f32", _ptr(ts), T, ngrid, dp2.struct, _ptr(raw_t), _ptr(raw_s), _ptr(nempty),
+                  _ptr(order) if order is not None else None, st)
             for k, d in enumerate(h.exc_doy):
                 a, b = int(h.exc_off[k]), int(h.exc_off[k + 1])
                 _call("xmhw_clim_direct_f32", _ptr(ts), T, ngrid, _ptr(dp2.exc_rows) + 4 * a, b - a, h.kp, float(q),

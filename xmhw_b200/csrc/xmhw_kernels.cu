@@ -83,13 +83,21 @@ __global__ void __launch_bounds__(32, MINB) clim_sweep_kernel(
 // WPB warps per block: with WPB > 1 the warps of a block step in lockstep (one barrier per doy), so
 // the SM's four resident warps stream the SAME ~30 KB of straight-line code through the 32 KB
 // instruction cache instead of four different positions of it.
+// 32-cell group of warp `w` of the grid: order[w] when the caller passed a processing order (land-looking groups
+// last, so that the warps of one lockstep block have the same amount of work), w otherwise; past the grid: none
+__device__ __forceinline__ int64_t sweep2_group(const int32_t* order, int64_t w, int64_t ngrid) {
+  const int64_t ncg = (ngrid + 31) / 32;
+  if (w >= ncg) return ncg;
+  return order ? (int64_t)__ldg(order + w) : w;
+}
+
 template <int KP, int MAXN, int WPB, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB) clim_sweep2_kernel(
     const __grid_constant__ ClimPlan2 p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr,
-    double* __restrict__ seas, int32_t* __restrict__ nempty) {
+    double* __restrict__ seas, int32_t* __restrict__ nempty, const int32_t* __restrict__ order) {
   extern __shared__ uint32_t pool[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t cell = ((int64_t)blockIdx.x * WPB + wib) * 32 + lane;
+  const int64_t cell = sweep2_group(order, (int64_t)blockIdx.x * WPB + wib, ngrid) * 32 + lane;
   const bool ok = cell < ngrid;
   const float* col = ts + (ok ? cell : 0);
   WarpEnv env;
@@ -220,7 +228,8 @@ enum { TM_WARPS = 8, TM_COLS_PER_WARP = 256 };
 template <int KP, int MAXN>
 __global__ void __launch_bounds__(32 * TM_WARPS, 1) clim_sweep2_tm_kernel(
     const __grid_constant__ ClimPlan2 p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr,
-    double* __restrict__ seas, int32_t* __restrict__ nempty, int smem_slots) {
+    double* __restrict__ seas, int32_t* __restrict__ nempty, const int32_t* __restrict__ order, int smem_slots,
+    int sync_every) {
   extern __shared__ uint32_t pool[];
   __shared__ uint32_t tm_base;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(32 * TM_WARPS, 1) clim_sweep2_tm_kernel(
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tbase = tm_base;
-  const int64_t cell = ((int64_t)blockIdx.x * TM_WARPS + wib) * 32 + lane;
+  const int64_t cell = sweep2_group(order, (int64_t)blockIdx.x * TM_WARPS + wib, ngrid) * 32 + lane;
   const bool ok = cell < ngrid;
   const float* col = ts + (ok ? cell : 0);
   const int split = smem_slots * p.slot_rows;
@@ -252,7 +261,7 @@ __global__ void __launch_bounds__(32 * TM_WARPS, 1) clim_sweep2_tm_kernel(
         thr[(int64_t)row * ngrid + cell] = a;
         seas[(int64_t)row * ngrid + cell] = b;
       }
-      __syncthreads();                             // lockstep: the 8 warps stream the same code
+      if (sync_every > 0 && (s + 1) % sync_every == 0) __syncthreads();      // lockstep: the 8 warps stream the same code
     }
     if (ok) nempty[cell] = sw.nzero;
   }
@@ -1307,7 +1316,7 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
 }
 
 int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan2* plan,
-                         double* thresh_raw, double* seas_raw, int32_t* nempty, void* stream) {
+                         double* thresh_raw, double* seas_raw, int32_t* nempty, const int32_t* group_order, void* stream) {
   if (!ts || !plan || !thresh_raw || !seas_raw || !nempty || T <= 0 || ngrid <= 0) return XMHW_E_ARG;
   if (ngrid > 0xffffffffll || T > 0x7fffffffll) return XMHW_E_ARG;
   if (plan->nsteps <= 0 || plan->nsteps > SC_MAX_STEPS || plan->nslots <= 0 || plan->nslots > 32 ||
@@ -1332,7 +1341,7 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
     e = cudaFuncSetAttribute(clim_sweep2_kernel<K, N, W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return (int)e;                                                                             \
     clim_sweep2_kernel<K, N, W, 1><<<(unsigned)((ncg + W - 1) / W), 32 * W, smem, (cudaStream_t)stream>>>(           \
-        p, ts, ngrid, thresh_raw, seas_raw, nempty);                                                                 \
+        p, ts, ngrid, thresh_raw, seas_raw, nempty, group_order);                                                    \
   }
 #define XMHW_SWEEP2(K, N)                                                                                            \
   { if (wpb == 4) XMHW_SWEEP2_W(K, N, 4) else if (wpb == 2) XMHW_SWEEP2_W(K, N, 2) else XMHW_SWEEP2_W(K, N, 1) }
@@ -1340,6 +1349,7 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
   // XMHW_B200_SWEEP2_TMEM=1: 8 warps per SM, the slots that do not fit shared memory live in tensor memory
   const int tm_on = getenv("XMHW_B200_SWEEP2_TMEM") ? atoi(getenv("XMHW_B200_SWEEP2_TMEM")) : 0;      // read per call
   if (tm_on) {
+    const int tm_sync = getenv("XMHW_B200_SWEEP2_TM_SYNC") ? atoi(getenv("XMHW_B200_SWEEP2_TM_SYNC")) : 1;   // development knob
     const int max_smem_slots = (int)((227 * 1024 - 1024) / ((size_t)TM_WARPS * plan->slot_rows * 128));
     const int min_smem_slots = plan->nslots - TM_COLS_PER_WARP / plan->slot_rows;
     if (min_smem_slots <= max_smem_slots) {
@@ -1350,7 +1360,8 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
     e = cudaFuncSetAttribute(clim_sweep2_tm_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);    \
     if (e != cudaSuccess) return (int)e;                                                                              \
     clim_sweep2_tm_kernel<K, N><<<(unsigned)((ncg + TM_WARPS - 1) / TM_WARPS), 32 * TM_WARPS, tsmem,                  \
-                                  (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw, nempty, smem_slots);    \
+                                  (cudaStream_t)stream>>>(p, ts, ngrid, thresh_raw, seas_raw, nempty, group_order,  \
+                                                          smem_slots, tm_sync);                                       \
   }
       switch (plan->kp) {
         case 8: if (big) XMHW_TM(8, 48) else XMHW_TM(8, 32) break;
