@@ -41,6 +41,8 @@ static void sweep_cells(const float* ts, int64_t ngrid, const ClimPlan* plan, do
   }
 }
 
+static int g_phased = 0;      // 1: TopkSweeperP::step_phased (the step of the tensor-memory kernel)
+
 template <int KP, int MAXN>
 static void sweep2_cells(const float* ts, int64_t ngrid, const ClimPlan2* plan, double* thr, double* seas,
                          int32_t* nzero) {
@@ -52,7 +54,7 @@ static void sweep2_cells(const float* ts, int64_t ngrid, const ClimPlan2* plan, 
     for (int s = -1; s < plan->nsteps; ++s) {
       double a, b;
       int row;
-      sw.step(s, a, b, row);
+      if (g_phased) sw.step_phased(s, a, b, row); else sw.step(s, a, b, row);
       if (s < 0) continue;
       thr[(int64_t)row * ngrid + cell] = a;
       seas[(int64_t)row * ngrid + cell] = b;
@@ -77,6 +79,8 @@ static void direct_cells(const float* ts, int64_t ngrid, const int32_t* rows, in
 }
 
 extern "C" {
+
+void emul_set_phased(int on) { g_phased = on; }
 
 int emul_clim_sweep2(const float* ts, int64_t T, int64_t ngrid, const ClimPlan2* plan, double* thr, double* seas,
                      int32_t* nzero) {

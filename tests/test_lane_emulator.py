@@ -70,10 +70,12 @@ def test_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct, keep):
     assert hp.rows_loaded < len(doy) * 1.1 and hp.max_size <= 48
 
 
-def sweep2(em, ts, doy, ndoy, w, q):
-    """two-stack top-K sweep (csrc/xmhw_topk.h) + the direct selection of the exceptional doys"""
+def sweep2(em, ts, doy, ndoy, w, q, phased=False):
+    """two-stack top-K sweep (csrc/xmhw_topk.h) + the direct selection of the exceptional doys;
+    phased: the step with separate push / flip loops (step_phased, what the tensor-memory kernel runs)"""
     from xmhw_b200 import plan2 as P2
     lib, cabi = em
+    lib.emul_set_phased(1 if phased else 0)
     hp = P2.build_clim_plan2(doy, ndoy, w, q)
     if hp is None:
         return None, None, None, None
@@ -100,8 +102,9 @@ CASES2 = CASES + [
 ]
 
 
+@pytest.mark.parametrize("phased", [False, True], ids=["step", "step_phased"])
 @pytest.mark.parametrize("name,years,ncell,nan_ppm,w,pct", CASES2, ids=[c[0] for c in CASES2])
-def test_topk_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct):
+def test_topk_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct, phased):
     """The two-stack top-K sweep is bit-equal to the oracle wherever its plan accepts the calendar;
     the cases it declines (huge K, very wide windows) are the general sweep's (test above)."""
     tm = S.daily_time(*years)
@@ -111,7 +114,7 @@ def test_topk_sweep_matches_oracle(em, name, years, ncell, nan_ppm, w, pct):
         ts[100:300, 3] = np.nan
         ts[:, 5] = np.nan
         ts[700:, 7] = np.nan
-    hp, thr, se, nz = sweep2(em, ts, doy, 366, w, pct / 100.0)
+    hp, thr, se, nz = sweep2(em, ts, doy, 366, w, pct / 100.0, phased=phased)
     if name in ("70yr_two_pieces", "w15_p10"):
         assert hp is None
         return

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) clim_sweep2_kernel(
   for (int s = -1; s < p.nsteps; ++s) {          // s = -1: initial fill of the first window
     double a, b;
     int row;
-    sw.step(s, a, b, row);
+    sw.step_phased(s, a, b, row);
     if (ok && s >= 0) {
       thr[(int64_t)row * ngrid + cell] = a;
       seas[(int64_t)row * ngrid + cell] = b;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(32 * TM_WARPS, 1) clim_sweep2_tm_kernel(
     for (int s = -1; s < p.nsteps; ++s) {          // s = -1: initial fill of the first window
       double a, b;
       int row;
-      sw.step(s, a, b, row);
+      sw.step_phased(s, a, b, row);
       if (ok && s >= 0) {
         thr[(int64_t)row * ngrid + cell] = a;
         seas[(int64_t)row * ngrid + cell] = b;
@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(32 * TM_WARPS, 1) clim_sweep2_tm_kernel(
     }
     if (ok) nempty[cell] = sw.nzero;
   }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (wib == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
@@ -1349,7 +1350,7 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
   // XMHW_B200_SWEEP2_TMEM=1: 8 warps per SM, the slots that do not fit shared memory live in tensor memory
   const int tm_on = getenv("XMHW_B200_SWEEP2_TMEM") ? atoi(getenv("XMHW_B200_SWEEP2_TMEM")) : 0;      // read per call
   if (tm_on) {
-    const int tm_sync = getenv("XMHW_B200_SWEEP2_TM_SYNC") ? atoi(getenv("XMHW_B200_SWEEP2_TM_SYNC")) : 1;   // development knob
+    const int tm_sync = getenv("XMHW_B200_SWEEP2_TM_SYNC") ? atoi(getenv("XMHW_B200_SWEEP2_TM_SYNC")) : 4;   // development knob
     const int max_smem_slots = (int)((227 * 1024 - 1024) / ((size_t)TM_WARPS * plan->slot_rows * 128));
     const int min_smem_slots = plan->nslots - TM_COLS_PER_WARP / plan->slot_rows;
     if (min_smem_slots <= max_smem_slots) {

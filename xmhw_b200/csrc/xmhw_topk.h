@@ -220,6 +220,108 @@ struct TopkSweeperP {
     }
   }
 
+  // ---- the same step with the pushes and the flip entries in two separate loops (step_phased): each loop
+  // body updates the accumulator along ONE path, which keeps ptxas from copying the 36 accumulator
+  // registers into a working set and back around every job (72 moves per job in step()).
+  XMHW_HD void push_jobs(bool fill, const uint32_t* rec, int n_push) {
+#pragma unroll 1
+    for (int j = 0; j < n_push; ++j) {
+      const uint32_t d0 = fill ? p.init[j][0] : rec[REC_PUSH + 2 * j];
+      const uint32_t d1 = fill ? p.init[j][1] : rec[REC_PUSH + 2 * j + 1];
+      const bool last = j + 1 == n_push;
+      const uint32_t nx0 = fill ? p.init[j + 1][0] : (last ? rec[REC_NEXT] : rec[REC_PUSH + 2 * j + 2]);
+      const uint32_t nx1 = fill ? p.init[j + 1][1] : (last ? rec[REC_NEXT + 1] : rec[REC_PUSH + 2 * j + 3]);
+      const int size = (int)((d0 >> 24) & 63u);
+      const int flags = (int)(d0 >> 30) | (int)(((d1 >> 17) & 1u) * JOB_F_RAGGED);
+      const int slot_base = (int)((d1 >> 5) & 31u) * p.slot_rows;
+      const int srow = slot_base + 1 + (int)((d1 >> 10) & 127u);
+      uint32_t k[MAXN];
+      int len = 0;
+      double sum = 0.0;
+#pragma unroll
+      for (int i = 0; i < MAXN; ++i) {
+        const float v = pv[i];
+        const uint32_t b = f32_bits(v);
+        const bool valid = (i < size) && ok && (v == v);
+        k[i] = valid ? (b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u)) : 0u;
+        if (valid) { ++len; sum = sum + (double)v; }
+      }
+      if ((nx0 >> 24) & 63u) prefetch(nx0, nx1);              // pv is free again: the next atom's loads go out now
+      const bool acc = env.any(len > 0);
+      if (acc) sort_desc<MAXN>(k);
+      if (flags & JOB_F_RAGGED) pool.template st_block_n<MAXN>(srow, size, k);
+      else pool.template st_block<MAXN>(srow, k);
+      const int lrow = slot_base, sum_row = slot_base + 1 + p.cap;
+      if (flags & JOB_F_FIRST) {
+        pool.st(lrow, XMHW_GUARD | (uint32_t)len);
+        pool.st(sum_row, f64_lo(sum)); pool.st(sum_row + 1, f64_hi(sum));
+      } else {
+        pool.st(lrow, pool.ld(lrow) + (uint32_t)len);
+        const double s2 = f64_from(pool.ld(sum_row), pool.ld(sum_row + 1)) + sum;
+        pool.st(sum_row, f64_lo(s2)); pool.st(sum_row + 1, f64_hi(s2));
+      }
+      n += len;
+      wsum = wsum + sum;
+      if (flags & JOB_F_COPY) {                                // accumulator := this atom (= merge into an empty one)
+#pragma unroll
+        for (int i = 0; i < KP; ++i) A[i] = 0u;
+      }
+      if (acc) merge_topk<KP, MAXN>(A, k);
+    }
+  }
+
+  XMHW_HD void flip_jobs(int n_flip, int flip_off) {
+    const bool alive = env.any(n > 0);                         // the window as it is when the flip starts
+#pragma unroll 1
+    for (int e = 0; e < n_flip; ++e) {
+      const uint32_t f0 = p.flip[flip_off + e];
+      const int slot_base = (int)(f0 & 31u) * p.slot_rows;
+      const int srow = slot_base + 1 + (int)((f0 >> 5) & 127u);
+      const int size = (int)((f0 >> 12) & 63u), flags = (int)((f0 >> 18) & 63u);
+      const int dst_base = (int)((f0 >> 24) & 31u) * p.slot_rows;
+      if (flags & (JOB_F_CLEAR | JOB_F_COPY)) {
+#pragma unroll
+        for (int i = 0; i < KP; ++i) A[i] = 0u;
+      }
+      if (!(flags & (JOB_F_CLEAR | JOB_F_STOREP)) && alive) {
+        uint32_t k[MAXN];
+        if (flags & JOB_F_RAGGED) pool.template ld_block_n<MAXN>(srow, size, k);
+        else pool.template ld_block<MAXN>(srow, k);
+        merge_topk<KP, MAXN>(A, k);
+      }
+      if (flags & JOB_F_STOREP) store_acc(dst_base, alive);
+      else if (flags & JOB_F_STORE) store_acc(slot_base, alive);
+    }
+  }
+
+  XMHW_HD void step_phased(int s, double& thresh, double& seas, int& out_row) {
+    const bool fill = s < 0;
+    const uint32_t* const rec = p.rec[fill ? 0 : s];
+    const uint32_t w0 = fill ? 0u : rec[0];
+    const int n_pop = (int)(w0 & 7u), n_push = fill ? p.n_init : (int)((w0 >> 3) & 3u), n_flip = (int)((w0 >> 6) & 63u);
+    const bool flip_late = ((w0 >> 5) & 1u) != 0u;
+    const int front_base = (int)((w0 >> 12) & 31u) * p.slot_rows;
+    out_row = (int)(w0 >> 17);
+    double psum = 0.0;
+    {
+      const uint32_t pw = fill ? 0u : rec[REC_POPS];
+      for (int j = 0; j < n_pop; ++j) {
+        const int sb = (int)((pw >> (5 * j)) & 31u) * p.slot_rows;
+        n -= (int)(at(sb) & 0xffu);
+        psum = psum + f64_from(at(sb + 1 + p.cap), at(sb + 2 + p.cap));
+      }
+    }
+    if (fill) prefetch(p.init[0][0], p.init[0][1]);
+    const int flip_off = fill ? 0 : (int)rec[REC_FLIP_OFF];
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) {                           // one site of each loop: flips before or after the pushes
+      if ((ph == 0) == flip_late) push_jobs(fill, rec, n_push);
+      else if (n_flip) flip_jobs(n_flip, flip_off);
+    }
+    if (fill) { thresh = qnan(); seas = qnan(); return; }
+    query(rec, psum, front_base, thresh, seas);
+  }
+
   // Pops, then the step's jobs (a flip's entries before or after the pushes), then the query.
   // s = -1 is the initial fill: the atoms of the first window (plan.init).
   XMHW_HD void step(int s, double& thresh, double& seas, int& out_row) {
@@ -287,6 +389,11 @@ struct TopkSweeperP {
       }
     }
     if (fill) { thresh = qnan(); seas = qnan(); return; }
+    query(rec, psum, front_base, thresh, seas);
+  }
+
+  // quantile + mean of the window as it stands after the step's pops / pushes / flips
+  XMHW_HD void query(const uint32_t* rec, double psum, int front_base, double& thresh, double& seas) {
     wsum = wsum - psum;
     const bool live = n > 0;
     nzero += live ? 0 : 1;
