@@ -141,8 +141,9 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
  * group_order: NULL, or a device permutation [ceil(ngrid/32)] i32 of the 32-cell groups = the order the
  * warps take them in (results do not depend on it).  The warps of a block advance in lockstep, so a block
  * whose groups have equal work wastes nothing: callers put the groups that look like land (all NaN in a
- * probe row) last.  With XMHW_B200_SWEEP2_TMEM=1 in the environment the kernel keeps the unit slots that do
- * not fit shared memory in tensor memory (8 warps per SM instead of 4 at the default window).          */
+ * probe row) last.  When fewer than 8 warps' unit slots fit the shared memory of one SM (default window:
+ * 4), the library launches the variant that keeps the remaining slots in tensor memory (tcgen05.ld / st),
+ * 8 warps per SM; XMHW_B200_SWEEP2_TMEM=0 in the environment turns that off.                           */
 int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan2* plan,
                          double* thresh_raw, double* seas_raw, int32_t* nempty, const int32_t* group_order, void* stream);
 int xmhw_clim_direct_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* rows, int32_t nrows, int32_t kp,

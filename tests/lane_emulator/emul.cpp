@@ -86,12 +86,13 @@ int emul_clim_sweep2(const float* ts, int64_t T, int64_t ngrid, const ClimPlan2*
                      int32_t* nzero) {
   (void)T;
   const bool big = plan->max_size > 32;
+  const bool n30 = plan->max_size <= 30;
   switch (plan->kp) {
-    case 8: if (big) sweep2_cells<8, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<8, 32>(ts, ngrid, plan, thr, seas, nzero); break;
-    case 16: if (big) sweep2_cells<16, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<16, 32>(ts, ngrid, plan, thr, seas, nzero); break;
-    case 24: if (big) sweep2_cells<24, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<24, 32>(ts, ngrid, plan, thr, seas, nzero); break;
-    case 36: if (big) sweep2_cells<36, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<36, 32>(ts, ngrid, plan, thr, seas, nzero); break;
-    case 48: if (big) sweep2_cells<48, 48>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<48, 32>(ts, ngrid, plan, thr, seas, nzero); break;
+    case 8: if (big) sweep2_cells<8, 48>(ts, ngrid, plan, thr, seas, nzero); else if (n30) sweep2_cells<8, 30>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<8, 32>(ts, ngrid, plan, thr, seas, nzero); break;
+    case 16: if (big) sweep2_cells<16, 48>(ts, ngrid, plan, thr, seas, nzero); else if (n30) sweep2_cells<16, 30>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<16, 32>(ts, ngrid, plan, thr, seas, nzero); break;
+    case 24: if (big) sweep2_cells<24, 48>(ts, ngrid, plan, thr, seas, nzero); else if (n30) sweep2_cells<24, 30>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<24, 32>(ts, ngrid, plan, thr, seas, nzero); break;
+    case 36: if (big) sweep2_cells<36, 48>(ts, ngrid, plan, thr, seas, nzero); else if (n30) sweep2_cells<36, 30>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<36, 32>(ts, ngrid, plan, thr, seas, nzero); break;
+    case 48: if (big) sweep2_cells<48, 48>(ts, ngrid, plan, thr, seas, nzero); else if (n30) sweep2_cells<48, 30>(ts, ngrid, plan, thr, seas, nzero); else sweep2_cells<48, 32>(ts, ngrid, plan, thr, seas, nzero); break;
     default: return -1;
   }
   return 0;

@@ -96,14 +96,26 @@ class DevicePlan2:
     exc_rows: object            # device int32: window rows of the exceptional doys (CSR by host.exc_off)
 
 
-# Which sweep "auto" picks.  Measured on B200 (30-year daily series, profiles/kernel_ms_r02o_sweep_occupancy.txt):
-# the two-stack top-K sweep is bound by the warps its unit slots leave room for.  Default window
-# (windowHalfWidth 5: 11 slots x 40 rows = 55 KB per warp, 4 warps per SM): 65 ms against 52 ms of the
-# general sorted-list sweep on the global grid (pctile 99: 47 against 37).  Narrow windows
-# (windowHalfWidth <= 2: <= 25 KB per warp, >= 8 warps per SM): 8.2 against 9.6 ms and 6.6 against 7.6 ms on
-# the quarter grid -- there the top-K sweep wins, so "auto" takes it when at least TOPK_AUTO_MIN_WARPS of
-# its warps fit one SM, and the general sweep otherwise.
+# Which sweep "auto" picks.  Measured on B200 (30-year daily series, profiles/kernel_ms_r02o_sweep_occupancy.txt,
+# profiles/kernel_ms_r02r_sweep2_tmem.txt): the two-stack top-K sweep is bound by the warps its unit slots leave
+# room for.  With 8 warps per SM it beats the general sorted-list sweep at every window measured -- in shared
+# memory alone for narrow windows (windowHalfWidth <= 2: <= 25 KB per warp), with the slots that do not fit
+# shared memory in TENSOR MEMORY otherwise (default window: 55 KB per warp; 39 ms against 52 ms on the global
+# grid).  "auto" therefore takes the top-K sweep whenever its plan exists and 8 warps fit one way or the
+# other, and the general sweep for the rest (large top-K capacity, very wide windows, > 48-year lists).
 TOPK_AUTO_MIN_WARPS = 8
+TM_WARPS, TM_COLS_PER_WARP = 8, 256          # csrc/xmhw_kernels.cu: the tensor-memory kernel's block and column budget
+
+
+def _topk_warps_per_sm(host_plan):
+    return (227 * 1024) // (host_plan.pool_rows * 128 + 256)
+
+
+def _topk_tmem_fits(host_plan):
+    """The launcher's test (xmhw_clim_sweep2_f32): the slots beyond TM_COLS_PER_WARP tensor-memory columns per warp
+    must fit 8 warps' share of the shared memory."""
+    max_smem_slots = (227 * 1024 - 1024) // (TM_WARPS * host_plan.slot_rows * 128)
+    return host_plan.nslots - TM_COLS_PER_WARP // host_plan.slot_rows <= max_smem_slots
 
 
 def _group_order(ts):
@@ -213,7 +225,8 @@ def threshold_arrays(ts, doy, ndoy, pctile=90, windowHalfWidth=5, smoothPercenti
         nempty = torch.empty(ngrid, dtype=torch.int32, device=ts.device)
         mode = sweep_mode()
         dp2 = device_plan2(doy, ndoy, windowHalfWidth, q, ts.device) if mode in ("topk", "auto") else None
-        if dp2 is not None and mode == "auto" and _topk_warps_per_sm(dp2.host) < TOPK_AUTO_MIN_WARPS:
+        if dp2 is not None and mode == "auto" and _topk_warps_per_sm(dp2.host) < TOPK_AUTO_MIN_WARPS \
+                and not _topk_tmem_fits(dp2.host):
             dp2 = None
         if dp2 is not None:
             # two-stack top-K sweep; rows of the doys it does not cover (absent labels) stay NaN

@@ -1347,8 +1347,12 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
 #define XMHW_SWEEP2(K, N)                                                                                            \
   { if (wpb == 4) XMHW_SWEEP2_W(K, N, 4) else if (wpb == 2) XMHW_SWEEP2_W(K, N, 2) else XMHW_SWEEP2_W(K, N, 1) }
   const bool big = plan->max_size > 32;
-  // XMHW_B200_SWEEP2_TMEM=1: 8 warps per SM, the slots that do not fit shared memory live in tensor memory
-  const int tm_on = getenv("XMHW_B200_SWEEP2_TMEM") ? atoi(getenv("XMHW_B200_SWEEP2_TMEM")) : 0;      // read per call
+  const bool n30 = plan->max_size <= 30;      // 30-year daily series: the 30-input sorting network, 30-row atoms
+  // Tensor-memory kernel (8 warps per SM, the slots that do not fit shared memory live in TMEM): taken when
+  // fewer than 8 warps of the shared-memory kernel fit one SM and the slots split.  XMHW_B200_SWEEP2_TMEM = 0 / 1
+  // forces it off / on (development knob, read per call).
+  const int tm_env = getenv("XMHW_B200_SWEEP2_TMEM") ? atoi(getenv("XMHW_B200_SWEEP2_TMEM")) : -1;
+  const bool tm_on = tm_env == 1 || (tm_env < 0 && fit < TM_WARPS);
   if (tm_on) {
     const int tm_sync = getenv("XMHW_B200_SWEEP2_TM_SYNC") ? atoi(getenv("XMHW_B200_SWEEP2_TM_SYNC")) : 4;   // development knob
     const int max_smem_slots = (int)((227 * 1024 - 1024) / ((size_t)TM_WARPS * plan->slot_rows * 128));
@@ -1365,11 +1369,11 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
                                                           smem_slots, tm_sync);                                       \
   }
       switch (plan->kp) {
-        case 8: if (big) XMHW_TM(8, 48) else XMHW_TM(8, 32) break;
-        case 16: if (big) XMHW_TM(16, 48) else XMHW_TM(16, 32) break;
-        case 24: if (big) XMHW_TM(24, 48) else XMHW_TM(24, 32) break;
-        case 36: if (big) XMHW_TM(36, 48) else XMHW_TM(36, 32) break;
-        case 48: if (big) XMHW_TM(48, 48) else XMHW_TM(48, 32) break;
+        case 8: if (big) XMHW_TM(8, 48) else if (n30) XMHW_TM(8, 30) else XMHW_TM(8, 32) break;
+        case 16: if (big) XMHW_TM(16, 48) else if (n30) XMHW_TM(16, 30) else XMHW_TM(16, 32) break;
+        case 24: if (big) XMHW_TM(24, 48) else if (n30) XMHW_TM(24, 30) else XMHW_TM(24, 32) break;
+        case 36: if (big) XMHW_TM(36, 48) else if (n30) XMHW_TM(36, 30) else XMHW_TM(36, 32) break;
+        case 48: if (big) XMHW_TM(48, 48) else if (n30) XMHW_TM(48, 30) else XMHW_TM(48, 32) break;
         default: return XMHW_E_PLAN;
       }
 #undef XMHW_TM
@@ -1377,11 +1381,11 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
     }
   }
   switch (plan->kp) {
-    case 8: if (big) XMHW_SWEEP2(8, 48) else XMHW_SWEEP2(8, 32) break;
-    case 16: if (big) XMHW_SWEEP2(16, 48) else XMHW_SWEEP2(16, 32) break;
-    case 24: if (big) XMHW_SWEEP2(24, 48) else XMHW_SWEEP2(24, 32) break;
-    case 36: if (big) XMHW_SWEEP2(36, 48) else XMHW_SWEEP2(36, 32) break;
-    case 48: if (big) XMHW_SWEEP2(48, 48) else XMHW_SWEEP2(48, 32) break;
+    case 8: if (big) XMHW_SWEEP2(8, 48) else if (n30) XMHW_SWEEP2(8, 30) else XMHW_SWEEP2(8, 32) break;
+    case 16: if (big) XMHW_SWEEP2(16, 48) else if (n30) XMHW_SWEEP2(16, 30) else XMHW_SWEEP2(16, 32) break;
+    case 24: if (big) XMHW_SWEEP2(24, 48) else if (n30) XMHW_SWEEP2(24, 30) else XMHW_SWEEP2(24, 32) break;
+    case 36: if (big) XMHW_SWEEP2(36, 48) else if (n30) XMHW_SWEEP2(36, 30) else XMHW_SWEEP2(36, 32) break;
+    case 48: if (big) XMHW_SWEEP2(48, 48) else if (n30) XMHW_SWEEP2(48, 30) else XMHW_SWEEP2(48, 32) break;
     default: return XMHW_E_PLAN;
   }
 #undef XMHW_SWEEP2

@@ -78,6 +78,25 @@ template <> XMHW_HD void bitonic_valley_desc<36>(uint32_t (&k)[36]) { XMHW_BITON
 template <> XMHW_HD void bitonic_valley_desc<48>(uint32_t (&k)[48]) { XMHW_BITONIC_48 }
 
 
+// maximum of t[0..N): a balanced tree instead of a serial chain (depth log N; ptxas pairs the levels into
+// 3-input VIMNMX3), t is clobbered
+template <int W, int N> XMHW_HD uint32_t umax_tree_w(uint32_t (&t)[N]) {      // the first W entries of t are live
+  if constexpr (W <= 1) {
+    return t[0];
+  } else {
+    constexpr int W3 = (W + 2) / 3;
+#pragma unroll
+    for (int i = 0; i < W3; ++i) {
+      uint32_t m = t[3 * i];
+      if (3 * i + 1 < W) m = umax32(m, t[3 * i + 1]);
+      if (3 * i + 2 < W) m = umax32(m, t[3 * i + 2]);
+      t[i] = m;
+    }
+    return umax_tree_w<W3, N>(t);
+  }
+}
+template <int N> XMHW_HD uint32_t umax_tree(uint32_t (&t)[N]) { return umax_tree_w<N, N>(t); }
+
 // A (KP keys, descending) := the KP largest of A u L (N keys, descending), descending.
 // max(A[i], L[KP-1-i]) is the top KP as a valley; the pruned bitonic merger sorts it.
 template <int KP, int N>
@@ -242,7 +261,7 @@ struct TopkSweeperP {
       for (int i = 0; i < MAXN; ++i) {
         const float v = pv[i];
         const uint32_t b = f32_bits(v);
-        const bool valid = (i < size) && ok && (v == v);
+        const bool valid = (i < size) && (v == v);      // lanes past the grid edge compute on cell 0: never stored
         k[i] = valid ? (b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u)) : 0u;
         if (valid) { ++len; sum = sum + (double)v; }
       }
@@ -430,29 +449,26 @@ struct TopkSweeperP {
     while (true) {
       const int kk = env.max_all(todo);
       if (kk == 0) break;
-      uint32_t q1 = 0u, q2 = 0u;
-      uint32_t am1 = 0xffffffffu, am2 = 0u;                    // A[i-1], A[i-2]
+      // t1[i] = min(A[i-1], S[kk-i]) (A[-1] = +inf), t2[i] = min(A[i-2], S[kk-i]): R(kk) = max t1, R(kk-1) = max t2
+      uint32_t t1[KP + 1], t2[KP + 1];
       if (Pool::kGather) {                                     // all front rows first (one wait), then the scan
         uint32_t sv[KP + 1];
         pool.template ld_front<KP + 1>(front_base, kk, sv);
 #pragma unroll
         for (int i = 0; i <= KP; ++i) {
-          q1 = umax32(q1, umin32(am1, sv[i]));
-          if (i >= 1) q2 = umax32(q2, umin32(am2, sv[i]));
-          am2 = am1;
-          am1 = i < KP ? A[i] : 0u;
+          t1[i] = i >= 1 ? umin32(A[i - 1], sv[i]) : sv[i];
+          t2[i] = i >= 2 ? umin32(A[i - 2], sv[i]) : (i == 1 ? sv[i] : 0u);
         }
       } else {
 #pragma unroll
         for (int i = 0; i <= KP; ++i) {
           const int row = kk - i > 0 ? kk - i : 0;             // warp-uniform; past the guard: dominated terms
           const uint32_t sv = pool.ld(front_base + row);
-          q1 = umax32(q1, umin32(am1, sv));
-          if (i >= 1) q2 = umax32(q2, umin32(am2, sv));
-          am2 = am1;
-          am1 = i < KP ? A[i] : 0u;
+          t1[i] = i >= 1 ? umin32(A[i - 1], sv) : sv;
+          t2[i] = i >= 2 ? umin32(A[i - 2], sv) : (i == 1 ? sv : 0u);
         }
       }
+      const uint32_t q1 = umax_tree<KP + 1>(t1), q2 = umax_tree<KP + 1>(t2);
       if (todo == kk) { r1 = q1; r2 = q2; todo = 0; }
     }
     if (live) {
