@@ -352,7 +352,7 @@ def run_ours(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.isfile(tp):
-        traffic = json.load(open(tp)).get(args.workload, {}).get("clim_sweep_dram_bytes")
+        traffic = json.load(open(tp)).get(args.workload, {}).get(sweep_name, {}).get("dram_bytes")
     b_alg = nloc * T * 4 + nocean_loc * 2 * ndoy * 8 + nocean_loc * 4 + nev * 180
     ms_rank = ms / args.steps
 

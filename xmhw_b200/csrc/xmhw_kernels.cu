@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(32, MINB) clim_sweep_kernel(
 // K1'  two-stack top-K climatology sweep (xmhw_topk.h): one warp = 32 cells, straight-line
 // sorting / merging networks per doy, the unit slots of the window in shared memory.
 // ---------------------------------------------------------------------------
-// WPB warps per block: with WPB > 1 the warps of a block step in lockstep (one barrier per doy), so
-// the SM's four resident warps stream the SAME ~30 KB of straight-line code through the 32 KB
-// instruction cache instead of four different positions of it.
+// WPB warps per block; `sync_every` > 0 makes them advance in lockstep (a barrier every so many doys) so that
+// they stream the same straight-line code through the instruction cache -- a gain while the step carried 70
+// register copies per job, a loss since (launcher: default 0).
 // 32-cell group of warp `w` of the grid: order[w] when the caller passed a processing order (land-looking groups
 // last, so that the warps of one lockstep block have the same amount of work), w otherwise; past the grid: none
 __device__ __forceinline__ int64_t sweep2_group(const int32_t* order, int64_t w, int64_t ngrid) {
@@ -94,7 +94,7 @@ __device__ __forceinline__ int64_t sweep2_group(const int32_t* order, int64_t w,
 template <int KP, int MAXN, int WPB, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB) clim_sweep2_kernel(
     const __grid_constant__ ClimPlan2 p, const float* __restrict__ ts, int64_t ngrid, double* __restrict__ thr,
-    double* __restrict__ seas, int32_t* __restrict__ nempty, const int32_t* __restrict__ order) {
+    double* __restrict__ seas, int32_t* __restrict__ nempty, const int32_t* __restrict__ order, int sync_every) {
   extern __shared__ uint32_t pool[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t cell = sweep2_group(order, (int64_t)blockIdx.x * WPB + wib, ngrid) * 32 + lane;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) clim_sweep2_kernel(
       thr[(int64_t)row * ngrid + cell] = a;
       seas[(int64_t)row * ngrid + cell] = b;
     }
-    if (WPB > 1) __syncthreads();
+    if (WPB > 1 && sync_every > 0 && (s + 1) % sync_every == 0) __syncthreads();
   }
   if (ok) nempty[cell] = sw.nzero;
 }
@@ -1342,7 +1342,7 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
     e = cudaFuncSetAttribute(clim_sweep2_kernel<K, N, W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return (int)e;                                                                             \
     clim_sweep2_kernel<K, N, W, 1><<<(unsigned)((ncg + W - 1) / W), 32 * W, smem, (cudaStream_t)stream>>>(           \
-        p, ts, ngrid, thresh_raw, seas_raw, nempty, group_order);                                                    \
+        p, ts, ngrid, thresh_raw, seas_raw, nempty, group_order, sync_every);                                        \
   }
 #define XMHW_SWEEP2(K, N)                                                                                            \
   { if (wpb == 4) XMHW_SWEEP2_W(K, N, 4) else if (wpb == 2) XMHW_SWEEP2_W(K, N, 2) else XMHW_SWEEP2_W(K, N, 1) }
@@ -1351,10 +1351,14 @@ int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_c
   // Tensor-memory kernel (8 warps per SM, the slots that do not fit shared memory live in TMEM): taken when
   // fewer than 8 warps of the shared-memory kernel fit one SM and the slots split.  XMHW_B200_SWEEP2_TMEM = 0 / 1
   // forces it off / on (development knob, read per call).
+  // The warps of a block may advance in lockstep (a barrier every `sync_every` doys) so that they stream the same
+  // code through the instruction cache.  Measured (profiles/kernel_ms_r02r_sweep2_tmem.txt): since the step
+  // lost its register copies the kernels run best WITHOUT the barrier (0); XMHW_B200_SWEEP2_SYNC = n sets it.
+  const int sync_every = getenv("XMHW_B200_SWEEP2_SYNC") ? atoi(getenv("XMHW_B200_SWEEP2_SYNC")) : 0;
   const int tm_env = getenv("XMHW_B200_SWEEP2_TMEM") ? atoi(getenv("XMHW_B200_SWEEP2_TMEM")) : -1;
   const bool tm_on = tm_env == 1 || (tm_env < 0 && fit < TM_WARPS);
   if (tm_on) {
-    const int tm_sync = getenv("XMHW_B200_SWEEP2_TM_SYNC") ? atoi(getenv("XMHW_B200_SWEEP2_TM_SYNC")) : 4;   // development knob
+    const int tm_sync = sync_every;
     const int max_smem_slots = (int)((227 * 1024 - 1024) / ((size_t)TM_WARPS * plan->slot_rows * 128));
     const int min_smem_slots = plan->nslots - TM_COLS_PER_WARP / plan->slot_rows;
     if (min_smem_slots <= max_smem_slots) {
