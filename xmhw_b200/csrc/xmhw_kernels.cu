@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) clim_sweep2_kernel(
   const bool ok = cell < ngrid;
   const float* col = ts + (ok ? cell : 0);
   WarpEnv env;
-  TopkSweeper<WarpEnv, KP, MAXN> sw(env, p, pool + (size_t)wib * p.nslots * p.slot_rows * 32, lane, col, ngrid, ok);
+  TopkSweeper<WarpEnv, KP, MAXN> sw(env, p, pool + (size_t)wib * p.nslots * p.slot_rows * 32, lane, col, ngrid, ok,
+                                    -wib * p.nslots * p.slot_rows);       // rows below this warp's pool: the earlier warps'
   for (int s = -1; s < p.nsteps; ++s) {          // s = -1: initial fill of the first window
     double a, b;
     int row;
@@ -156,6 +157,7 @@ struct SplitPool {
   uint32_t* p;           // shared-memory row 0, this lane's word
   int split;
   uint32_t tcol;         // TMEM address (lane quarter << 16 | column) of row `split`
+  int min_srow, min_tcol;     // lowest readable shared-memory row / TMEM column relative to this warp's (<= 0)
   static constexpr bool kGather = true;
   __device__ __forceinline__ uint32_t ld(int row) const {
     if (row < split) return p[row * 32];
@@ -210,14 +212,27 @@ struct SplitPool {
         if (i < size) tm_st1(tcol + (uint32_t)(row0 - split + i), &k[i]);
     }
   }
+  // see PlainPool::ld_front: rows past the guard are read unclamped when that memory exists
   template <int N> __device__ __forceinline__ void ld_front(int base, int kk, uint32_t (&sv)[N]) const {
     if (base < split) {
+      if (base + kk - (N - 1) >= min_srow) {
+        const uint32_t* const r = p + (base + kk) * 32;
 #pragma unroll
-      for (int i = 0; i < N; ++i) sv[i] = p[(base + (kk - i > 0 ? kk - i : 0)) * 32];
+        for (int i = 0; i < N; ++i) sv[i] = *(r - i * 32);
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) sv[i] = p[(base + (kk - i > 0 ? kk - i : 0)) * 32];
+      }
     } else {
       uint32_t a[N];
+      const int c0 = base - split + kk;
+      if (c0 - (N - 1) >= min_tcol) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) a[i] = tcol + (uint32_t)(base - split + (kk - i > 0 ? kk - i : 0));
+        for (int i = 0; i < N; ++i) a[i] = tcol + (uint32_t)(c0 - i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = tcol + (uint32_t)(base - split + (kk - i > 0 ? kk - i : 0));
+      }
       tm_gather<N>(a, sv);
     }
   }
@@ -250,6 +265,8 @@ __global__ void __launch_bounds__(32 * TM_WARPS, 1) clim_sweep2_tm_kernel(
   pl.p = pool + (size_t)wib * split * 32 + lane;
   pl.split = split;
   pl.tcol = tbase + ((uint32_t)((wib & 3) * 32) << 16) + (uint32_t)((wib >> 2) * TM_COLS_PER_WARP);
+  pl.min_srow = -wib * split;
+  pl.min_tcol = -(wib >> 2) * TM_COLS_PER_WARP;
   WarpEnv env;
   {
     TopkSweeperP<WarpEnv, SplitPool, KP, MAXN> sw(env, p, pl, col, ngrid, ok);

@@ -115,8 +115,9 @@ XMHW_HD void merge_topk(uint32_t (&A)[KP], const uint32_t (&L)[N]) {
 // upper rows are columns of tensor memory (tcgen05.ld / st, 32 lanes x 32 bit shape).
 struct PlainPool {
   uint32_t* p;           // row 0, this lane's word
+  int min_row;           // lowest row (<= 0) that is still readable memory: the rows of the block's earlier warps
   static constexpr bool kGather = false;      // query: load each front row right where it is used
-  XMHW_HD PlainPool(uint32_t* base, int lane) : p(base + lane) {}
+  XMHW_HD PlainPool(uint32_t* base, int lane, int lowest = 0) : p(base + lane), min_row(lowest) {}
   XMHW_HD uint32_t ld(int row) const { return p[row * 32]; }
   XMHW_HD void st(int row, uint32_t v) const { p[row * 32] = v; }
   template <int N> XMHW_HD void ld_block(int row0, uint32_t (&k)[N]) const {
@@ -140,10 +141,19 @@ struct PlainPool {
     for (int i = 0; i < N; ++i)
       if (i < size) r[i * 32] = k[i];
   }
-  // front rows of the query: sv[i] = row max(kk - i, 0) of the slot at `base`
+  // Front rows of the query: sv[i] = row kk - i of the slot at `base` for i <= kk.  The entries past the
+  // guard row (i > kk) only enter terms that are dominated whatever their value (min(A[i-1], x) <= A[i-1] <=
+  // A[kk-1], the i = kk term), so when the rows below the slot are readable memory they are read as they
+  // come (one address per row instead of compare + select + add); else they are clamped onto the guard row.
   template <int N> XMHW_HD void ld_front(int base, int kk, uint32_t (&sv)[N]) const {
+    if (base + kk - (N - 1) >= min_row) {
+      const uint32_t* const r = p + (base + kk) * 32;
 #pragma unroll
-    for (int i = 0; i < N; ++i) sv[i] = p[(base + (kk - i > 0 ? kk - i : 0)) * 32];
+      for (int i = 0; i < N; ++i) sv[i] = *(r - i * 32);
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) sv[i] = p[(base + (kk - i > 0 ? kk - i : 0)) * 32];
+    }
   }
 };
 
@@ -451,21 +461,13 @@ struct TopkSweeperP {
       if (kk == 0) break;
       // t1[i] = min(A[i-1], S[kk-i]) (A[-1] = +inf), t2[i] = min(A[i-2], S[kk-i]): R(kk) = max t1, R(kk-1) = max t2
       uint32_t t1[KP + 1], t2[KP + 1];
-      if (Pool::kGather) {                                     // all front rows first (one wait), then the scan
+      {
         uint32_t sv[KP + 1];
         pool.template ld_front<KP + 1>(front_base, kk, sv);
 #pragma unroll
         for (int i = 0; i <= KP; ++i) {
           t1[i] = i >= 1 ? umin32(A[i - 1], sv[i]) : sv[i];
           t2[i] = i >= 2 ? umin32(A[i - 2], sv[i]) : (i == 1 ? sv[i] : 0u);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i <= KP; ++i) {
-          const int row = kk - i > 0 ? kk - i : 0;             // warp-uniform; past the guard: dominated terms
-          const uint32_t sv = pool.ld(front_base + row);
-          t1[i] = i >= 1 ? umin32(A[i - 1], sv) : sv;
-          t2[i] = i >= 2 ? umin32(A[i - 2], sv) : (i == 1 ? sv : 0u);
         }
       }
       const uint32_t q1 = umax_tree<KP + 1>(t1), q2 = umax_tree<KP + 1>(t2);
@@ -485,8 +487,9 @@ struct TopkSweeperP {
 // the sweep on a plain (shared / host) memory pool
 template <class Env, int KP, int MAXN>
 struct TopkSweeper : TopkSweeperP<Env, PlainPool, KP, MAXN> {
-  XMHW_HD TopkSweeper(const Env& e, const ClimPlan2& pl, uint32_t* po, int ln, const float* c, int64_t ng, bool k)
-      : TopkSweeperP<Env, PlainPool, KP, MAXN>(e, pl, PlainPool(po, ln), c, ng, k) {}
+  XMHW_HD TopkSweeper(const Env& e, const ClimPlan2& pl, uint32_t* po, int ln, const float* c, int64_t ng, bool k,
+                      int lowest_row = 0)
+      : TopkSweeperP<Env, PlainPool, KP, MAXN>(e, pl, PlainPool(po, ln, lowest_row), c, ng, k) {}
 };
 
 // ---------------------------------------------------------------------------
