@@ -146,6 +146,10 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
  * 8 warps per SM; XMHW_B200_SWEEP2_TMEM=0 in the environment turns that off.                           */
 int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan2* plan,
                          double* thresh_raw, double* seas_raw, int32_t* nempty, const int32_t* group_order, void* stream);
+/* A processing order for xmhw_clim_sweep2_f32: the 32-cell groups that hold data in at least one of three
+ * probe rows (first, middle, last time step) first, the all-NaN ("land") groups last, each half in grid
+ * order.  flags: workspace of ceil(ngrid/32) bytes; order: ceil(ngrid/32) i32.                          */
+int xmhw_group_order_f32(const float* ts, int64_t T, int64_t ngrid, uint8_t* flags, int32_t* order, void* stream);
 int xmhw_clim_direct_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* rows, int32_t nrows, int32_t kp,
                          double q, double* thresh_row, double* seas_row, int32_t* nempty, void* stream);
 

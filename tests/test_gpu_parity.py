@@ -519,3 +519,22 @@ def test_intermediate_dataset(core):
         else:
             assert np.array_equal(np.isnan(g), np.isnan(exp[k])), k
             assert np.allclose(g, exp[k], rtol=0, atol=1e-12, equal_nan=True), k
+
+
+def test_group_order_is_stable_land_last_permutation(core):
+    """xmhw_group_order_f32: the 32-cell groups with data in a probe row first, the all-NaN groups last, both in
+    grid order (ragged last group included) -- compared with the same rule in numpy."""
+    from xmhw_b200 import synth
+    time = synth.daily_time(2001, 2003)
+    for ncell, land_shape in ((5000, (50, 100)), (1024 * 33 + 7, None)):
+        land = synth.land_mask(*land_shape).ravel() if land_shape else (np.arange(ncell) // 97 % 3 == 0).astype(np.uint8)
+        ts_h = synth.synth_sst(len(time), ncell, synth.season_table(time), land=land[:ncell], nan_ppm=2000)
+        ts_h[0, 64:96] = np.nan                     # a data gap in one probe row only: still a group with data
+        ts = torch.from_numpy(ts_h).cuda()
+        order = core._group_order(ts).cpu().numpy()
+        T = len(time)
+        probe = np.isnan(ts_h[0]) & np.isnan(ts_h[T // 2]) & np.isnan(ts_h[T - 1])
+        ncg = (ncell + 31) // 32
+        probe = np.concatenate([probe, np.ones(ncg * 32 - ncell, bool)]).reshape(ncg, 32).all(1)
+        exp = np.concatenate([np.flatnonzero(~probe), np.flatnonzero(probe)])
+        assert probe.any() and (~probe).any() and np.array_equal(order, exp)

@@ -73,6 +73,7 @@ _SIGNATURES = {
     "xmhw_strerror": (C.c_char_p, [C.c_int]),
     "xmhw_clim_sweep_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlanStruct),
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xmhw_group_order_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_clim_sweep2_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ClimPlan2Struct),
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xmhw_clim_direct_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,

@@ -1107,6 +1107,67 @@ __global__ void __launch_bounds__(256) count_valid_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------
+// processing order of the 32-cell groups for the top-K sweep (xmhw_clim_sweep2_f32 group_order): groups whose 32
+// cells are all NaN in three probe rows (first, middle, last time step: land, as far as a probe can tell) go
+// last, both halves in grid order -- a stable partition.  Any permutation is correct; this one makes the
+// blocks of the sweep homogeneous at the cost of three row reads.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) group_flags_kernel(const float* __restrict__ ts, int64_t T, int64_t ngrid,
+                                                          uint8_t* __restrict__ flags) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // one warp = one group
+  const int lane = threadIdx.x & 31;
+  const int64_t ncg = (ngrid + 31) / 32;
+  if (g >= ncg) return;
+  const int64_t cell = g * 32 + lane;
+  bool valid = false;
+  if (cell < ngrid) {
+    const float a = __ldg(ts + cell), b = __ldg(ts + (T / 2) * ngrid + cell), c = __ldg(ts + (T - 1) * ngrid + cell);
+    valid = a == a || b == b || c == c;
+  }
+  const bool any = __any_sync(0xffffffffu, valid);
+  if (lane == 0) flags[g] = any ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(1024) group_order_kernel(const uint8_t* __restrict__ flags, int64_t ncg,
+                                                           int32_t* __restrict__ order) {
+  // ONE block: count the groups with data, then assign positions chunk by chunk (ballot ranks + warp totals)
+  __shared__ int wtot[2][32];
+  __shared__ int base[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int cnt = 0;
+  for (int64_t g = tid; g < ncg; g += 1024) cnt += flags[g] == 0;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) wtot[0][warp] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    int n = 0;
+    for (int w = 0; w < 32; ++w) n += wtot[0][w];
+    base[0] = 0; base[1] = n;
+  }
+  __syncthreads();
+  for (int64_t g0 = 0; g0 < ncg; g0 += 1024) {
+    const int64_t g = g0 + tid;
+    const int f = g < ncg ? (int)flags[g] : 2;                 // 0 data, 1 land-looking, 2 past the end
+    const unsigned b0 = __ballot_sync(0xffffffffu, f == 0), b1 = __ballot_sync(0xffffffffu, f == 1);
+    const unsigned lt = (1u << lane) - 1u;
+    if (lane == 0) { wtot[0][warp] = __popc(b0); wtot[1][warp] = __popc(b1); }
+    __syncthreads();
+    if (f < 2) {
+      int off = 0;
+      for (int w = 0; w < warp; ++w) off += wtot[f][w];
+      order[base[f] + off + __popc((f == 0 ? b0 : b1) & lt)] = (int32_t)g;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int n0 = 0, n1 = 0;
+      for (int w = 0; w < 32; ++w) { n0 += wtot[0][w]; n1 += wtot[1][w]; }
+      base[0] += n0; base[1] += n1;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
 // intermediate=True (identify.py:404-411): per-timestep fields of mhw_df (features.py:22-69)
 // ---------------------------------------------------------------------------
 __global__ void event_labels_kernel(const int32_t* __restrict__ ei, int64_t nev, int64_t cap, int64_t ngrid,
@@ -1704,6 +1765,15 @@ int xmhw_count_valid_f32(const float* ts, int64_t T, int64_t ngrid, int32_t* nva
   ny = ny < 1 ? 1 : (ny > 64 ? 64 : ny);
   const int tchunk = (int)((T + ny - 1) / ny);
   count_valid_kernel<<<dim3((unsigned)nbx, (unsigned)ny), nt, 0, st>>>(ts, T, ngrid, tchunk, nvalid);
+  return cuda_status();
+}
+
+int xmhw_group_order_f32(const float* ts, int64_t T, int64_t ngrid, uint8_t* flags, int32_t* order, void* stream) {
+  if (!ts || !flags || !order || T <= 0 || ngrid <= 0 || ngrid > 0x3fffffffll * 32) return XMHW_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ncg = (ngrid + 31) / 32;
+  group_flags_kernel<<<(unsigned)((ncg * 32 + 255) / 256), 256, 0, st>>>(ts, T, ngrid, flags);
+  group_order_kernel<<<1, 1024, 0, st>>>(flags, ncg, order);
   return cuda_status();
 }
 
