@@ -130,10 +130,6 @@ def _group_order(ts):
     return order
 
 
-def _topk_warps_per_sm(host_plan):
-    return (227 * 1024) // (host_plan.pool_rows * 128 + 256)
-
-
 def sweep_mode():
     """XMHW_B200_SWEEP: "auto" (default, see TOPK_AUTO_MIN_WARPS), "topk" (the two-stack top-K sweep
     whenever the calendar fits) or "general" (always the sorted-list sweep of plan.py)."""
