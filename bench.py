@@ -347,6 +347,10 @@ def run_ours(args):
     peak, peak_src = hbm_peak()
     sweep_name = "xmhw_clim_sweep2_f32" if "xmhw_clim_sweep2_f32" in kernel_ms else "xmhw_clim_sweep_f32"
     sweep_ms = kernel_ms[sweep_name]
+    sweep_kernel = "clim_sweep_kernel"
+    if sweep_name.endswith("sweep2_f32"):
+        dp2 = core.device_plan2(doy, ndoy, tkw.get("windowHalfWidth", 5), tkw.get("pctile", 90) / 100.0, dev)
+        sweep_kernel = core.sweep2_kernel_name(dp2.host) if dp2 is not None else "clim_sweep2_kernel"
     sweep_bytes = nloc * T * 4 + nocean_loc * 2 * ndoy * 8
     ach = sweep_bytes / (sweep_ms * 1e-3) / 1e9
     traffic = None
@@ -430,7 +434,7 @@ def run_ours(args):
                 "result_checksum": {"events": int(sums["events"]), "table": "%016x" % sums["table"],
                                     "clim": "%016x" % sums["clim"]},
                 "e2e": e2e, "gpu_launches": launches,
-                "roofline": {"bound": "hbm", "kernel": "clim_sweep2_kernel" if sweep_name.endswith("sweep2_f32") else "clim_sweep_kernel",
+                "roofline": {"bound": "hbm", "kernel": sweep_kernel,
                              "achieved": ach, "peak": peak,
                              "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": sweep_bytes // len(chunks), "ms_per_launch": sweep_ms / len(chunks),

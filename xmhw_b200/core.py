@@ -118,6 +118,14 @@ def _topk_tmem_fits(host_plan):
     return host_plan.nslots - TM_COLS_PER_WARP // host_plan.slot_rows <= max_smem_slots
 
 
+def sweep2_kernel_name(host_plan):
+    """Which kernel xmhw_clim_sweep2_f32 launches for this plan (the launcher's rule, for reports)."""
+    import os
+    tm = int(os.environ.get("XMHW_B200_SWEEP2_TMEM", "-1"))
+    use_tm = (tm == 1 or (tm < 0 and _topk_warps_per_sm(host_plan) < TM_WARPS)) and _topk_tmem_fits(host_plan)
+    return "clim_sweep2_tm_kernel" if use_tm else "clim_sweep2_kernel"
+
+
 def _group_order(ts):
     """Processing order of the 32-cell groups for the top-K sweep (xmhw_group_order_f32): groups that look like
     land (all 32 cells NaN in three probe rows) last, so a block's warps carry equal work.  Any permutation is
