@@ -4,8 +4,9 @@
 // All kernels map one grid cell to one lane (32 adjacent cells per warp): the
 // reference layouts (time, cell) / (doy, cell) are then read and written as
 // contiguous 128 B / 256 B row segments with no transpose pass.  None of this
-// is a contraction, so tensor cores are not used; the kernels are HBM-, LSU- and
-// ALU-bound.  Compiled with --fmad=false so that the float64 expressions round
+// is a contraction, so no tensor-core instruction is issued; tensor MEMORY is
+// used as lane-private storage by the dominant kernel (clim_sweep2_tm_kernel).
+// The kernels are HBM-, LSU- and ALU-bound.  Compiled with --fmad=false so that the float64 expressions round
 // exactly like numpy/pandas (no FMA contraction).
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -1,4 +1,4 @@
-// Two-stack top-K climatology sweep (the fast path of xmhw_clim_sweep2_f32).
+// Two-stack top-K climatology sweep (xmhw_clim_sweep2_f32; the default sweep wherever its plan fits).
 //
 // Reference semantics: for every (cell, doy d) pool ts[t+k], doy[t] = d, |k| <= w, drop NaN,
 // take numpy's 'linear' quantile and the mean (xmhw/identify.py:184-209 window_roll,
@@ -17,9 +17,10 @@
 //                unit and all younger units of the front; built at a FLIP by walking the
 //                stashed units from the youngest to the oldest, merging into the (then free)
 //                accumulator and storing it over the unit's own stash;
-//   query        K-th largest of (front array S) u (A):  max_i min(A[i-1], S[K-1-i]) -- the
-//                array in registers is indexed statically, the one in shared memory per lane,
-//                so every lane may have its own K (NaN data) without any divergence.
+//   query        K-th largest of (front array S) u (A):  max_i min(A[i-1], S[K-1-i]); the warp loops over
+//                its DISTINCT ranks K (they differ between lanes only where samples are missing), so the
+//                slot rows are addressed warp-uniformly -- which lets a slot live in shared memory OR in
+//                tensor-memory columns (tcgen05.ld / st, see SplitPool in xmhw_kernels.cu).
 // Every step is the same straight-line code for all lanes (sorting / merging networks and a
 // fixed-length max-min scan): no data-dependent walk, no SIMT loss, no global key scratch.
 // One lane = one grid cell like every other kernel of this library.
