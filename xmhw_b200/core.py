@@ -358,8 +358,17 @@ def detect_arrays(ts, doy, ndoy, thresh, seas, minDuration=5, joinGaps=True, max
                                           _ptr(counts), _ptr(stage), stage_cap, _ptr(overflow), st)
         scratch = torch.empty(ngrid // 1024 + 2, dtype=torch.int64, device=dev)
         _call("xmhw_exclusive_scan_i32", _ptr(counts), ngrid, _ptr(offsets), _ptr(scratch), st)
-        tail = offsets[ngrid:].cpu()           # the one host sync: event total (sizes the table) + overflow flag
-        nev, overflowed = int(tail[0]), bool(int(tail[1]) & 0xffffffff)
+        # the one host sync: event total (sizes the table) + overflow flag.  The copy is asynchronous and the
+        # cell-major {thresh, seas} pairs (an event's consecutive days become one contiguous run; independent of
+        # the events) are enqueued BEHIND it, so the device keeps working while the host waits and launches
+        tail_h = torch.empty(2, dtype=torch.int64, pin_memory=True)
+        tail_h.copy_(offsets[ngrid:], non_blocking=True)
+        got_tail = torch.cuda.Event()
+        got_tail.record()
+        clim_cm = torch.empty((ngrid, ndoy, 2), dtype=torch.float64, device=dev)
+        _call("xmhw_clim_cellmajor_f64", _ptr(thresh), _ptr(seas), ndoy, ngrid, _ptr(clim_cm), st)
+        got_tail.synchronize()
+        nev, overflowed = int(tail_h[0]), bool(int(tail_h[1]) & 0xffffffff)
         offsets = offsets[:ngrid + 1]
         cap = max(nev, 1)
         ev_i32 = torch.empty((EI_COUNT, cap), dtype=torch.int32, device=dev)
@@ -372,9 +381,6 @@ def detect_arrays(ts, doy, ndoy, thresh, seas, minDuration=5, joinGaps=True, max
                 _call("xmhw_events_gather", _ptr(stage), stage_cap, _ptr(counts), _ptr(offsets), ngrid, cap,
                                              _ptr(ev_i32), st)
             del stage
-            # cell-major {thresh, seas} pairs: an event's consecutive days become one contiguous run
-            clim_cm = torch.empty((ngrid, ndoy, 2), dtype=torch.float64, device=dev)
-            _call("xmhw_clim_cellmajor_f64", _ptr(thresh), _ptr(seas), ndoy, ngrid, _ptr(clim_cm), st)
             _call("xmhw_event_stats_cm_f32", _ptr(ts), T, ngrid, _ptr(doy32), ndoy, _ptr(clim_cm), nev, cap,
                                               _ptr(ev_i32), _ptr(ev_f64), st)
     return EventTable(ev_i32, ev_f64, nev, offsets, nvalid, T, ngrid)
