@@ -274,7 +274,8 @@ struct TopkSweeperP {
         const uint32_t b = f32_bits(v);
         const bool valid = (i < size) && (v == v);      // lanes past the grid edge compute on cell 0: never stored
         k[i] = valid ? (b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u)) : 0u;
-        if (valid) { ++len; sum = sum + (double)v; }
+        len += valid ? 1 : 0;
+        sum = sum + (double)(valid ? v : 0.0f);        // an invalid sample adds +0.0f (exact): one f32 select, no f64 selects
       }
       if ((nx0 >> 24) & 63u) prefetch(nx0, nx1);              // pv is free again: the next atom's loads go out now
       const bool acc = env.any(len > 0);
