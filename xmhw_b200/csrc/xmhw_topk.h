@@ -266,17 +266,25 @@ struct TopkSweeperP {
       const int slot_base = (int)((d1 >> 5) & 31u) * p.slot_rows;
       const int srow = slot_base + 1 + (int)((d1 >> 10) & 127u);
       uint32_t k[MAXN];
-      int len = 0;
-      double sum = 0.0;
+      // XMHW_PUSH_SUMS interleaved partial counts / f64 sums (1 = one sequential chain).  Measured on B200 (global
+      // grid, same box): 1 chain 34.8 ms, 2 chains 38.1 ms, 3 chains 37.8 ms -- ptxas needs 10 more registers and
+      // schedules the conversion worse; the sequential chain stays.
+      int len3[3] = {0, 0, 0};
+      double sum3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
       for (int i = 0; i < MAXN; ++i) {
         const float v = pv[i];
         const uint32_t b = f32_bits(v);
         const bool valid = (i < size) && (v == v);      // lanes past the grid edge compute on cell 0: never stored
         k[i] = valid ? (b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u)) : 0u;
-        len += valid ? 1 : 0;
-        sum = sum + (double)(valid ? v : 0.0f);        // an invalid sample adds +0.0f (exact): one f32 select, no f64 selects
+#ifndef XMHW_PUSH_SUMS
+#define XMHW_PUSH_SUMS 1
+#endif
+        len3[i % XMHW_PUSH_SUMS] += valid ? 1 : 0;
+        sum3[i % XMHW_PUSH_SUMS] = sum3[i % XMHW_PUSH_SUMS] + (double)(valid ? v : 0.0f);   // an invalid sample adds +0.0f (exact): one f32 select
       }
+      const int len = (len3[0] + len3[1]) + len3[2];
+      const double sum = (sum3[0] + sum3[1]) + sum3[2];
       if ((nx0 >> 24) & 63u) prefetch(nx0, nx1);              // pv is free again: the next atom's loads go out now
       const bool acc = env.any(len > 0);
       if (acc) sort_desc<MAXN>(k);
