@@ -81,7 +81,8 @@ def static_config(name, wl, T, nocean, ngrid):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    """Samples the SM clock and the throttle reasons while the timed region runs (NVML every 20 ms, else
+    nvidia-smi every 200 ms)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -91,6 +92,8 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], False
 
     def run(self):
+        if self._run_nvml():
+            return
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -99,6 +102,32 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             time.sleep(0.2)
+
+    def _run_nvml(self):
+        """The same fields through NVML (nvidia_ml_py), every 20 ms: an nvidia-smi process per sample takes
+        ~150 ms, too coarse for a timed region of a few hundred ms.  False when NVML is not usable."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            get_reasons(h)
+        except Exception:
+            return False
+        bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))      # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        while not self.stop_flag:
+            try:
+                r = int(get_reasons(h))
+                row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "0", "", "", "", ""]
+                for bit, col in bits:
+                    row[col] = "Active" if r & bit else "Not Active"
+                self.rows.append(row)
+            except Exception:
+                pass
+            time.sleep(0.02)
+        return True
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
