@@ -254,3 +254,23 @@ def test_save_zarr_compressed_roundtrip(tmp_path):
     assert np.array_equal(b2["index_start"].values, ev["index_start"].values)
     assert np.array_equal(b2["duration_moderate"].values, ev["duration_moderate"].values)
     assert b2.attrs["xmhw_parameters"].startswith("MHW detected") and b2.coord_attrs["row"]["long_name"] == "event row"
+
+
+def test_sweep_selection_rule_matches_the_launcher():
+    """core's "auto" rule (which sweep, which kernel) for the calendars of the bench workloads: host logic only.
+    The numbers mirror xmhw_clim_sweep2_f32's launcher (8 warps per SM: shared memory alone, or shared +
+    tensor memory when the unit slots split)."""
+    from xmhw_b200 import core, plan2
+    tm = synth.daily_time(1982, 2011)
+    doy = synth.doy366(tm)
+    hp = plan2.build_clim_plan2(doy, 366, 5, 0.9)                     # config 3: 11 slots x 40 rows = 55 KB per warp
+    assert hp.kp == 36 and core._topk_warps_per_sm(hp) == 4 and core._topk_tmem_fits(hp)
+    assert core.sweep2_kernel_name(hp) == "clim_sweep2_tm_kernel"
+    hp2 = plan2.build_clim_plan2(doy, 366, 2, 0.9)                    # narrow window: 8 warps fit shared memory
+    assert core._topk_warps_per_sm(hp2) >= 8 and core.sweep2_kernel_name(hp2) == "clim_sweep2_kernel"
+    tm40 = synth.daily_time(1982, 2021)
+    hp40 = plan2.build_clim_plan2(synth.doy366(tm40), 366, 5, 0.9)    # 40-year lists: 48-key arrays, 52-row slots
+    assert hp40 is None or (core._topk_warps_per_sm(hp40) < 8 and not core._topk_tmem_fits(hp40))   # -> general sweep
+    pent = np.tile(np.arange(1, 74), 30)
+    hpp = plan2.build_clim_plan2(pent, 73, 5, 0.9)
+    assert hpp is not None and (core._topk_warps_per_sm(hpp) >= 8 or core._topk_tmem_fits(hpp))
