@@ -138,17 +138,20 @@ int xmhw_clim_sweep_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_cl
  * The few doys the plan excludes (doy 60 of the 366-day calendar: its window holds leap years
  * only) are computed by xmhw_clim_direct_f32 from their row list: rows [nrows] i32 time indices,
  * thresh_row / seas_row = that doy's row of the raw arrays, nempty += 1 where it has no sample.
- * group_order: NULL, or a device permutation [ceil(ngrid/32)] i32 of the 32-cell groups = the order the
- * warps take them in (results do not depend on it).  The warps of a block advance in lockstep, so a block
+ * group_order: NULL, or a device array [ceil(ngrid/32) + 1] i32: a permutation of the 32-cell groups = the
+ * order the warps take them in (results do not depend on it), followed by one word the library uses as
+ * a work ticket (zeroed by the library; only the persistent launch mode of the tensor-memory kernel, a
+ * development option, draws groups from it).  The warps of a block advance in lockstep, so a block
  * whose groups have equal work wastes nothing: callers put the groups that look like land (all NaN in a
  * probe row) last.  When fewer than 8 warps' unit slots fit the shared memory of one SM (default window:
  * 4), the library launches the variant that keeps the remaining slots in tensor memory (tcgen05.ld / st),
  * 8 warps per SM; XMHW_B200_SWEEP2_TMEM=0 in the environment turns that off.                           */
 int xmhw_clim_sweep2_f32(const float* ts, int64_t T, int64_t ngrid, const xmhw_clim_plan2* plan,
-                         double* thresh_raw, double* seas_raw, int32_t* nempty, const int32_t* group_order, void* stream);
+                         double* thresh_raw, double* seas_raw, int32_t* nempty, int32_t* group_order, void* stream);
 /* A processing order for xmhw_clim_sweep2_f32: the 32-cell groups that hold data in at least one of three
  * probe rows (first, middle, last time step) first, the all-NaN ("land") groups last, each half in grid
- * order.  flags: workspace of ceil(ngrid/32) bytes; order: ceil(ngrid/32) i32.                          */
+ * order.  flags: workspace of ceil(ngrid/32) bytes; order: ceil(ngrid/32) + 1 i32 (the last word is the
+ * sweep's work ticket, see xmhw_clim_sweep2_f32).                                                         */
 int xmhw_group_order_f32(const float* ts, int64_t T, int64_t ngrid, uint8_t* flags, int32_t* order, void* stream);
 int xmhw_clim_direct_f32(const float* ts, int64_t T, int64_t ngrid, const int32_t* rows, int32_t nrows, int32_t kp,
                          double q, double* thresh_row, double* seas_row, int32_t* nempty, void* stream);

@@ -133,7 +133,7 @@ def _group_order(ts):
     T, ngrid = ts.shape
     ncg = (ngrid + 31) // 32
     flags = torch.empty(ncg, dtype=torch.uint8, device=ts.device)
-    order = torch.empty(ncg, dtype=torch.int32, device=ts.device)
+    order = torch.empty(ncg + 1, dtype=torch.int32, device=ts.device)       # + the sweep's work ticket
     _call("xmhw_group_order_f32", _ptr(ts), T, ngrid, _ptr(flags), _ptr(order), _stream())
     return order
 
