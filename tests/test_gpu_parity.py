@@ -150,15 +150,20 @@ def test_config4_skipna99_winter_blocks(core):
     assert_events_match(ev.to_numpy(), exp, _float_fields())
 
 
-@pytest.mark.parametrize("mode", ["topk", "topk_tmem", "general"])
+@pytest.mark.parametrize("mode", ["topk", "topk_tmem", "topk_tmem_persist", "topk_sync", "general"])
 def test_both_sweeps_forced(core, monkeypatch, mode):
     """The two climatology sweeps (two-stack top-K, csrc/xmhw_topk.h; general sorted lists, csrc/xmhw_lane.h)
     forced on the same 30-year series incl. land, NaNs and a ragged last warp: bit-equal to the oracle
     and therefore to each other (the default picks one by the top-K capacity)."""
     from xmhw_b200 import synth
     monkeypatch.setenv("XMHW_B200_SWEEP", mode.split("_")[0])
-    if mode == "topk_tmem":            # 8 warps per SM, the unit slots beyond shared memory in tensor memory
+    if mode.startswith("topk_tmem"):   # 8 warps per SM, the unit slots beyond shared memory in tensor memory
         monkeypatch.setenv("XMHW_B200_SWEEP2_TMEM", "1")
+    if mode == "topk_tmem_persist":    # one persistent block per SM, groups drawn from the ticket word
+        monkeypatch.setenv("XMHW_B200_SWEEP2_PERSIST", "1")
+    if mode == "topk_sync":            # shared-memory kernel with the lockstep barrier
+        monkeypatch.setenv("XMHW_B200_SWEEP2_TMEM", "0")
+        monkeypatch.setenv("XMHW_B200_SWEEP2_SYNC", "1")
     time = synth.daily_time(1982, 2011)
     doy = synth.doy366(time)
     ncell = 200
@@ -540,3 +545,25 @@ def test_group_order_is_stable_land_last_permutation(core):
         probe = np.concatenate([probe, np.ones(ncg * 32 - ncell, bool)]).reshape(ncg, 32).all(1)
         exp = np.concatenate([np.flatnonzero(~probe), np.flatnonzero(probe)])
         assert probe.any() and (~probe).any() and np.array_equal(order, exp)
+
+
+def test_tmem_persistent_launch_equals_block_launch(core, monkeypatch):
+    """The persistent launch mode of the tensor-memory sweep (one block per SM, warps draw groups from the ticket
+    word) on a grid large enough that every warp sweeps several groups: bit-equal raw climatologies to the default
+    launch (one block per 8 groups), which the other tests pin to the oracle."""
+    from xmhw_b200 import synth
+    time = synth.daily_time(1982, 2011)
+    doy = synth.doy366(time)
+    nlat, nlon = 60, 1000                              # 60 000 cells = 1 875 groups > 148 SMs x 8 warps
+    land = synth.land_mask(nlat, nlon, 0.3).ravel()
+    ts = core.synth_sst_device(len(time), nlat * nlon, synth.season_table(time), land=land, nan_ppm=2000)
+    monkeypatch.setenv("XMHW_B200_SWEEP", "topk")
+    monkeypatch.setenv("XMHW_B200_SWEEP2_TMEM", "1")
+    out = {}
+    for persist in ("0", "1"):
+        monkeypatch.setenv("XMHW_B200_SWEEP2_PERSIST", persist)
+        th, se, ne = core.threshold_arrays(ts, doy, 366, smoothPercentile=False, feb29=False, return_nempty=True)
+        out[persist] = (th.clone(), se.clone(), ne.clone())
+    for a, b in zip(out["0"], out["1"]):
+        assert torch.equal(torch.nan_to_num(a.double(), nan=-1.0), torch.nan_to_num(b.double(), nan=-1.0))
+    assert int(torch.isnan(out["0"][0]).all(0).sum()) > 1000      # land columns really are there
