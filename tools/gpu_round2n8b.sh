@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 20 --warmup 5 --no-cpu --no-e2e > gpurun_out/bench_r02x_n8.json 2> gpurun_out/bench_r02x_n8.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus 8 --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_r02x_n8.json 2> gpurun_out/bench_r02x_n8.err
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/bench_r02x_n8.json").readline())
