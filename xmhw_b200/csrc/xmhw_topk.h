@@ -361,8 +361,10 @@ struct TopkSweeperP {
     query(rec, psum, front_base, thresh, seas);
   }
 
-  // Pops, then the step's jobs (a flip's entries before or after the pushes), then the query.
-  // s = -1 is the initial fill: the atoms of the first window (plan.init).
+  // The first formulation of the step (one loop over pushes and flip entries through the shared job<>() body):
+  // pops, then the step's jobs (a flip's entries before or after the pushes), then the query; s = -1 is the
+  // initial fill (plan.init).  The kernels run step_phased() above; this one stays as the independent second
+  // implementation the host emulator checks against the oracle (tests/test_lane_emulator.py runs both).
   XMHW_HD void step(int s, double& thresh, double& seas, int& out_row) {
     const bool fill = s < 0;
     const uint32_t* const rec = p.rec[fill ? 0 : s];
